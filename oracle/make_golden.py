@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by EXECUTING the reference (test infrastructure).
+
+Run in the build container only (``/root/reference`` does not exist on the GPU
+box):  ``python oracle/make_golden.py``.  Hardware modules (``rtlsdr``,
+``hackrf``, ``sounddevice``) are mocked; numpy and scipy are the real ones, so
+the arrays stored here are what the reference's own classes return for the
+given seeded IQ.  Nothing from the reference is copied into the repo: its
+modules are imported (or, for the Qt-bound waterfall widget, three helper
+methods are compiled from its source file at run time) and only their outputs
+are written.
+
+Versions used are recorded in each fixture (``meta``).
+"""
+from __future__ import annotations
+
+import ast
+import json
+import os
+import sys
+import types
+from unittest.mock import MagicMock
+
+import numpy as np
+import scipy
+
+REF = os.environ.get("TDSA_REFERENCE_ROOT", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+OUT = os.path.join(ROOT, "tests", "golden")
+
+for _m in ("rtlsdr", "hackrf", "sounddevice"):
+    sys.modules[_m] = MagicMock()
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+
+from datasources.rtl_samples import RtlSamplesDataSource          # noqa: E402
+from datasources.hackrf_samples import HackrfSamplesDataSource    # noqa: E402
+from datasources.hackrf_sweep import HackRFSweepDataSource        # noqa: E402
+from utils.signal_processing import TraceAverager                 # noqa: E402
+from core.display_data_processor import DataProcessor             # noqa: E402
+from core.tare_state import TareState                             # noqa: E402
+
+from topdogspectrumanalyser_b200 import synth                     # noqa: E402
+
+META = json.dumps({"numpy": np.__version__, "scipy": scipy.__version__,
+                   "reference_commit": "1e46762", "generator": "oracle/make_golden.py"})
+
+
+class FakeSdr:
+    """Stands in for pyrtlsdr's RtlSdr: hands out complex128 frames like the real one."""
+
+    def __init__(self, frames, fs, fc):
+        self.frames, self.i, self.fs, self.fc = frames, 0, fs, fc
+
+    def get_sample_rate(self):
+        return self.fs
+
+    def get_center_freq(self):
+        return self.fc
+
+    def read_samples(self, n):
+        f = self.frames[self.i]
+        self.i += 1
+        assert len(f) == n
+        return f.astype(np.complex128)
+
+
+def run_rtl(iq, n, fs, fc, window="hanning", psd=False, avg=None):
+    src = RtlSamplesDataSource(int(fs), int(fc))
+    src.set_fft_size(n)
+    src.set_window_type(window)
+    src.set_psd_mode(psd)
+    if avg is not None:
+        src.set_averaging(*avg)
+    src.sdr = FakeSdr(iq, fs, fc)
+    src.running = True
+    rows, bins = [], None
+    for _ in range(len(iq)):
+        p, bins = src.get_power_levels()
+        rows.append(np.array(p, dtype=np.float64, copy=True))
+    return np.stack(rows), bins
+
+
+def run_hackrf(iq, n, fs, fc, psd=False, avg=None):
+    src = HackrfSamplesDataSource(int(fs), int(fc))
+    src.num_samples = n
+    src._allocate_fft_resources()
+    src.set_psd_mode(psd)
+    if avg is not None:
+        src.set_averaging(*avg)
+    src.running = True
+    rows = []
+    for f in iq:
+        chunk = np.zeros(65536, dtype=np.complex64)      # READ_CHUNK; newest tail is consumed
+        chunk[-n:] = f
+        src._sample_queue.put(chunk)
+        p, bins = src.get_power_levels()
+        rows.append(np.array(p, copy=True))
+    return np.stack(rows), bins, src._window.copy()
+
+
+def gen_rtl():
+    fs, fc = 2.048e6, 98e6
+    out = {"meta": META, "fs": fs, "fc": fc}
+    # config 1: N=1024, Hann, power mode, tone at +250 kHz
+    iq = synth.cfg1_frames(b=8, n=1024, fs=fs, seed=0)
+    db, bins = run_rtl(iq, 1024, fs, fc)
+    out.update(cfg1_iq=iq, cfg1_db=db, cfg1_bins=bins)
+    # every window x {power, psd} at N=4096 (cfg-2 style signal), 2 frames each
+    iq = synth.cfg2_frames(b=2, n=4096, seed=1)
+    out["w_iq"] = iq
+    for w in ("hanning", "hamming", "rectangle"):
+        for psd in (False, True):
+            db, bins = run_rtl(iq, 4096, fs, fc, window=w, psd=psd)
+            out[f"w_{w}_{'psd' if psd else 'power'}"] = db
+    out["w_bins"] = bins
+    # other sizes (Hann, power)
+    for n in (512, 2048, 8192):
+        iq = synth.cfg2_frames(b=2, n=n, seed=10 + n)
+        db, bins = run_rtl(iq, n, fs, fc)
+        out[f"n{n}_iq"], out[f"n{n}_db"] = iq, db
+    # known-answer frames at N=1024: impulse, zeros, DC, on-bin tone
+    n = 1024
+    kat = np.zeros((4, n), dtype=np.complex64)
+    kat[0, 0] = 1.0
+    kat[2, :] = 1.0
+    kat[3, :] = np.exp(2j * np.pi * 100 * np.arange(n) / n).astype(np.complex64)
+    db, _ = run_rtl(kat, n, fs, fc)
+    out.update(kat_iq=kat, kat_db=db)
+    # averaging sequences through the source (exp n=8, lin n=4), 12 frames, N=512
+    iq = synth.cfg2_frames(b=12, n=512, seed=21)
+    out["avg_iq"] = iq
+    out["avg_exp8_power"], _ = run_rtl(iq, 512, fs, fc, avg=("exp", 8))
+    out["avg_lin4_power"], _ = run_rtl(iq, 512, fs, fc, avg=("lin", 4))
+    out["avg_lin4_psd"], _ = run_rtl(iq, 512, fs, fc, psd=True, avg=("lin", 4))
+    np.savez_compressed(os.path.join(OUT, "rtl_chain.npz"), **out)
+
+
+def gen_hackrf():
+    fs, fc = 20e6, 2450e6
+    out = {"meta": META, "fs": fs, "fc": fc}
+    iq = synth.cfg2_frames(b=6, n=1024, seed=31)
+    iq = (iq + np.complex64(0.25 - 0.1j)).astype(np.complex64)     # a DC offset to remove
+    iq[3] = 0                                                      # silence -> hold last good
+    out["iq"] = iq
+    db, bins, win = run_hackrf(iq, 1024, fs, fc)
+    out.update(mag20=db, bins=bins, window=win)
+    out["psd"], _, _ = run_hackrf(iq, 1024, fs, fc, psd=True)
+    out["avg_exp4"], _, _ = run_hackrf(iq, 1024, fs, fc, avg=("exp", 4))
+    np.savez_compressed(os.path.join(OUT, "hackrf_chain.npz"), **out)
+
+
+def gen_averager():
+    rng = np.random.default_rng(41)
+    frames = rng.random((10, 64)) * 10.0
+    out = {"meta": META, "frames": frames}
+    for mode, n in (("off", 8), ("exp", 1), ("exp", 8), ("lin", 4), ("lin", 100)):
+        a = TraceAverager()
+        a.set_mode(mode, n)
+        out[f"{mode}{n}"] = np.stack([np.array(a.process(f), copy=True) for f in frames])
+    # float32 input is accumulated in float64 (signal_processing.py:47)
+    a = TraceAverager()
+    a.set_mode("exp", 4)
+    f32 = frames.astype(np.float32)
+    out["exp4_f32in"] = np.stack([np.array(a.process(f), copy=True) for f in f32])
+    np.savez_compressed(os.path.join(OUT, "trace_averager.npz"), **out)
+
+
+def gen_holds_tare_sweepavg():
+    rng = np.random.default_rng(51)
+    frames = rng.normal(-60.0, 8.0, (40, 96))
+    frames[0, 5] = np.nan
+    frames[3, 7] = np.nan
+    frames[4, 5] = np.nan
+    mw = types.SimpleNamespace(max_power_levels=None, min_power_levels=None, min_hold_enabled=True,
+                               status_label=MagicMock(), tare_active=False, baseline_power_levels=None)
+    dm = types.SimpleNamespace(max_peak_search_enabled=True, tare_state=TareState(),
+                               _update_tare_button_label=lambda *_: None, _clear_tare=lambda: None)
+    dp = DataProcessor(mw, dm)
+    mx, mn = [], []
+    for f in frames[:8]:
+        f = f.copy()
+        dp._update_max_hold(f)
+        dp._update_min_hold(f)
+        mx.append(mw.max_power_levels.copy())
+        mn.append(mw.min_power_levels.copy())
+    out = {"meta": META, "frames": frames, "max_hold": np.stack(mx), "min_hold": np.stack(mn)}
+    # tare: collect 32 frames, then subtract
+    clean = np.nan_to_num(frames, nan=-70.0)
+    dm.tare_state = TareState(collecting=True)
+    tared = [np.array(dp._apply_tare(f.copy()), copy=True) for f in clean]
+    out.update(tare_in=clean, tare_out=np.stack(tared), tare_baseline=mw.baseline_power_levels)
+    # sweep-domain averaging (display_data_processor.py:214-218) with the reference averager
+    dp._sweep_averager.set_mode("exp", 4)
+    sw = []
+    for f in clean[:10]:
+        linear = 10.0 ** (f / 10.0)
+        sw.append(10.0 * np.log10(np.maximum(dp._sweep_averager.process(linear), 1e-30)))
+    out["sweep_avg_exp4"] = np.stack(sw)
+    # top-5 peak finder on planted peaks (display_data_processor.py:432-471)
+    p = rng.normal(-90.0, 1.0, 512)
+    for i, v in ((40, -20.0), (200, -35.0), (207, -36.0), (333, -30.0), (450, -50.0), (500, -25.0)):
+        p[i] = v
+    fb = np.linspace(1e6, 2e6, 512)
+    out["peaks_power"], out["peaks_bins"] = p, fb
+    out["peaks"] = np.array(DataProcessor._find_top_peaks(fb, p), dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "trace_state.npz"), **out)
+
+
+def gen_stitch():
+    start, stop, bin_size = 2400_000_000, 2500_000_000, 100_000
+    src = HackRFSweepDataSource(start, stop, bin_size)
+    rng = np.random.default_rng(61)
+    # hackrf_sweep emits 5 MHz rows out of order (interleaved quarters); 20 MHz steps
+    rows, los, his = [], [], []
+    for step in range(5):
+        base = start + step * 20_000_000
+        for q in (0, 2, 1, 3):
+            lo = base + q * 5_000_000
+            los.append(lo)
+            his.append(lo + 5_000_000)
+            rows.append(rng.normal(-70.0, 5.0, 50).astype(np.float32))
+    def feed():
+        for r, lo, hi in zip(rows, los, his):
+            line = ", ".join(["2026-01-01", "00:00:00", str(lo), str(hi), "100000.00", "20"]
+                             + [f"{v:.2f}" for v in r])
+            src._parse(line)
+    feed()
+    first = src.get_data()          # still NaN: sweep not wrapped yet
+    feed()                          # wrap -> stitch of the first pass
+    full = src.get_data()
+    parsed = np.stack([np.array([float(f"{v:.2f}") for v in r], dtype=np.float32) for r in rows])
+    np.savez_compressed(os.path.join(OUT, "sweep_stitch.npz"), meta=META, start=start, stop=stop,
+                        bin_size=bin_size, rows=parsed, lo=np.array(los), hi=np.array(his),
+                        grid=src.frequency_grid, before_wrap=first, stitched=full)
+
+
+def gen_waterfall():
+    """Compile _init_buffer/_add_row/_display_view/_calc_lines from the widget's source."""
+    path = os.path.join(REF, "displays", "waterfall.py")
+    tree = ast.parse(open(path).read())
+    want = {"_calc_lines", "_init_buffer", "_add_row", "_display_view"}
+    fns = []
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef):
+            fns += [n for n in node.body if isinstance(n, ast.FunctionDef) and n.name in want]
+    assert {f.name for f in fns} == want
+    mod = ast.Module(body=[ast.ClassDef(name="Ring", bases=[], keywords=[], body=fns, decorator_list=[])],
+                     type_ignores=[])
+    ast.fix_missing_locations(mod)
+    ns = {"np": np, "_MAX_HISTORY": 2000, "logger": MagicMock()}
+    exec(compile(mod, path, "exec"), ns)
+    ring = ns["Ring"]()
+    ring.seconds_per_row, ring.wf_time_span, ring.wf_min_db = 0.5, 6.0, -100.0   # H = 12
+    ring.frequency_bins = np.arange(32)
+    ring._init_buffer()
+    rng = np.random.default_rng(71)
+    rows = rng.normal(-60, 5, (30, 32)).astype(np.float32)
+    views = []
+    for r in rows:
+        ring._add_row(r)
+        views.append(ring._display_view().copy())
+    np.savez_compressed(os.path.join(OUT, "waterfall_ring.npz"), meta=META, h=ring.history_lines,
+                        rows=rows, views=np.stack(views), fill=-100.0)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gen_rtl()
+    gen_hackrf()
+    gen_averager()
+    gen_holds_tare_sweepavg()
+    gen_stitch()
+    gen_waterfall()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -1,0 +1,584 @@
+// tdsa_api.cu — C ABI of libtdsa.so (see include/tdsa.h for the contract and the
+// reference file:line each entry point replaces).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/tdsa.h"
+#include "tdsa_aux.cuh"
+#include "tdsa_big.cuh"
+#include "tdsa_launch.cuh"
+
+namespace tdsa {
+std::atomic<int64_t> g_launch_count{0};
+}
+
+using namespace tdsa;
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CK(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess) return fail(TDSA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                       __FILE__, __LINE__);                                             \
+  } while (0)
+
+static inline void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------
+struct tdsa_plan {
+  int n = 0, log2n = 0;
+  int window_id = 0, window_norm = 0, mode = 0, precision = 0;
+  double floor = 1e-10, fs = 1.0;
+  int device = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<double> window_host;           // float64, no fftshift sign
+  // device tables
+  double* d_win64 = nullptr; float* d_win32 = nullptr;        // with (-1)^n folded in
+  double2* d_tw64 = nullptr; float2* d_tw32 = nullptr;
+  bool win_dirty = true;
+  // large-FFT (two-kernel) tables: inner plan size M = N/256
+  double2* d_twin64 = nullptr; float2* d_twin32 = nullptr;    // twiddles of the M-point inner transform
+  // scratch (grown on demand)
+  void* scratch = nullptr; size_t scratch_bytes = 0;
+  void* scratch2 = nullptr; size_t scratch2_bytes = 0;
+  // host pipeline
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr};
+  void* d_in[2] = {nullptr, nullptr}; void* d_out[2] = {nullptr, nullptr};
+  size_t d_in_bytes = 0, d_out_bytes = 0;
+};
+
+static bool is_big(const tdsa_plan* p) {
+  return p->log2n > (p->precision == TDSA_PREC_F32 ? MaxLog2<float>::value : MaxLog2<double>::value);
+}
+
+static int ensure_scratch(void** ptr, size_t* have, size_t need) {
+  if (*have >= need) return TDSA_OK;
+  if (*ptr) cudaFree(*ptr);
+  *ptr = nullptr;
+  *have = 0;
+  cudaError_t e = cudaMalloc(ptr, need);
+  if (e != cudaSuccess) return fail(TDSA_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+  *have = need;
+  return TDSA_OK;
+}
+
+// np.hanning / np.hamming / np.blackman (numpy/lib/_function_base_impl.py): n = arange(1-M, M, 2)
+static void build_window(int id, int norm, int n, std::vector<double>& w) {
+  w.assign(n, 1.0);
+  if (n == 1) return;
+  const double pi = 3.141592653589793238462643383279502884;
+  for (int i = 0; i < n; ++i) {
+    const double nn = (double)(1 - n + 2 * i);
+    const double x = pi * nn / (double)(n - 1);
+    switch (id) {
+      case TDSA_WINDOW_HANN: w[i] = 0.5 + 0.5 * cos(x); break;
+      case TDSA_WINDOW_HAMMING: w[i] = 0.54 + 0.46 * cos(x); break;
+      case TDSA_WINDOW_BLACKMAN: w[i] = 0.42 + 0.5 * cos(x) + 0.08 * cos(2.0 * x); break;
+      default: w[i] = 1.0; break;
+    }
+  }
+  if (norm == TDSA_NORM_RMS_F32) {   // hackrf_samples.py:314-316 (float32 arithmetic)
+    std::vector<float> wf(n);
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) { wf[i] = (float)w[i]; acc += (double)(wf[i] * wf[i]); }
+    const float rms = sqrtf((float)(acc / n));
+    for (int i = 0; i < n; ++i) w[i] = (double)(wf[i] / rms);
+  }
+}
+
+static int upload_window(tdsa_plan* p) {
+  const int n = p->n;
+  std::vector<double> w64(n);
+  std::vector<float> w32(n);
+  for (int i = 0; i < n; ++i) {
+    const double s = (i & 1) ? -1.0 : 1.0;   // (-1)^n  <=>  fftshift of the spectrum (n even)
+    w64[i] = s * p->window_host[i];
+    w32[i] = (float)w64[i];
+  }
+  CK(cudaMemcpy(p->d_win64, w64.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(p->d_win32, w32.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+  p->win_dirty = false;
+  return TDSA_OK;
+}
+
+// exp(-2*pi*i*m/L), folded to the first octant with exact integer arithmetic so that
+// symmetric entries are bit-identical and the axes are exact.
+static void twiddle(int64_t m, int64_t L, double* re, double* im) {
+  const double half_pi = 1.570796326794896619231321691639751442;
+  m %= L;
+  const int64_t q = (4 * m) / L;          // quadrant
+  const int64_t r = 4 * m - q * L;        // angle inside the quadrant = (pi/2) * r / L
+  double c, s;
+  if (2 * r <= L) { const double a = half_pi * ((double)r / (double)L); c = cos(a); s = sin(a); }
+  else { const double a = half_pi * ((double)(L - r) / (double)L); c = sin(a); s = cos(a); }
+  double C, S;
+  switch (q) {
+    case 0: C = c; S = s; break;
+    case 1: C = -s; S = c; break;
+    case 2: C = -c; S = -s; break;
+    default: C = s; S = -c; break;
+  }
+  *re = C;
+  *im = -S;
+}
+
+// Tables for an in-place DIF of 2^log2n points: radix-16 passes 0..npass-2 need
+// W_{L_i}^{c*q}; table i is laid out [q][c], c in [0, L_i/16).
+static int64_t tw_total(int log2n) {
+  const int npass = (log2n + 3) / 4;
+  int64_t t = 0;
+  for (int i = 0; i < npass - 1; ++i) t += (int64_t)1 << (log2n - 4 * i);
+  return t;
+}
+
+static void build_twiddles(int log2n, std::vector<double2>& t64) {
+  const int npass = (log2n + 3) / 4;
+  t64.clear();
+  t64.reserve(tw_total(log2n));
+  for (int i = 0; i < npass - 1; ++i) {
+    const int64_t L = (int64_t)1 << (log2n - 4 * i), S = L >> 4;
+    for (int q = 0; q < 16; ++q)
+      for (int64_t c = 0; c < S; ++c) {
+        double2 w;
+        twiddle(c * q, L, &w.x, &w.y);
+        t64.push_back(w);
+      }
+  }
+}
+
+static int upload_twiddles(int log2n, double2** d64, float2** d32) {
+  std::vector<double2> t64;
+  build_twiddles(log2n, t64);
+  const size_t cnt = t64.size() ? t64.size() : 1;
+  std::vector<float2> t32(cnt);
+  for (size_t i = 0; i < t64.size(); ++i) t32[i] = make_float2((float)t64[i].x, (float)t64[i].y);
+  CK(cudaMalloc(d64, sizeof(double2) * cnt));
+  CK(cudaMalloc(d32, sizeof(float2) * cnt));
+  if (!t64.empty()) {
+    CK(cudaMemcpy(*d64, t64.data(), sizeof(double2) * t64.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(*d32, t32.data(), sizeof(float2) * t64.size(), cudaMemcpyHostToDevice));
+  }
+  return TDSA_OK;
+}
+
+static EpiParams make_epi(const tdsa_plan* p, float* db, double* lin) {
+  EpiParams ep;
+  ep.db_out = db;
+  ep.lin_out = lin;
+  ep.mode = p->mode;
+  ep.floor = p->floor;
+  ep.scale = (p->mode == TDSA_MODE_PSD) ? 1.0 / (p->fs * (double)p->n) : 1.0;
+  return ep;
+}
+
+static int run_big(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t stride, const double2* dc, int epi, float* db,
+                   double* lin, LaunchInfo* info, bool dry);
+
+// one launch of the fused path for frames already in device memory
+static int run_fused(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t stride, const double2* dc, int epi,
+                     float* db, double* lin, LaunchInfo* info, bool dry) {
+  if (p->win_dirty) { int rc = upload_window(p); if (rc) return rc; }
+  if (is_big(p)) return run_big(p, iq, n_frames, stride, dc, epi, db, lin, info, dry);
+  cudaError_t e;
+  if (p->precision == TDSA_PREC_F32) {
+    FftArgs<float> a;
+    a.iq = (const float2*)iq; a.n_frames = n_frames; a.frame_stride = stride;
+    a.window = p->d_win32; a.tw = p->d_tw32; a.dc = dc; a.in_ct = nullptr; a.ep = make_epi(p, db, lin);
+    e = launch_fft_f32(p->log2n, epi, a, p->sm_count, p->stream, info, dry);
+  } else {
+    FftArgs<double> a;
+    a.iq = (const float2*)iq; a.n_frames = n_frames; a.frame_stride = stride;
+    a.window = p->d_win64; a.tw = p->d_tw64; a.dc = dc; a.in_ct = nullptr; a.ep = make_epi(p, db, lin);
+    e = launch_fft_f64(p->log2n, epi, a, p->sm_count, p->stream, info, dry);
+  }
+  if (e != cudaSuccess) return fail(TDSA_ERR_CUDA, "fused FFT launch failed (N=%d): %s", p->n, cudaGetErrorString(e));
+  return TDSA_OK;
+}
+
+#include "tdsa_big_host.inl"
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+int tdsa_version(void) { return TDSA_VERSION; }
+const char* tdsa_last_error(void) { return g_err.c_str(); }
+int64_t tdsa_launch_count(void) { return g_launch_count.load(); }
+
+int tdsa_create(int n_fft, int window_id, int window_norm, int mode, double log_floor, double fs, int precision,
+                tdsa_handle_t* out) {
+  if (!out) return fail(TDSA_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (n_fft < 64 || n_fft > (1 << 20) || (n_fft & (n_fft - 1)))
+    return fail(TDSA_ERR_UNSUPPORTED, "n_fft=%d: only powers of two in [64, 1048576] are supported", n_fft);
+  if (window_id < 0 || window_id > TDSA_WINDOW_CUSTOM) return fail(TDSA_ERR_INVALID, "bad window_id %d", window_id);
+  if (mode < 0 || mode > TDSA_MODE_MAG20) return fail(TDSA_ERR_INVALID, "bad mode %d", mode);
+  if (precision != TDSA_PREC_F64 && precision != TDSA_PREC_F32) return fail(TDSA_ERR_INVALID, "bad precision %d", precision);
+  tdsa_plan* p = new tdsa_plan();
+  p->n = n_fft;
+  while ((1 << p->log2n) < n_fft) ++p->log2n;
+  p->window_id = window_id; p->window_norm = window_norm; p->mode = mode; p->precision = precision;
+  p->floor = log_floor; p->fs = fs;
+  cudaError_t e = cudaGetDevice(&p->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device);
+  if (e != cudaSuccess) { delete p; return fail(TDSA_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(e)); }
+  build_window(window_id == TDSA_WINDOW_CUSTOM ? TDSA_WINDOW_RECT : window_id, window_norm, n_fft, p->window_host);
+  int rc = TDSA_OK;
+  do {
+    if (cudaMalloc(&p->d_win64, sizeof(double) * n_fft) != cudaSuccess ||
+        cudaMalloc(&p->d_win32, sizeof(float) * n_fft) != cudaSuccess) { rc = fail(TDSA_ERR_NOMEM, "window alloc failed"); break; }
+    rc = upload_twiddles(p->log2n, &p->d_tw64, &p->d_tw32);
+    if (rc) break;
+    if (p->log2n > MaxLog2<float>::value || p->log2n > MaxLog2<double>::value) {
+      // tables for the inner (N/256)-point transform of the two-kernel path
+      rc = upload_twiddles(p->log2n - 8, &p->d_twin64, &p->d_twin32);
+      if (rc) break;
+    }
+  } while (0);
+  if (rc) { tdsa_destroy(p); return rc; }
+  *out = p;
+  return TDSA_OK;
+}
+
+int tdsa_destroy(tdsa_handle_t p) {
+  if (!p) return TDSA_OK;
+  cudaFree(p->d_win64); cudaFree(p->d_win32); cudaFree(p->d_tw64); cudaFree(p->d_tw32);
+  cudaFree(p->d_twin64); cudaFree(p->d_twin32);
+  cudaFree(p->scratch); cudaFree(p->scratch2);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(p->d_in[i]); cudaFree(p->d_out[i]);
+    if (p->ev_h2d[i]) cudaEventDestroy(p->ev_h2d[i]);
+    if (p->ev_k[i]) cudaEventDestroy(p->ev_k[i]);
+  }
+  if (p->side) cudaStreamDestroy(p->side);
+  delete p;
+  return TDSA_OK;
+}
+
+int tdsa_set_stream(tdsa_handle_t p, void* s) {
+  if (!p) return fail(TDSA_ERR_INVALID, "null plan");
+  p->stream = (cudaStream_t)s;
+  return TDSA_OK;
+}
+
+int tdsa_set_window(tdsa_handle_t p, int window_id, int window_norm) {
+  if (!p) return fail(TDSA_ERR_INVALID, "null plan");
+  if (window_id < 0 || window_id >= TDSA_WINDOW_CUSTOM) return fail(TDSA_ERR_INVALID, "bad window_id %d", window_id);
+  p->window_id = window_id; p->window_norm = window_norm;
+  build_window(window_id, window_norm, p->n, p->window_host);
+  p->win_dirty = true;
+  return TDSA_OK;
+}
+
+int tdsa_set_window_table_host(tdsa_handle_t p, const double* w) {
+  if (!p || !w) return fail(TDSA_ERR_INVALID, "null argument");
+  p->window_id = TDSA_WINDOW_CUSTOM;
+  p->window_host.assign(w, w + p->n);
+  p->win_dirty = true;
+  return TDSA_OK;
+}
+
+int tdsa_get_window_table_host(tdsa_handle_t p, double* w) {
+  if (!p || !w) return fail(TDSA_ERR_INVALID, "null argument");
+  memcpy(w, p->window_host.data(), sizeof(double) * p->n);
+  return TDSA_OK;
+}
+
+int tdsa_set_mode(tdsa_handle_t p, int mode, double log_floor, double fs) {
+  if (!p) return fail(TDSA_ERR_INVALID, "null plan");
+  if (mode < 0 || mode > TDSA_MODE_MAG20) return fail(TDSA_ERR_INVALID, "bad mode %d", mode);
+  p->mode = mode; p->floor = log_floor; p->fs = fs;
+  return TDSA_OK;
+}
+
+int tdsa_set_precision(tdsa_handle_t p, int precision) {
+  if (!p) return fail(TDSA_ERR_INVALID, "null plan");
+  if (precision != TDSA_PREC_F64 && precision != TDSA_PREC_F32) return fail(TDSA_ERR_INVALID, "bad precision %d", precision);
+  p->precision = precision;
+  return TDSA_OK;
+}
+
+static int check_batch(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, const void* out) {
+  if (!p) return fail(TDSA_ERR_INVALID, "null plan");
+  if (n_frames < 0 || stride < 1) return fail(TDSA_ERR_INVALID, "n_frames=%lld frame_stride=%lld", (long long)n_frames, (long long)stride);
+  if (n_frames > 0 && (!iq || !out)) return fail(TDSA_ERR_INVALID, "null buffer");
+  if (((uintptr_t)iq & 7) != 0) return fail(TDSA_ERR_INVALID, "iq must be 8-byte aligned");
+  return TDSA_OK;
+}
+
+int tdsa_psd_db_batch(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, float* db_out) {
+  int rc = check_batch(p, iq, n_frames, stride, db_out);
+  if (rc) return rc;
+  return run_fused(p, iq, n_frames, stride, nullptr, kEpiDb, db_out, nullptr, nullptr, false);
+}
+
+int tdsa_power_linear_batch(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, double* lin_out) {
+  int rc = check_batch(p, iq, n_frames, stride, lin_out);
+  if (rc) return rc;
+  return run_fused(p, iq, n_frames, stride, nullptr, kEpiLinear, nullptr, lin_out, nullptr, false);
+}
+
+int tdsa_psd_db_batch_dc(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, double dc_alpha,
+                         double* dc_state, int32_t* silent_out, float* db_out) {
+  int rc = check_batch(p, iq, n_frames, stride, db_out);
+  if (rc) return rc;
+  if (!dc_state) return fail(TDSA_ERR_INVALID, "dc_state is NULL");
+  if (n_frames == 0) return TDSA_OK;
+  // scratch2: mean[F] (double2) | pw[F] (double) | dc[F] (double2)
+  const size_t need = (size_t)n_frames * (sizeof(double2) * 2 + sizeof(double));
+  rc = ensure_scratch(&p->scratch2, &p->scratch2_bytes, need);
+  if (rc) return rc;
+  double2* mean = (double2*)p->scratch2;
+  double2* dc = mean + n_frames;
+  double* pw = (double*)(dc + n_frames);
+  const int grid = (int)std::min<int64_t>(n_frames, (int64_t)p->sm_count * 8);
+  frame_stats_kernel<<<grid, 256, 0, p->stream>>>((const float2*)iq, n_frames, stride, p->n, mean, pw);
+  count_launch();
+  dc_scan_kernel<<<1, 32, 0, p->stream>>>(mean, pw, n_frames, dc_alpha, dc_state, dc, silent_out);
+  count_launch();
+  CK(cudaGetLastError());
+  return run_fused(p, iq, n_frames, stride, dc, kEpiDb, db_out, nullptr, nullptr, false);
+}
+
+int tdsa_psd_db_avg_hold(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, int avg_mode, int avg_n,
+                         double* avg_state, int32_t* count_state_host, float* max_hold, float* min_hold,
+                         int32_t* hold_valid_host, int last_only, float* db_out) {
+  int rc = check_batch(p, iq, n_frames, stride, db_out);
+  if (rc) return rc;
+  const bool averaging = avg_mode != TDSA_AVG_OFF && avg_n > 1;
+  if (averaging && (!avg_state || !count_state_host)) return fail(TDSA_ERR_INVALID, "averaging needs avg_state and count_state");
+  if ((max_hold || min_hold) && !hold_valid_host) return fail(TDSA_ERR_INVALID, "holds need hold_valid");
+  if (p->mode == TDSA_MODE_MAG20 && averaging) return fail(TDSA_ERR_INVALID, "mag20 branch is never averaged (hackrf_samples.py:378-383)");
+  if (n_frames == 0) return TDSA_OK;
+  // frames are folded in chunks so the float64 linear-power scratch stays bounded (<= 256 MiB)
+  const int64_t chunk_max = std::max<int64_t>(1, ((int64_t)256 << 20) / ((int64_t)p->n * 8));
+  int count = averaging ? *count_state_host : 0;
+  int mxv = hold_valid_host ? hold_valid_host[0] : 0, mnv = hold_valid_host ? hold_valid_host[1] : 0;
+  for (int64_t f0 = 0; f0 < n_frames; f0 += chunk_max) {
+    const int64_t nf = std::min(chunk_max, n_frames - f0);
+    rc = ensure_scratch(&p->scratch, &p->scratch_bytes, (size_t)nf * p->n * sizeof(double));
+    if (rc) return rc;
+    double* lin = (double*)p->scratch;
+    rc = run_fused(p, (const float2*)iq + f0 * stride, nf, stride, nullptr, kEpiLinear, nullptr, lin, nullptr, false);
+    if (rc) return rc;
+    TraceScanArgs a;
+    a.lin = lin; a.n_frames = nf; a.width = p->n; a.avg_mode = avg_mode; a.avg_n = avg_n; a.count0 = count;
+    a.avg_state = avg_state; a.max_hold = max_hold; a.min_hold = min_hold; a.max_valid0 = mxv; a.min_valid0 = mnv;
+    a.last_only = last_only;
+    a.db_out = last_only ? db_out : db_out + f0 * p->n;
+    a.floor = p->floor; a.mode = p->mode;
+    trace_scan_kernel<<<(p->n + 255) / 256, 256, 0, p->stream>>>(a);
+    count_launch();
+    CK(cudaGetLastError());
+    if (averaging) {   // TraceAverager._count after nf more frames (signal_processing.py:46-58)
+      if (avg_mode == TDSA_AVG_LIN) count = (int)std::min<int64_t>((int64_t)avg_n, (int64_t)count + nf);
+      else count = std::max(count, 1);
+    }
+    if (max_hold) mxv = 1;
+    if (min_hold) mnv = 1;
+  }
+  if (averaging) *count_state_host = count;
+  if (hold_valid_host) { hold_valid_host[0] = mxv; hold_valid_host[1] = mnv; }
+  return TDSA_OK;
+}
+
+int tdsa_welch(tdsa_handle_t p, const void* iq_stream, int64_t n_samples, int64_t hop, float* avg_db, float* peak_db) {
+  if (!p || !iq_stream || !avg_db || !peak_db) return fail(TDSA_ERR_INVALID, "null argument");
+  if (hop < 1 || n_samples < p->n) return fail(TDSA_ERR_INVALID, "need hop >= 1 and n_samples >= n_fft");
+  if (p->mode == TDSA_MODE_MAG20) return fail(TDSA_ERR_INVALID, "welch averages power; use power or psd mode");
+  const int64_t nseg = (n_samples - p->n) / hop + 1;
+  const int64_t n = p->n;
+  // state: sum[N] double | peak[N] float, kept behind the linear scratch
+  const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(nseg, ((int64_t)128 << 20) / (n * 8)));
+  const size_t lin_bytes = (size_t)chunk * n * sizeof(double);
+  int rc = ensure_scratch(&p->scratch, &p->scratch_bytes, lin_bytes + (size_t)n * (sizeof(double) + sizeof(float)));
+  if (rc) return rc;
+  double* lin = (double*)p->scratch;
+  double* sum = (double*)((char*)p->scratch + lin_bytes);
+  float* peak = (float*)(sum + n);
+  const bool big = is_big(p);
+  for (int64_t s0 = 0; s0 < nseg; s0 += chunk) {
+    const int64_t ns = std::min(chunk, nseg - s0);
+    // big plans leave the linear rows in the permuted [s][klow] order (coalesced); finish un-permutes
+    rc = big ? run_big(p, (const float2*)iq_stream + s0 * hop, ns, hop, nullptr, kEpiLinearPermuted, nullptr, lin, nullptr, false)
+             : run_fused(p, (const float2*)iq_stream + s0 * hop, ns, hop, nullptr, kEpiLinear, nullptr, lin, nullptr, false);
+    if (rc) return rc;
+    welch_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, p->stream>>>(lin, ns, n, sum, peak, s0 == 0, p->floor, p->mode);
+    count_launch();
+    CK(cudaGetLastError());
+  }
+  welch_finish_kernel<<<(int)((n + 255) / 256), 256, 0, p->stream>>>(sum, peak, n, nseg, big ? p->log2n - 8 : 0, p->floor,
+                                                                   p->mode, avg_db, peak_db);
+  count_launch();
+  CK(cudaGetLastError());
+  return TDSA_OK;
+}
+
+int tdsa_trace_update(const float* rows, int64_t n_rows, int64_t width, double cal_offset_db, int avg_mode, int avg_n,
+                      double* avg_state, int32_t* count_state_host, float* max_hold, float* min_hold,
+                      int32_t* hold_valid_host, float* rows_out, void* cuda_stream, int32_t* row_flags_scratch) {
+  if (!rows || n_rows < 0 || width < 1) return fail(TDSA_ERR_INVALID, "bad rows");
+  if (!row_flags_scratch) return fail(TDSA_ERR_INVALID, "row_flags_scratch (int32[n_rows], device) is required");
+  const bool averaging = avg_mode != TDSA_AVG_OFF && avg_n > 1;
+  if (averaging && (!avg_state || !count_state_host)) return fail(TDSA_ERR_INVALID, "averaging needs avg_state and count_state");
+  if ((max_hold || min_hold) && !hold_valid_host) return fail(TDSA_ERR_INVALID, "holds need hold_valid");
+  if (n_rows == 0) return TDSA_OK;
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  CK(cudaMemsetAsync(row_flags_scratch, 0, sizeof(int32_t) * n_rows, s));
+  dim3 g((unsigned)((width + 255) / 256), (unsigned)n_rows);
+  row_allnan_kernel<<<g, 256, 0, s>>>(rows, n_rows, width, row_flags_scratch);
+  count_launch();
+  TraceUpdateArgs a;
+  a.rows = rows; a.n_rows = n_rows; a.width = width; a.cal = cal_offset_db;
+  a.avg_mode = avg_mode; a.avg_n = avg_n; a.count0 = averaging ? *count_state_host : 0;
+  a.avg_state = avg_state; a.max_hold = max_hold; a.min_hold = min_hold;
+  a.max_valid0 = hold_valid_host ? hold_valid_host[0] : 0;
+  a.min_valid0 = hold_valid_host ? hold_valid_host[1] : 0;
+  a.has_value = row_flags_scratch; a.rows_out = rows_out;
+  trace_update_kernel<<<(unsigned)((width + 255) / 256), 256, 0, s>>>(a);
+  count_launch();
+  CK(cudaGetLastError());
+  // host-side scalars need the number of non-NaN rows: read the flags back (tiny, synchronous)
+  std::vector<int32_t> flags(n_rows);
+  CK(cudaMemcpyAsync(flags.data(), row_flags_scratch, sizeof(int32_t) * n_rows, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  int64_t live = 0;
+  for (int32_t v : flags) live += v != 0;
+  if (live > 0) {
+    if (averaging) {
+      int c = *count_state_host;
+      if (avg_mode == TDSA_AVG_LIN) c = (int)std::min<int64_t>(avg_n, (int64_t)c + live);
+      else c = std::max(c, 1);
+      *count_state_host = c;
+    }
+    if (hold_valid_host) {
+      if (max_hold) hold_valid_host[0] = 1;
+      if (min_hold) hold_valid_host[1] = 1;
+    }
+  }
+  return TDSA_OK;
+}
+
+int tdsa_stitch(const float* rows, const double* row_lo_hz, double row_hz, int64_t n_rows, int64_t bins_per_row,
+                double start_hz, double stop_hz, int64_t m, double* grid_out, void* cuda_stream, int32_t* order_scratch) {
+  if (!rows || !row_lo_hz || !grid_out || !order_scratch) return fail(TDSA_ERR_INVALID, "null argument");
+  if (n_rows < 1 || bins_per_row < 1 || m < 1) return fail(TDSA_ERR_INVALID, "bad sizes");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  stitch_rank_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, s>>>(row_lo_hz, n_rows, order_scratch);
+  count_launch();
+  StitchArgs a;
+  a.rows = rows; a.lo = row_lo_hz; a.order = order_scratch; a.row_hz = row_hz; a.n_rows = n_rows; a.k = bins_per_row;
+  a.start = start_hz; a.stop = stop_hz; a.m = m; a.out = grid_out;
+  stitch_interp_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(a);
+  count_launch();
+  CK(cudaGetLastError());
+  return TDSA_OK;
+}
+
+int tdsa_ring_push(const float* rows, int64_t n_rows, float* ring, int64_t H, int64_t W, int64_t* ptr_host,
+                   void* cuda_stream) {
+  if (!rows || !ring || !ptr_host || H < 1 || W < 1 || n_rows < 0) return fail(TDSA_ERR_INVALID, "bad argument");
+  if (n_rows == 0) return TDSA_OK;
+  const int64_t first = n_rows > H ? n_rows - H : 0;   // older rows would be overwritten anyway
+  dim3 g((unsigned)((W + 255) / 256), (unsigned)(n_rows - first));
+  ring_push_kernel<<<g, 256, 0, (cudaStream_t)cuda_stream>>>(rows, first, n_rows, ring, H, W, *ptr_host);
+  count_launch();
+  CK(cudaGetLastError());
+  int64_t p = (*ptr_host - n_rows) % H;
+  if (p < 0) p += H;
+  *ptr_host = p;
+  return TDSA_OK;
+}
+
+int tdsa_h2d_async(const void* pinned_host, void* dev, size_t bytes, void* side_stream, void* done_event) {
+  if (!pinned_host || !dev) return fail(TDSA_ERR_INVALID, "null pointer");
+  CK(cudaMemcpyAsync(dev, pinned_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)side_stream));
+  if (done_event) CK(cudaEventRecord((cudaEvent_t)done_event, (cudaStream_t)side_stream));
+  return TDSA_OK;
+}
+
+int tdsa_psd_db_batch_host(tdsa_handle_t p, const void* iq_host, int64_t n_frames, int64_t stride, float* db_out_host,
+                           int64_t chunk_frames) {
+  if (!p) return fail(TDSA_ERR_INVALID, "null plan");
+  if (n_frames < 0 || stride < 1) return fail(TDSA_ERR_INVALID, "bad frame geometry");
+  if (n_frames == 0) return TDSA_OK;
+  if (!iq_host || !db_out_host) return fail(TDSA_ERR_INVALID, "null buffer");
+  const int64_t n = p->n;
+  if (chunk_frames < 1) chunk_frames = std::max<int64_t>(1, ((int64_t)32 << 20) / (n * 8));   // ~32 MiB of IQ per chunk
+  chunk_frames = std::min(chunk_frames, n_frames);
+  const size_t in_bytes = (size_t)((chunk_frames - 1) * stride + n) * sizeof(float2);
+  const size_t out_bytes = (size_t)chunk_frames * n * sizeof(float);
+  if (!p->side) {
+    CK(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CK(cudaEventCreateWithFlags(&p->ev_h2d[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&p->ev_k[i], cudaEventDisableTiming));
+    }
+  }
+  if (p->d_in_bytes < in_bytes) {
+    for (int i = 0; i < 2; ++i) { cudaFree(p->d_in[i]); p->d_in[i] = nullptr; CK(cudaMalloc(&p->d_in[i], in_bytes)); }
+    p->d_in_bytes = in_bytes;
+  }
+  if (p->d_out_bytes < out_bytes) {
+    for (int i = 0; i < 2; ++i) { cudaFree(p->d_out[i]); p->d_out[i] = nullptr; CK(cudaMalloc(&p->d_out[i], out_bytes)); }
+    p->d_out_bytes = out_bytes;
+  }
+  // The compute stream must be a real (non-legacy) stream for overlap; fall back to the side stream's sibling.
+  cudaStream_t user = p->stream;
+  int rc = TDSA_OK;
+  int64_t c = 0;
+  for (int64_t f0 = 0; f0 < n_frames; f0 += chunk_frames, ++c) {
+    const int b = (int)(c & 1);
+    const int64_t nf = std::min(chunk_frames, n_frames - f0);
+    const size_t bytes = (size_t)((nf - 1) * stride + n) * sizeof(float2);
+    // buffer b is free once the kernel + D2H of chunk c-2 are done
+    if (c >= 2) CK(cudaStreamWaitEvent(p->side, p->ev_k[b], 0));
+    CK(cudaMemcpyAsync(p->d_in[b], (const float2*)iq_host + f0 * stride, bytes, cudaMemcpyHostToDevice, p->side));
+    CK(cudaEventRecord(p->ev_h2d[b], p->side));
+    CK(cudaStreamWaitEvent(user, p->ev_h2d[b], 0));
+    rc = run_fused(p, p->d_in[b], nf, stride, nullptr, kEpiDb, (float*)p->d_out[b], nullptr, nullptr, false);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(db_out_host + f0 * n, p->d_out[b], (size_t)nf * n * sizeof(float), cudaMemcpyDeviceToHost, user));
+    CK(cudaEventRecord(p->ev_k[b], user));
+  }
+  CK(cudaStreamSynchronize(user));
+  return TDSA_OK;
+}
+
+int tdsa_plan_info(tdsa_handle_t p, int* n_fft, int* threads, int* ctas_per_sm, int* smem, int* grid) {
+  if (!p) return fail(TDSA_ERR_INVALID, "null plan");
+  LaunchInfo info;
+  int rc = run_fused(p, nullptr, 1 << 20, p->n, nullptr, kEpiDb, nullptr, nullptr, &info, true);
+  if (rc) return rc;
+  if (n_fft) *n_fft = p->n;
+  if (threads) *threads = info.threads;
+  if (ctas_per_sm) *ctas_per_sm = info.ctas_per_sm;
+  if (smem) *smem = info.smem;
+  if (grid) *grid = info.grid;
+  return TDSA_OK;
+}
+
+}  // extern "C"

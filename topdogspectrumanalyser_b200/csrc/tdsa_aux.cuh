@@ -1,0 +1,334 @@
+// tdsa_aux.cuh — trace-state, stitch, ring and front-end kernels around the fused FFT.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "tdsa_fft.cuh"
+
+namespace tdsa {
+
+// ---------------------------------------------------------------------------------------
+// HackRF front end, datasources/hackrf_samples.py:351,360: per-frame mean(x), mean(|x|^2)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) frame_stats_kernel(const float2* __restrict__ iq, int64_t n_frames,
+                                                         int64_t frame_stride, int n, double2* __restrict__ mean_out,
+                                                         double* __restrict__ pw_out) {
+  __shared__ double s_r[8], s_i[8], s_p[8];
+  for (int64_t f = blockIdx.x; f < n_frames; f += gridDim.x) {
+    const float2* x = iq + f * frame_stride;
+    double sr = 0.0, si = 0.0, sp = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      float2 v = x[i];
+      sr += (double)v.x;
+      si += (double)v.y;
+      sp += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sr += __shfl_xor_sync(0xffffffffu, sr, o);
+      si += __shfl_xor_sync(0xffffffffu, si, o);
+      sp += __shfl_xor_sync(0xffffffffu, sp, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s_r[w] = sr; s_i[w] = si; s_p[w] = sp; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0, b = 0.0, c = 0.0;
+      for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { a += s_r[k]; b += s_i[k]; c += s_p[k]; }
+      mean_out[f] = make_double2(a / n, b / n);
+      pw_out[f] = c / n;
+    }
+    __syncthreads();
+  }
+}
+
+// dc_f = (1-alpha)*dc_{f-1} + alpha*mean_f for non-silent frames (hackrf_samples.py:351-365).
+// Sequential in f by definition; one thread.
+__global__ void dc_scan_kernel(const double2* __restrict__ mean, const double* __restrict__ pw, int64_t n_frames,
+                               double alpha, double* __restrict__ dc_state, double2* __restrict__ dc_out,
+                               int32_t* __restrict__ silent_out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double dr = dc_state[0], di = dc_state[1];
+  for (int64_t f = 0; f < n_frames; ++f) {
+    const bool silent = pw[f] < 1e-20;
+    if (!silent) {
+      dr = (1.0 - alpha) * dr + alpha * mean[f].x;
+      di = (1.0 - alpha) * di + alpha * mean[f].y;
+    }
+    dc_out[f] = make_double2(dr, di);
+    if (silent_out) silent_out[f] = silent ? 1 : 0;
+  }
+  dc_state[0] = dr;
+  dc_state[1] = di;
+}
+
+// ---------------------------------------------------------------------------------------
+// TraceAverager + dB + max/min hold over consecutive frames, one thread per bin.
+// utils/signal_processing.py:35-61; core/display_data_processor.py:371-395,473-480.
+// ---------------------------------------------------------------------------------------
+struct TraceScanArgs {
+  const double* lin;       // [F][W] linear power (already scaled for PSD)
+  int64_t n_frames;
+  int64_t width;
+  int avg_mode;            // 0 off, 1 exp, 2 lin
+  int avg_n;
+  int count0;              // averager count before this call (0 = empty buffer)
+  double* avg_state;       // [W] float64 buffer (TraceAverager._buffer)
+  float* max_hold;         // [W] or null
+  float* min_hold;         // [W] or null
+  int max_valid0, min_valid0;
+  int last_only;
+  float* db_out;           // [F][W] or [W] when last_only
+  double floor;
+  int mode;                // dB branch (mag20 never reaches here with averaging on)
+};
+
+__global__ void __launch_bounds__(256) trace_scan_kernel(const TraceScanArgs a) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.width) return;
+  const bool averaging = a.avg_mode != 0 && a.avg_n > 1;
+  double buf = (averaging && a.count0 > 0) ? a.avg_state[k] : 0.0;
+  int count = a.count0;
+  const double alpha = 1.0 / (double)a.avg_n;
+  bool mxv = a.max_valid0 != 0, mnv = a.min_valid0 != 0;
+  float mx = (a.max_hold && mxv) ? a.max_hold[k] : 0.f;
+  float mn = (a.min_hold && mnv) ? a.min_hold[k] : 0.f;
+  EpiParams ep;
+  ep.db_out = nullptr; ep.lin_out = nullptr; ep.scale = 1.0; ep.floor = a.floor; ep.mode = a.mode;
+  for (int64_t f = 0; f < a.n_frames; ++f) {
+    const double p = a.lin[f * a.width + k];
+    double v = p;
+    if (averaging) {
+      if (count == 0) {
+        buf = p;
+        count = 1;
+      } else if (a.avg_mode == 1) {
+        buf = __dmul_rn(buf, 1.0 - alpha);              // buffer *= (1 - alpha)
+        buf = __dadd_rn(buf, __dmul_rn(alpha, p));      // buffer += alpha * x
+      } else {
+        if (count < a.avg_n) ++count;
+        buf = __dadd_rn(buf, __ddiv_rn(__dsub_rn(p, buf), (double)count));   // buffer += (x - buffer)/count
+      }
+      v = buf;
+    }
+    const float db = to_db<double>(v, ep);
+    if (!a.last_only) a.db_out[f * a.width + k] = db;
+    else if (f == a.n_frames - 1) a.db_out[k] = db;
+    if (a.max_hold) {
+      if (!mxv) { mx = isnan(db) ? -500.0f : db; mxv = true; }
+      else mx = fmaxf(mx, db);
+    }
+    if (a.min_hold) {
+      if (!mnv) { mn = isnan(db) ? 500.0f : db; mnv = true; }
+      else mn = fminf(mn, db);
+    }
+  }
+  if (averaging && a.n_frames > 0) a.avg_state[k] = buf;
+  if (a.max_hold && mxv) a.max_hold[k] = mx;
+  if (a.min_hold && mnv) a.min_hold[k] = mn;
+}
+
+// ---------------------------------------------------------------------------------------
+// Trace update on dB rows: cal offset (display_data_processor.py:317-327), sweep-domain
+// averaging (:211-218), holds (:371-395). Rows that are entirely NaN are skipped (:211).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) row_allnan_kernel(const float* __restrict__ rows, int64_t n_rows, int64_t width,
+                                                        int32_t* __restrict__ has_value) {
+  // has_value[r] != 0 iff row r holds at least one non-NaN
+  const int64_t r = blockIdx.y;
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows || k >= width) return;
+  if (!isnan(rows[r * width + k])) has_value[r] = 1;
+}
+
+struct TraceUpdateArgs {
+  const float* rows;
+  int64_t n_rows, width;
+  double cal;
+  int avg_mode, avg_n, count0;
+  double* avg_state;
+  float* max_hold;
+  float* min_hold;
+  int max_valid0, min_valid0;
+  const int32_t* has_value;   // per row
+  float* rows_out;            // [n_rows][width] or null
+};
+
+__global__ void __launch_bounds__(256) trace_update_kernel(const TraceUpdateArgs a) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.width) return;
+  const bool averaging = a.avg_mode != 0 && a.avg_n > 1;
+  double buf = (averaging && a.count0 > 0) ? a.avg_state[k] : 0.0;
+  int count = a.count0;
+  const double alpha = 1.0 / (double)a.avg_n;
+  bool mxv = a.max_valid0 != 0, mnv = a.min_valid0 != 0;
+  float mx = (a.max_hold && mxv) ? a.max_hold[k] : 0.f;
+  float mn = (a.min_hold && mnv) ? a.min_hold[k] : 0.f;
+  bool touched = false;
+  for (int64_t r = 0; r < a.n_rows; ++r) {
+    double x = (double)a.rows[r * a.width + k];
+    if (a.cal != 0.0) x += a.cal;
+    if (!a.has_value[r]) {               // NaN-only frame: the reference returns before any state update
+      if (a.rows_out) a.rows_out[r * a.width + k] = (float)x;
+      continue;
+    }
+    if (averaging) {
+      const double lin = pow(10.0, x / 10.0);
+      if (count == 0) {
+        buf = lin;
+        count = 1;
+      } else if (a.avg_mode == 1) {
+        buf = __dmul_rn(buf, 1.0 - alpha);
+        buf = __dadd_rn(buf, __dmul_rn(alpha, lin));
+      } else {
+        if (count < a.avg_n) ++count;
+        buf = __dadd_rn(buf, __ddiv_rn(__dsub_rn(lin, buf), (double)count));
+      }
+      touched = true;
+      x = 10.0 * log10(fmax(buf, 1e-30));
+    }
+    const float db = (float)x;
+    if (a.rows_out) a.rows_out[r * a.width + k] = db;
+    if (a.max_hold) {
+      if (!mxv) { mx = isnan(db) ? -500.0f : db; mxv = true; }
+      else mx = fmaxf(mx, db);
+    }
+    if (a.min_hold) {
+      if (!mnv) { mn = isnan(db) ? 500.0f : db; mnv = true; }
+      else mn = fminf(mn, db);
+    }
+  }
+  if (averaging && touched) a.avg_state[k] = buf;
+  if (a.max_hold && mxv) a.max_hold[k] = mx;
+  if (a.min_hold && mnv) a.min_hold[k] = mn;
+}
+
+// ---------------------------------------------------------------------------------------
+// hackrf_sweep stitch, datasources/hackrf_sweep.py:150-166.
+// rank[r] = position of row r when rows are ordered by hz_low (argsort; ties by index).
+// ---------------------------------------------------------------------------------------
+__global__ void stitch_rank_kernel(const double* __restrict__ lo, int64_t n_rows, int32_t* __restrict__ order) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  const double v = lo[r];
+  int32_t rank = 0;
+  for (int64_t j = 0; j < n_rows; ++j) {
+    const double u = lo[j];
+    rank += (u < v) || (u == v && j < r);
+  }
+  order[rank] = (int32_t)r;   // order[i] = index of the row with the i-th lowest hz_low
+}
+
+struct StitchArgs {
+  const float* rows;       // [R][K]
+  const double* lo;        // [R]
+  const int32_t* order;    // [R]
+  double row_hz;           // hz_high - hz_low of every row
+  int64_t n_rows, k;
+  double start, stop;
+  int64_t m;
+  double* out;             // [m]
+};
+
+// x of sample i of row r, exactly as np.arange(lo + bw/2, hi, bw) produces it (start + i*bw).
+__device__ __forceinline__ double stitch_x(const StitchArgs& a, int64_t sorted_idx, double bw) {
+  const int64_t rr = sorted_idx / a.k, i = sorted_idx - rr * a.k;
+  const double x0 = __dadd_rn(a.lo[a.order[rr]], __ddiv_rn(bw, 2.0));
+  return __dadd_rn(x0, __dmul_rn((double)i, bw));
+}
+__device__ __forceinline__ double stitch_y(const StitchArgs& a, int64_t sorted_idx) {
+  const int64_t rr = sorted_idx / a.k, i = sorted_idx - rr * a.k;
+  return (double)a.rows[(int64_t)a.order[rr] * a.k + i];
+}
+
+__global__ void __launch_bounds__(256) stitch_interp_kernel(const StitchArgs a) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.m) return;
+  // np.linspace(start, stop, m): arange(m)*step + start, last element forced to stop
+  const double step = __ddiv_rn(__dsub_rn(a.stop, a.start), (double)(a.m - 1));
+  double xv = __dadd_rn(__dmul_rn((double)g, step), a.start);
+  if (g == a.m - 1 && a.m > 1) xv = a.stop;
+  const double bw = __ddiv_rn(a.row_hz, (double)a.k);
+  const int64_t total = a.n_rows * a.k;
+  // np.interp: left/right clamp, then j = largest index with xp[j] <= x
+  const double x_first = stitch_x(a, 0, bw), x_last = stitch_x(a, total - 1, bw);
+  if (xv < x_first) { a.out[g] = stitch_y(a, 0); return; }        // default left = fp[0]
+  if (xv > x_last) { a.out[g] = stitch_y(a, total - 1); return; } // default right = fp[-1]
+  int64_t lo_i = 0, hi_i = total - 1;     // invariant: x[lo_i] <= xv, and (hi_i == total-1 or x[hi_i] > xv)
+  while (hi_i - lo_i > 1) {
+    const int64_t mid = (lo_i + hi_i) >> 1;
+    if (stitch_x(a, mid, bw) <= xv) lo_i = mid; else hi_i = mid;
+  }
+  int64_t j = lo_i;
+  if (stitch_x(a, hi_i, bw) <= xv) j = hi_i;
+  const double xj = stitch_x(a, j, bw), yj = stitch_y(a, j);
+  if (j == total - 1 || xj == xv) { a.out[g] = yj; return; }
+  const double xj1 = stitch_x(a, j + 1, bw), yj1 = stitch_y(a, j + 1);
+  const double slope = __ddiv_rn(__dsub_rn(yj1, yj), __dsub_rn(xj1, xj));
+  double res = __dadd_rn(__dmul_rn(slope, __dsub_rn(xv, xj)), yj);
+  if (isnan(res)) {
+    res = __dadd_rn(__dmul_rn(slope, __dsub_rn(xv, xj1)), yj1);
+    if (isnan(res) && yj == yj1) res = yj;
+  }
+  a.out[g] = res;
+}
+
+// ---------------------------------------------------------------------------------------
+// waterfall ring, displays/waterfall.py:173-177: row r lands at (ptr0 - 1 - r) mod H and +H.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ring_push_kernel(const float* __restrict__ rows, int64_t first_row,
+                                                       int64_t n_rows, float* __restrict__ ring, int64_t H, int64_t W,
+                                                       int64_t ptr0) {
+  const int64_t r = first_row + blockIdx.y;
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows || k >= W) return;
+  int64_t p = (ptr0 - 1 - r) % H;
+  if (p < 0) p += H;
+  const float v = rows[r * W + k];
+  ring[p * W + k] = v;
+  ring[(p + H) * W + k] = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// Welch reduce over a chunk of segments (config 3): sum of linear power, fmax of per-segment dB.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) welch_reduce_kernel(const double* __restrict__ lin, int64_t n_seg, int64_t width,
+                                                          double* __restrict__ sum_state, float* __restrict__ peak_state,
+                                                          int first_chunk, double floor, int mode) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= width) return;
+  EpiParams ep;
+  ep.db_out = nullptr; ep.lin_out = nullptr; ep.scale = 1.0; ep.floor = floor; ep.mode = mode;
+  double s = first_chunk ? 0.0 : sum_state[k];
+  float pk = first_chunk ? -INFINITY : peak_state[k];
+  for (int64_t f = 0; f < n_seg; ++f) {
+    const double p = lin[f * width + k];
+    s += p;
+    pk = fmaxf(pk, to_db<double>(p, ep));
+  }
+  sum_state[k] = s;
+  peak_state[k] = pk;
+}
+
+// final: avg_db[k] = dB(sum/nseg); optional un-permute for the two-kernel large-FFT path:
+// permuted index i = s*M + klow with s = 16*k0 + k1  ->  k = k0 + 16*k1 + 256*klow.
+__global__ void __launch_bounds__(256) welch_finish_kernel(const double* __restrict__ sum_state,
+                                                          const float* __restrict__ peak_state, int64_t width,
+                                                          int64_t n_seg, int log2_m_perm, double floor, int mode,
+                                                          float* __restrict__ avg_db, float* __restrict__ peak_db) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= width) return;
+  int64_t k = i;
+  if (log2_m_perm > 0) {
+    const int64_t m = (int64_t)1 << log2_m_perm;
+    const int64_t s = i >> log2_m_perm, kl = i & (m - 1);
+    k = (s >> 4) + 16 * (s & 15) + 256 * kl;
+  }
+  EpiParams ep;
+  ep.db_out = nullptr; ep.lin_out = nullptr; ep.scale = 1.0; ep.floor = floor; ep.mode = mode;
+  avg_db[k] = to_db<double>(sum_state[i] / (double)n_seg, ep);
+  peak_db[k] = peak_state[i];
+}
+
+}  // namespace tdsa

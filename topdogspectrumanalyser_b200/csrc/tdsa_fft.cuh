@@ -1,0 +1,377 @@
+// tdsa_fft.cuh — fused window + FFT + |.|^2 + dB + fftshift kernels for sm_100a.
+//
+// Replaces, per frame, datasources/rtl_samples.py:169-184 of the reference
+// (x*w -> scipy.fft.fft -> fftshift -> abs**2 -> 10*log10(. + floor)) and the
+// hackrf variant datasources/hackrf_samples.py:365-383, over a batch of frames.
+//
+// Decomposition (mirrored in tools/fft_plan_model.py, which checks it against numpy):
+//   * 16 points per thread, T = N/16 threads per frame, in-place DIF.
+//   * passes are radix 16 while >= 4 bits remain, then one final radix 2/4/8 pass.
+//   * pass 0 reads x[t + j*T] straight from global memory (coalesced), multiplies by
+//     the window (with (-1)^n folded in, which makes the output fftshift-ed for free)
+//     and runs its butterflies in registers; later passes exchange through a padded
+//     shared-memory buffer laid out so that every access pattern is bank-conflict free.
+//   * the final pass gives thread t the sub-transform whose outputs are bins
+//     k = t + T*u + (N/R)*q, so dB stores are coalesced; no bit-reversal pass.
+//   * twiddles are exact-rounded tables built on the host in float64.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tdsa {
+
+// ---------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------
+template <typename T> struct CplxOf;
+template <> struct CplxOf<float> { using type = float2; };
+template <> struct CplxOf<double> { using type = double2; };
+
+template <typename T> __device__ __forceinline__ typename CplxOf<T>::type mk(T a, T b);
+template <> __device__ __forceinline__ float2 mk<float>(float a, float b) { return make_float2(a, b); }
+template <> __device__ __forceinline__ double2 mk<double>(double a, double b) { return make_double2(a, b); }
+
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float2 ldg_stream(const float2* p) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+
+template <typename T> __device__ __forceinline__ void cmul(T& xr, T& xi, T wr, T wi) {
+  T r = xr * wr - xi * wi;
+  T i = xr * wi + xi * wr;
+  xr = r;
+  xi = i;
+}
+
+// ---------------------------------------------------------------------------------------
+// butterflies (forward DFT, W = exp(-2*pi*i/R)); all indices are compile-time after unrolling
+// ---------------------------------------------------------------------------------------
+template <typename T, int I0, int I1, int I2, int I3>
+__device__ __forceinline__ void r4(T (&re)[16], T (&im)[16]) {
+  T t0r = re[I0] + re[I2], t0i = im[I0] + im[I2];
+  T t1r = re[I0] - re[I2], t1i = im[I0] - im[I2];
+  T t2r = re[I1] + re[I3], t2i = im[I1] + im[I3];
+  T t3r = re[I1] - re[I3], t3i = im[I1] - im[I3];
+  re[I0] = t0r + t2r; im[I0] = t0i + t2i;
+  re[I2] = t0r - t2r; im[I2] = t0i - t2i;
+  re[I1] = t1r + t3i; im[I1] = t1i - t3r;   // t1 - i*t3
+  re[I3] = t1r - t3i; im[I3] = t1i + t3r;   // t1 + i*t3
+}
+
+template <typename T, int A, int B> __device__ __forceinline__ void swp(T (&re)[16], T (&im)[16]) {
+  T r = re[A]; re[A] = re[B]; re[B] = r;
+  T i = im[A]; im[A] = im[B]; im[B] = i;
+}
+
+// x *= (1 - i)/sqrt(2)   (W8^1 = W16^2)
+template <typename T> __device__ __forceinline__ void mul_w8_1(T& xr, T& xi) {
+  const T h = T(0.70710678118654752440);
+  T r = (xr + xi) * h, i = (xi - xr) * h;
+  xr = r; xi = i;
+}
+// x *= (-1 - i)/sqrt(2)  (W8^3 = W16^6)
+template <typename T> __device__ __forceinline__ void mul_w8_3(T& xr, T& xi) {
+  const T h = T(0.70710678118654752440);
+  T r = (xi - xr) * h, i = -(xr + xi) * h;
+  xr = r; xi = i;
+}
+// x *= -i
+template <typename T> __device__ __forceinline__ void mul_mi(T& xr, T& xi) {
+  T r = xi, i = -xr;
+  xr = r; xi = i;
+}
+
+// 16-point DFT over all 16 registers, natural order in and out: a[q] = sum_j a[j] W16^(jq).
+template <typename T> __device__ __forceinline__ void dft16(T (&re)[16], T (&im)[16]) {
+  const T c1 = T(0.92387953251128675613);   // cos(pi/8)
+  const T s1 = T(0.38268343236508977173);   // sin(pi/8)
+  // stage A: over j1 (stride 4); a[j0 + 4*q0] = B[j0][q0]
+  r4<T, 0, 4, 8, 12>(re, im);
+  r4<T, 1, 5, 9, 13>(re, im);
+  r4<T, 2, 6, 10, 14>(re, im);
+  r4<T, 3, 7, 11, 15>(re, im);
+  // twiddle B[j0][q0] *= W16^(j0*q0)
+  cmul<T>(re[5], im[5], c1, -s1);           // j0=1,q0=1 : W16^1
+  mul_w8_1<T>(re[9], im[9]);                // j0=1,q0=2 : W16^2
+  cmul<T>(re[13], im[13], s1, -c1);         // j0=1,q0=3 : W16^3
+  mul_w8_1<T>(re[6], im[6]);                // j0=2,q0=1 : W16^2
+  mul_mi<T>(re[10], im[10]);                // j0=2,q0=2 : W16^4
+  mul_w8_3<T>(re[14], im[14]);              // j0=2,q0=3 : W16^6
+  cmul<T>(re[7], im[7], s1, -c1);           // j0=3,q0=1 : W16^3
+  mul_w8_3<T>(re[11], im[11]);              // j0=3,q0=2 : W16^6
+  cmul<T>(re[15], im[15], -c1, s1);         // j0=3,q0=3 : W16^9
+  // stage B: over j0; a[4*q0 + q1] = A[q0 + 4*q1]
+  r4<T, 0, 1, 2, 3>(re, im);
+  r4<T, 4, 5, 6, 7>(re, im);
+  r4<T, 8, 9, 10, 11>(re, im);
+  r4<T, 12, 13, 14, 15>(re, im);
+  // 4x4 transpose to natural order
+  swp<T, 1, 4>(re, im);  swp<T, 2, 8>(re, im);  swp<T, 3, 12>(re, im);
+  swp<T, 6, 9>(re, im);  swp<T, 7, 13>(re, im); swp<T, 11, 14>(re, im);
+}
+
+// R-point DFTs (R = 2, 4, 8) over registers [O, O+R), natural order in and out.
+template <typename T, int R, int O> struct DftSmall;
+template <typename T, int O> struct DftSmall<T, 2, O> {
+  static __device__ __forceinline__ void run(T (&re)[16], T (&im)[16]) {
+    T ar = re[O] + re[O + 1], ai = im[O] + im[O + 1];
+    T br = re[O] - re[O + 1], bi = im[O] - im[O + 1];
+    re[O] = ar; im[O] = ai; re[O + 1] = br; im[O + 1] = bi;
+  }
+};
+template <typename T, int O> struct DftSmall<T, 4, O> {
+  static __device__ __forceinline__ void run(T (&re)[16], T (&im)[16]) { r4<T, O, O + 1, O + 2, O + 3>(re, im); }
+};
+template <typename T, int O> struct DftSmall<T, 8, O> {
+  static __device__ __forceinline__ void run(T (&re)[16], T (&im)[16]) {
+    // DIF radix-2 split: u_j = a_j + a_{j+4} (even outputs), v_j = (a_j - a_{j+4}) W8^j (odd outputs)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      T ur = re[O + j] + re[O + j + 4], ui = im[O + j] + im[O + j + 4];
+      T vr = re[O + j] - re[O + j + 4], vi = im[O + j] - im[O + j + 4];
+      re[O + j] = ur; im[O + j] = ui; re[O + j + 4] = vr; im[O + j + 4] = vi;
+    }
+    mul_w8_1<T>(re[O + 5], im[O + 5]);
+    mul_mi<T>(re[O + 6], im[O + 6]);
+    mul_w8_3<T>(re[O + 7], im[O + 7]);
+    r4<T, O, O + 1, O + 2, O + 3>(re, im);          // X[2m]   at O+m
+    r4<T, O + 4, O + 5, O + 6, O + 7>(re, im);      // X[2m+1] at O+4+m
+    // interleave: out[2m] = a[m], out[2m+1] = a[4+m]  -> permutation (0 2 4 6 1 3 5 7)^-1
+    T r1 = re[O + 1], r2 = re[O + 2], r3 = re[O + 3], r4_ = re[O + 4], r5 = re[O + 5], r6 = re[O + 6];
+    T i1 = im[O + 1], i2 = im[O + 2], i3 = im[O + 3], i4_ = im[O + 4], i5 = im[O + 5], i6 = im[O + 6];
+    re[O + 1] = r4_; im[O + 1] = i4_;
+    re[O + 2] = r1;  im[O + 2] = i1;
+    re[O + 3] = r5;  im[O + 3] = i5;
+    re[O + 4] = r2;  im[O + 4] = i2;
+    re[O + 5] = r6;  im[O + 5] = i6;
+    re[O + 6] = r3;  im[O + 6] = i3;
+  }
+};
+
+template <typename T, int R> __device__ __forceinline__ void dft_last(T (&re)[16], T (&im)[16]) {
+  if constexpr (R == 16) {
+    dft16<T>(re, im);
+  } else if constexpr (R == 8) {
+    DftSmall<T, 8, 0>::run(re, im); DftSmall<T, 8, 8>::run(re, im);
+  } else if constexpr (R == 4) {
+    DftSmall<T, 4, 0>::run(re, im); DftSmall<T, 4, 4>::run(re, im);
+    DftSmall<T, 4, 8>::run(re, im); DftSmall<T, 4, 12>::run(re, im);
+  } else {
+    DftSmall<T, 2, 0>::run(re, im);  DftSmall<T, 2, 2>::run(re, im);
+    DftSmall<T, 2, 4>::run(re, im);  DftSmall<T, 2, 6>::run(re, im);
+    DftSmall<T, 2, 8>::run(re, im);  DftSmall<T, 2, 10>::run(re, im);
+    DftSmall<T, 2, 12>::run(re, im); DftSmall<T, 2, 14>::run(re, im);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// compile-time plan for one (element type, size)
+// ---------------------------------------------------------------------------------------
+template <typename T, int LOG2N> struct Plan {
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int THREADS = N / 16;
+  static constexpr int NPASS = (LOG2N + 3) / 4;
+  static constexpr int R_LAST = (LOG2N % 4) ? (1 << (LOG2N % 4)) : 16;
+  static constexpr int NB_LAST = 16 / R_LAST;          // butterflies per thread in the last pass
+  static constexpr int REV_DIGITS = NPASS - 1;         // hex digits reversed in the last pass
+  static constexpr bool WIDE = sizeof(T) == 8;         // 16-byte exchange elements
+  // padded exchange layout: phys(p) = p + PAD4*(p >> 4) + (p >> HB); table found by
+  // tools/fft_plan_model.py ("banks"): zero bank conflicts for every pass at every size.
+  static constexpr int PAD4 = (LOG2N == 12) ? 0 : ((LOG2N == 11 && WIDE) ? 0 : 1);
+  static constexpr int HB = (LOG2N <= 11) ? (WIDE ? 7 : 8) : (LOG2N == 12 ? 8 : LOG2N - 4);
+  static __host__ __device__ constexpr int phys(int p) { return p + PAD4 * (p >> 4) + (p >> HB); }
+  static constexpr int PHYS_SIZE = phys(N - 1) + 1;
+  // twiddle tables for passes 1..NPASS-2 live in shared memory: 16 * S_i entries each
+  static __host__ __device__ constexpr int len(int i) { return N >> (4 * i); }        // L_i
+  static __host__ __device__ constexpr int stride(int i) { return N >> (4 * i + 4); } // S_i (radix-16 pass)
+  static __host__ __device__ constexpr int tw_offset(int i) {   // entries before pass i's table
+    int o = 0;
+    for (int k = 0; k < i; ++k) o += len(k);
+    return o;
+  }
+  static constexpr int TW_TOTAL = tw_offset(NPASS - 1);          // all non-last passes
+  static constexpr int TW_SMEM = TW_TOTAL - N;                   // passes >= 1
+  static constexpr size_t SMEM_BYTES = (size_t)(PHYS_SIZE + (TW_SMEM > 0 ? TW_SMEM : 0)) * 2 * sizeof(T);
+};
+
+__host__ __device__ constexpr int hexrev(int v, int digits) {
+  int o = 0;
+  for (int d = 0; d < digits; ++d) { o = (o << 4) | (v & 15); v >>= 4; }
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------
+// epilogues: what happens to |X[k]|^2 of frame f, bin k (k already fftshift-ed)
+// ---------------------------------------------------------------------------------------
+enum : int { kModePower = 0, kModePsd = 1, kModeMag20 = 2 };
+
+struct EpiParams {
+  float* db_out;       // float32 [F][N]   (dB epilogue)
+  double* lin_out;     // float64 [F][N]   (linear epilogue)
+  double scale;        // 1 for power/mag20, 1/(fs*N) for psd
+  double floor;        // log floor
+  int mode;
+};
+
+// dB from linear power. T-typed so the float64 path adds the floor before narrowing.
+template <typename T> __device__ __forceinline__ float to_db(T p, const EpiParams& ep) {
+  const float kDbPerLog2 = 3.01029995663981195f;   // 10*log10(2)
+  if (ep.mode == kModeMag20) {
+    float m = sqrtf((float)p) + (float)ep.floor;
+    return 2.0f * kDbPerLog2 * lg2_approx(m);
+  }
+  T v = p * (T)ep.scale + (T)ep.floor;
+  return kDbPerLog2 * lg2_approx((float)v);
+}
+
+struct EpiDb {
+  template <typename T> static __device__ __forceinline__ void store(const EpiParams& ep, int64_t f, int n, int k, T p) {
+    ep.db_out[f * n + k] = to_db<T>(p, ep);
+  }
+};
+struct EpiLinear {
+  template <typename T> static __device__ __forceinline__ void store(const EpiParams& ep, int64_t f, int n, int k, T p) {
+    ep.lin_out[f * n + k] = (double)p * ep.scale;
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// the fused kernel
+// ---------------------------------------------------------------------------------------
+template <typename T> struct FftArgs {
+  const float2* iq;            // complex64 input
+  int64_t n_frames;
+  int64_t frame_stride;        // in complex samples
+  const T* window;             // T[N], includes the (-1)^n fftshift factor
+  const typename CplxOf<T>::type* tw;   // twiddles for passes 0..NPASS-2, [pass][q][c]
+  const double2* dc;           // optional per-frame DC estimate to subtract (hackrf path) or nullptr
+  const typename CplxOf<T>::type* in_ct;   // TAIL kernels: complex T input [n_frames][N] (no window)
+  EpiParams ep;
+};
+
+// TAIL = 0: the whole transform (complex64 frames in, window applied).
+// TAIL = 1: second kernel of the two-kernel large-FFT path: "frame" g is sub-transform
+//           s2 = g & 255 of big frame g >> 8 (input complex T from big_head_kernel's scratch);
+//           bin klow of it is bin (s2 >> 4) + 16*(s2 & 15) + 256*klow of the 256*N-point frame.
+// TAIL = 2: same input, rows left in the permuted [g][klow] order (coalesced stores).
+template <typename T, int LOG2N, typename Epi, bool PERSIST_TW, int MIN_CTAS, int TAIL>
+__global__ void __launch_bounds__(Plan<T, LOG2N>::THREADS, MIN_CTAS)
+fft_fused_kernel(const FftArgs<T> a) {
+  using P = Plan<T, LOG2N>;
+  using CT = typename CplxOf<T>::type;
+  constexpr int N = P::N, TH = P::THREADS, NPASS = P::NPASS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CT* ex = reinterpret_cast<CT*>(smem_raw);
+  CT* tws = ex + P::PHYS_SIZE;   // pass >= 1 twiddles
+
+  const int t = threadIdx.x;
+
+  // one-time: stage the small (pass >= 1) twiddle tables in shared memory
+  if constexpr (P::TW_SMEM > 0) {
+    for (int i = t; i < P::TW_SMEM; i += TH) tws[i] = a.tw[N + i];
+  }
+  // one-time: per-thread constants that do not change from frame to frame
+  T win[16];
+  T tw0r[PERSIST_TW ? 16 : 1], tw0i[PERSIST_TW ? 16 : 1];
+  if constexpr (PERSIST_TW) {
+    if constexpr (TAIL == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) win[j] = a.window[t + j * TH];
+    }
+#pragma unroll
+    for (int q = 1; q < 16; ++q) { CT w = a.tw[q * TH + t]; tw0r[q] = w.x; tw0i[q] = w.y; }
+  }
+  if constexpr (P::TW_SMEM > 0) __syncthreads();
+
+  for (int64_t f = blockIdx.x; f < a.n_frames; f += gridDim.x) {
+    T re[16], im[16];
+    // ---- pass 0: global -> registers, window, radix-16, twiddle ------------------------
+    if constexpr (TAIL != 0) {
+      const CT* src = a.in_ct + f * N + t;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { const CT x = src[j * TH]; re[j] = x.x; im[j] = x.y; }
+    } else {
+      const float2* src = a.iq + f * a.frame_stride + t;
+      float2 v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = ldg_stream(src + j * TH);
+      T dcr = T(0), dci = T(0);
+      if (a.dc != nullptr) { double2 d = a.dc[f]; dcr = (T)d.x; dci = (T)d.y; }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        T w;
+        if constexpr (PERSIST_TW) w = win[j]; else w = a.window[t + j * TH];
+        re[j] = ((T)v[j].x - dcr) * w;
+        im[j] = ((T)v[j].y - dci) * w;
+      }
+    }
+    dft16<T>(re, im);
+    if constexpr (NPASS > 1) {
+#pragma unroll
+      for (int q = 1; q < 16; ++q) {
+        T wr, wi;
+        if constexpr (PERSIST_TW) { wr = tw0r[q]; wi = tw0i[q]; }
+        else { CT w = a.tw[q * TH + t]; wr = w.x; wi = w.y; }
+        cmul<T>(re[q], im[q], wr, wi);
+      }
+      {
+        const int pb = P::phys(t);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) ex[pb + P::phys(q * TH)] = mk<T>(re[q], im[q]);
+      }
+      __syncthreads();
+      // ---- middle passes (radix 16, in place, one butterfly per thread) -----------------
+#pragma unroll
+      for (int i = 1; i < NPASS - 1; ++i) {
+        constexpr int dummy = 0; (void)dummy;
+        const int L = N >> (4 * i), S = N >> (4 * i + 4);
+        const int c = t & (S - 1), s = t / S;
+        const int pb = P::phys(s * L + c);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { CT x = ex[pb + P::phys(j * S)]; re[j] = x.x; im[j] = x.y; }
+        dft16<T>(re, im);
+        const CT* twi = tws + (P::tw_offset(i) - N);
+#pragma unroll
+        for (int q = 1; q < 16; ++q) { CT w = twi[q * S + c]; cmul<T>(re[q], im[q], w.x, w.y); }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) ex[pb + P::phys(q * S)] = mk<T>(re[q], im[q]);
+        __syncthreads();
+      }
+      // ---- last pass: radix R_LAST, NB_LAST butterflies per thread, digit-reversed reads --
+      constexpr int R = P::R_LAST, NB = P::NB_LAST;
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+        const int b = t + TH * u;
+        const int pb = P::phys(hexrev(b, P::REV_DIGITS) * R);
+#pragma unroll
+        for (int j = 0; j < R; ++j) { CT x = ex[pb + P::phys(j)]; re[u * R + j] = x.x; im[u * R + j] = x.y; }
+      }
+      dft_last<T, R>(re, im);
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          const int k = t + TH * u + (N / R) * q;
+          const int e = u * R + q;
+          const T pw = re[e] * re[e] + im[e] * im[e];
+          if constexpr (TAIL == 1) {
+            const int s2 = (int)(f & 255);
+            Epi::template store<T>(a.ep, f >> 8, N * 256, (s2 >> 4) + 16 * (s2 & 15) + 256 * k, pw);
+          } else {
+            Epi::template store<T>(a.ep, f, N, k, pw);
+          }
+        }
+      }
+      __syncthreads();   // exchange buffer is reused by the next frame's pass 0
+    }
+  }
+}
+
+}  // namespace tdsa

@@ -1,0 +1,25 @@
+// float64 instantiations of the fused kernel (the reference's arithmetic; strict parity path).
+#include "tdsa_launch.cuh"
+namespace tdsa {
+cudaError_t launch_fft_f64(int log2n, int epi, const FftArgs<double>& a, int sm, cudaStream_t s, LaunchInfo* info, bool dry) {
+  return launch_fft_impl<double>(log2n, epi, a, sm, s, info, dry);
+}
+}  // namespace tdsa
+
+#include "tdsa_big.cuh"
+namespace tdsa {
+cudaError_t launch_big_head_f64(const BigArgs<double>& a, int sm, cudaStream_t s) {
+  constexpr int kSmem = 4096 * 2 * sizeof(double);
+  static bool once = false;
+  if (!once) {
+    cudaError_t e = cudaFuncSetAttribute(big_head_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return e;
+    once = true;
+  }
+  const int64_t work = a.n_frames * (((int64_t)1 << a.log2n) >> 12);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(work, (int64_t)sm * 2));
+  big_head_kernel<double><<<grid, 256, kSmem, s>>>(a);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+}  // namespace tdsa

@@ -1,0 +1,94 @@
+// tdsa_launch.cuh — host-side dispatch of fft_fused_kernel over (size, epilogue).
+#pragma once
+#include <algorithm>
+#include <atomic>
+
+#include "tdsa_fft.cuh"
+
+namespace tdsa {
+
+enum : int { kEpiDb = 0, kEpiLinear = 1, kEpiDbTail = 2, kEpiLinearTail = 3, kEpiLinearPermuted = 4 };
+
+struct LaunchInfo {
+  int threads = 0;
+  int smem = 0;
+  int ctas_per_sm = 0;
+  int grid = 0;
+};
+
+extern std::atomic<int64_t> g_launch_count;
+
+// Largest single-CTA size per element type (shared-memory bound): f32 2^14, f64 2^13.
+template <typename T> struct MaxLog2 { static constexpr int value = sizeof(T) == 4 ? 14 : 13; };
+constexpr int kMinLog2 = 6;
+
+template <typename T, int LOG2N, typename Epi, int TAIL>
+cudaError_t launch_one(const FftArgs<T>& a, int sm_count, cudaStream_t stream, LaunchInfo* info, bool dry) {
+  using P = Plan<T, LOG2N>;
+  // float32: window and pass-0 twiddles stay in registers across frames (47 registers);
+  // float64 would need 94, so that path reads them through L1/L2 instead.
+  constexpr bool kPersist = sizeof(T) == 4 && P::THREADS <= 512;
+  constexpr int kMinCtas = (P::THREADS >= 512) ? 1 : 2;
+  auto kern = fft_fused_kernel<T, LOG2N, Epi, kPersist, kMinCtas, TAIL>;
+  static int occ = -1;          // per instantiation, per process (single device type)
+  if (occ < 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    int o = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, P::THREADS, P::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    occ = std::max(o, 1);
+  }
+  const int64_t want = (int64_t)sm_count * occ;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.n_frames, want));
+  if (info) { info->threads = P::THREADS; info->smem = (int)P::SMEM_BYTES; info->ctas_per_sm = occ; info->grid = grid; }
+  if (dry || a.n_frames <= 0) return cudaSuccess;
+  kern<<<grid, P::THREADS, P::SMEM_BYTES, stream>>>(a);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return cudaGetLastError();
+}
+
+// Tail kernels exist for inner sizes 2^6 .. 2^12 (N = 2^14 .. 2^20).
+constexpr int kMaxTailLog2 = 12;
+
+template <typename T, int LOG2N>
+cudaError_t launch_epi(int epi, const FftArgs<T>& a, int sm_count, cudaStream_t stream, LaunchInfo* info, bool dry) {
+  switch (epi) {
+    case kEpiDb: return launch_one<T, LOG2N, EpiDb, 0>(a, sm_count, stream, info, dry);
+    case kEpiLinear: return launch_one<T, LOG2N, EpiLinear, 0>(a, sm_count, stream, info, dry);
+    default: break;
+  }
+  if constexpr (LOG2N <= kMaxTailLog2) {
+    switch (epi) {
+      case kEpiDbTail: return launch_one<T, LOG2N, EpiDb, 1>(a, sm_count, stream, info, dry);
+      case kEpiLinearTail: return launch_one<T, LOG2N, EpiLinear, 1>(a, sm_count, stream, info, dry);
+      case kEpiLinearPermuted: return launch_one<T, LOG2N, EpiLinear, 2>(a, sm_count, stream, info, dry);
+      default: break;
+    }
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <typename T, int LOG2N> struct Dispatch {
+  static cudaError_t run(int log2n, int epi, const FftArgs<T>& a, int sm, cudaStream_t s, LaunchInfo* info, bool dry) {
+    if (log2n == LOG2N) return launch_epi<T, LOG2N>(epi, a, sm, s, info, dry);
+    if constexpr (LOG2N < MaxLog2<T>::value) return Dispatch<T, LOG2N + 1>::run(log2n, epi, a, sm, s, info, dry);
+    return cudaErrorInvalidValue;
+  }
+};
+
+template <typename T>
+cudaError_t launch_fft_impl(int log2n, int epi, const FftArgs<T>& a, int sm, cudaStream_t s, LaunchInfo* info, bool dry) {
+  if (log2n < kMinLog2 || log2n > MaxLog2<T>::value) return cudaErrorInvalidValue;
+  return Dispatch<T, kMinLog2>::run(log2n, epi, a, sm, s, info, dry);
+}
+
+// defined in tdsa_fft_f32.cu / tdsa_fft_f64.cu
+cudaError_t launch_fft_f32(int log2n, int epi, const FftArgs<float>& a, int sm, cudaStream_t s, LaunchInfo* info, bool dry);
+cudaError_t launch_fft_f64(int log2n, int epi, const FftArgs<double>& a, int sm, cudaStream_t s, LaunchInfo* info, bool dry);
+// head kernel of the two-kernel path (tdsa_big.cuh), defined next to the matching precision
+template <typename T> struct BigArgs;
+cudaError_t launch_big_head_f32(const BigArgs<float>& a, int sm, cudaStream_t s);
+cudaError_t launch_big_head_f64(const BigArgs<double>& a, int sm, cudaStream_t s);
+
+}  // namespace tdsa

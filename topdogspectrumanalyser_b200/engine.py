@@ -1,0 +1,301 @@
+"""Host-side wrapper over the C ABI: torch tensors are only the device-memory container.
+
+``SpectrumPlan`` owns one ``tdsa_handle_t``; every method hands ``data_ptr()``s and the
+current CUDA stream to libtdsa.so.  No arithmetic of the hot path happens in Python or
+in torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+# utils/constants.py:152-155 of the reference
+LOG_FLOOR = 1e-12
+POWER_LOG_FLOOR = 1e-10
+
+
+def default_floor(mode: str) -> float:
+    return POWER_LOG_FLOOR if mode == "power" else LOG_FLOOR
+
+
+def numpy_window(name: str, n: int, norm: str = "none") -> np.ndarray:
+    """The float64 table the reference would build (rtl_samples.py:199-206, hackrf_samples.py:311-316)."""
+    name = name.lower()
+    fn = {"hanning": np.hanning, "hann": np.hanning, "hamming": np.hamming, "rectangle": np.ones,
+          "rect": np.ones, "blackman": np.blackman}.get(name, np.hanning)
+    w = fn(n)
+    if norm == "rms":
+        w32 = w.astype(np.float32)
+        w32 /= np.sqrt(np.mean(w32 ** 2))
+        return w32.astype(np.float64)
+    return np.asarray(w, dtype=np.float64)
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise L.TdsaError("topdogspectrumanalyser_b200 needs a CUDA device (B200); there is no CPU fallback")
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+@dataclass
+class TraceState:
+    """Device-resident trace state: TraceAverager buffer + max/min hold rows.
+
+    Mirrors ``TraceAverager._buffer/_count`` (utils/signal_processing.py:15-17) and
+    ``mw.max_power_levels / mw.min_power_levels`` (core/display_data_processor.py:371-395).
+    """
+    width: int
+    device: torch.device
+    avg_mode: str = "off"
+    avg_n: int = 1
+    max_hold_enabled: bool = False
+    min_hold_enabled: bool = False
+    avg: torch.Tensor = field(init=False)
+    max_hold: torch.Tensor = field(init=False)
+    min_hold: torch.Tensor = field(init=False)
+    count: C.c_int32 = field(init=False)
+    valid: C.Array = field(init=False)
+
+    def __post_init__(self):
+        self.avg = torch.zeros(self.width, dtype=torch.float64, device=self.device)
+        self.max_hold = torch.zeros(self.width, dtype=torch.float32, device=self.device)
+        self.min_hold = torch.zeros(self.width, dtype=torch.float32, device=self.device)
+        self.count = C.c_int32(0)
+        self.valid = (C.c_int32 * 2)(0, 0)
+
+    def set_averaging(self, mode: str, n: int) -> None:       # TraceAverager.set_mode, :19-28
+        self.avg_mode, self.avg_n = mode, max(1, int(n))
+        self.reset_averaging()
+
+    def reset_averaging(self) -> None:                        # TraceAverager.reset, :30-33
+        self.count.value = 0
+
+    def clear_holds(self) -> None:
+        self.valid[0] = 0
+        self.valid[1] = 0
+
+    @property
+    def averaging(self) -> bool:                              # TraceAverager.is_active, :63-65
+        return self.avg_mode != "off" and self.avg_n > 1
+
+
+class SpectrumPlan:
+    """One FFT size on one GPU. Thread-compatible, like the reference's data sources."""
+
+    def __init__(self, n_fft: int, window: str = "hanning", window_norm: str = "none", mode: str = "power",
+                 log_floor: Optional[float] = None, fs: float = 1.0, precision: str = "f64",
+                 device: Optional[torch.device] = None):
+        _require_cuda()
+        self.lib = L.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.n_fft = int(n_fft)
+        self.mode = mode
+        self.fs = float(fs)
+        self.log_floor = default_floor(mode) if log_floor is None else float(log_floor)
+        self.precision = precision
+        self.window_name, self.window_norm = window, window_norm
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.tdsa_create(self.n_fft, L.WINDOW_RECT, L.NORM_NONE, L.MODE_IDS[mode], self.log_floor,
+                                         self.fs, L.PREC_IDS[precision], C.byref(self._h)))
+        self.set_window(window, window_norm)
+
+    # ---- configuration -----------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.tdsa_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_window(self, window: str, norm: str = "none") -> None:
+        """Install numpy's own table so the window is bit-identical to the reference's."""
+        self.window_name, self.window_norm = window, norm
+        w = np.ascontiguousarray(numpy_window(window, self.n_fft, norm))
+        L.check(self.lib.tdsa_set_window_table_host(self._h, w.ctypes.data))
+
+    def set_window_builtin(self, window: str, norm: str = "none") -> None:
+        """Use the library's own C implementation of the window (no numpy on the path)."""
+        L.check(self.lib.tdsa_set_window(self._h, L.WINDOW_IDS[window.lower()],
+                                         L.NORM_RMS_F32 if norm == "rms" else L.NORM_NONE))
+
+    def window_table(self) -> np.ndarray:
+        w = np.empty(self.n_fft, dtype=np.float64)
+        L.check(self.lib.tdsa_get_window_table_host(self._h, w.ctypes.data))
+        return w
+
+    def set_mode(self, mode: str, log_floor: Optional[float] = None, fs: Optional[float] = None) -> None:
+        self.mode = mode
+        self.log_floor = default_floor(mode) if log_floor is None else float(log_floor)
+        if fs is not None:
+            self.fs = float(fs)
+        L.check(self.lib.tdsa_set_mode(self._h, L.MODE_IDS[mode], self.log_floor, self.fs))
+
+    def set_precision(self, precision: str) -> None:
+        self.precision = precision
+        L.check(self.lib.tdsa_set_precision(self._h, L.PREC_IDS[precision]))
+
+    def info(self) -> dict:
+        v = [C.c_int32() for _ in range(5)]
+        L.check(self.lib.tdsa_plan_info(self._h, *[C.byref(x) for x in v]))
+        keys = ("n_fft", "threads_per_cta", "ctas_per_sm", "smem_bytes", "grid")
+        return dict(zip(keys, (int(x.value) for x in v)))
+
+    # ---- helpers -----------------------------------------------------------------------
+    def _bind(self) -> None:
+        L.check(self.lib.tdsa_set_stream(self._h, _stream_ptr()))
+
+    def _frames(self, iq: torch.Tensor, n_frames, frame_stride):
+        if iq.dtype != torch.complex64 or not iq.is_cuda or not iq.is_contiguous():
+            raise ValueError("iq must be a contiguous complex64 CUDA tensor")
+        if n_frames is None:
+            if iq.dim() != 2 or iq.shape[1] != self.n_fft:
+                raise ValueError(f"iq must be [B, {self.n_fft}] (or pass n_frames/frame_stride for a flat stream)")
+            return int(iq.shape[0]), self.n_fft
+        stride = self.n_fft if frame_stride is None else int(frame_stride)
+        if (n_frames - 1) * stride + self.n_fft > iq.numel():
+            raise ValueError("frames run past the end of iq")
+        return int(n_frames), stride
+
+    # ---- kernel 1 ----------------------------------------------------------------------
+    def psd_db(self, iq: torch.Tensor, out: Optional[torch.Tensor] = None, n_frames: Optional[int] = None,
+               frame_stride: Optional[int] = None) -> torch.Tensor:
+        """dB rows ``float32 [B, N]`` of fftshift(FFT(iq*window)) — rtl_samples.py:169-184 per row."""
+        b, stride = self._frames(iq, n_frames, frame_stride)
+        if out is None:
+            out = torch.empty((b, self.n_fft), dtype=torch.float32, device=iq.device)
+        self._bind()
+        L.check(self.lib.tdsa_psd_db_batch(self._h, iq.data_ptr(), b, stride, out.data_ptr()))
+        return out
+
+    def power_linear(self, iq: torch.Tensor, out: Optional[torch.Tensor] = None, n_frames: Optional[int] = None,
+                     frame_stride: Optional[int] = None) -> torch.Tensor:
+        b, stride = self._frames(iq, n_frames, frame_stride)
+        if out is None:
+            out = torch.empty((b, self.n_fft), dtype=torch.float64, device=iq.device)
+        self._bind()
+        L.check(self.lib.tdsa_power_linear_batch(self._h, iq.data_ptr(), b, stride, out.data_ptr()))
+        return out
+
+    def psd_db_dc(self, iq: torch.Tensor, dc_state: torch.Tensor, dc_alpha: float = 1.0,
+                  out: Optional[torch.Tensor] = None):
+        """HackRF-style front end (hackrf_samples.py:351-368). Returns ``(db, silent_flags)``."""
+        b, stride = self._frames(iq, None, None)
+        if out is None:
+            out = torch.empty((b, self.n_fft), dtype=torch.float32, device=iq.device)
+        silent = torch.empty(b, dtype=torch.int32, device=iq.device)
+        self._bind()
+        L.check(self.lib.tdsa_psd_db_batch_dc(self._h, iq.data_ptr(), b, stride, float(dc_alpha), dc_state.data_ptr(),
+                                              silent.data_ptr(), out.data_ptr()))
+        return out, silent
+
+    def psd_db_avg_hold(self, iq: torch.Tensor, state: TraceState, last_only: bool = False,
+                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Frames folded into the running trace state (averager + holds) on the device."""
+        b, stride = self._frames(iq, None, None)
+        rows = 1 if last_only else b
+        if out is None:
+            out = torch.empty((rows, self.n_fft), dtype=torch.float32, device=iq.device)
+        self._bind()
+        L.check(self.lib.tdsa_psd_db_avg_hold(
+            self._h, iq.data_ptr(), b, stride, L.AVG_IDS[state.avg_mode], state.avg_n, state.avg.data_ptr(),
+            C.byref(state.count), state.max_hold.data_ptr() if state.max_hold_enabled else None,
+            state.min_hold.data_ptr() if state.min_hold_enabled else None, state.valid, int(last_only), out.data_ptr()))
+        return out
+
+    def welch(self, stream: torch.Tensor, hop: int):
+        """Config 3: ``(avg_db, peak_db)`` over overlapping segments of a flat complex64 stream."""
+        if stream.dtype != torch.complex64 or not stream.is_cuda or not stream.is_contiguous():
+            raise ValueError("stream must be a contiguous complex64 CUDA tensor")
+        avg = torch.empty(self.n_fft, dtype=torch.float32, device=stream.device)
+        peak = torch.empty(self.n_fft, dtype=torch.float32, device=stream.device)
+        self._bind()
+        L.check(self.lib.tdsa_welch(self._h, stream.data_ptr(), stream.numel(), int(hop), avg.data_ptr(), peak.data_ptr()))
+        return avg, peak
+
+    # ---- host-buffer entry point (what the data source calls) ----------------------------
+    def psd_db_host(self, iq_host: np.ndarray, out_host: Optional[np.ndarray] = None,
+                    chunk_frames: int = 0) -> np.ndarray:
+        """complex64 host frames -> float32 host dB rows; H2D, kernel and D2H are pipelined in the library."""
+        if iq_host.dtype != np.complex64 or not iq_host.flags.c_contiguous or iq_host.ndim != 2 \
+                or iq_host.shape[1] != self.n_fft:
+            raise ValueError(f"iq_host must be C-contiguous complex64 [B, {self.n_fft}]")
+        b = iq_host.shape[0]
+        if out_host is None:
+            out_host = np.empty((b, self.n_fft), dtype=np.float32)
+        self._bind()
+        with torch.cuda.device(self.device):
+            L.check(self.lib.tdsa_psd_db_batch_host(self._h, iq_host.ctypes.data, b, self.n_fft,
+                                                    out_host.ctypes.data, int(chunk_frames)))
+        return out_host
+
+
+# ---- plan-free operators -------------------------------------------------------------------
+def trace_update(rows: torch.Tensor, state: TraceState, cal_offset_db: float = 0.0,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Device-resident DataProcessor state on dB rows (display_data_processor.py:211-218,317-327,371-395)."""
+    _require_cuda()
+    lib = L.load()
+    if rows.dtype != torch.float32 or not rows.is_cuda or not rows.is_contiguous() or rows.dim() != 2:
+        raise ValueError("rows must be contiguous float32 CUDA [R, W]")
+    r, w = rows.shape
+    if out is None:
+        out = torch.empty_like(rows)
+    flags = torch.empty(max(r, 1), dtype=torch.int32, device=rows.device)
+    L.check(lib.tdsa_trace_update(rows.data_ptr(), r, w, float(cal_offset_db), L.AVG_IDS[state.avg_mode], state.avg_n,
+                                  state.avg.data_ptr(), C.byref(state.count),
+                                  state.max_hold.data_ptr() if state.max_hold_enabled else None,
+                                  state.min_hold.data_ptr() if state.min_hold_enabled else None, state.valid,
+                                  out.data_ptr(), _stream_ptr(), flags.data_ptr()))
+    return out
+
+
+def stitch(rows: torch.Tensor, row_lo_hz: torch.Tensor, row_hz: float, start_hz: float, stop_hz: float,
+           m: int) -> torch.Tensor:
+    """hackrf_sweep stitch on the device (datasources/hackrf_sweep.py:150-166)."""
+    _require_cuda()
+    lib = L.load()
+    if rows.dtype != torch.float32 or row_lo_hz.dtype != torch.float64:
+        raise ValueError("rows float32 [R, K], row_lo_hz float64 [R]")
+    rows, row_lo_hz = rows.contiguous(), row_lo_hz.contiguous()
+    r, k = rows.shape
+    out = torch.empty(m, dtype=torch.float64, device=rows.device)
+    order = torch.empty(r, dtype=torch.int32, device=rows.device)
+    L.check(lib.tdsa_stitch(rows.data_ptr(), row_lo_hz.data_ptr(), float(row_hz), r, k, float(start_hz),
+                            float(stop_hz), int(m), out.data_ptr(), _stream_ptr(), order.data_ptr()))
+    return out
+
+
+class WaterfallRing:
+    """Device history ring with the widget's semantics (displays/waterfall.py:163-180)."""
+
+    def __init__(self, h: int, w: int, fill: float, device):
+        _require_cuda()
+        self.lib = L.load()
+        self.h, self.w = int(h), int(w)
+        self.buf = torch.full((2 * self.h, self.w), float(fill), dtype=torch.float32, device=device)
+        self.ptr = C.c_int64(0)
+
+    def push(self, rows: torch.Tensor) -> None:
+        rows = rows.reshape(-1, self.w)
+        if rows.dtype != torch.float32 or not rows.is_contiguous():
+            raise ValueError("rows must be contiguous float32")
+        L.check(self.lib.tdsa_ring_push(rows.data_ptr(), rows.shape[0], self.buf.data_ptr(), self.h, self.w,
+                                        C.byref(self.ptr), _stream_ptr()))
+
+    def view(self) -> torch.Tensor:
+        p = int(self.ptr.value)
+        return self.buf[p:p + self.h]

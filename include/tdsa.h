@@ -132,6 +132,14 @@ int tdsa_psd_db_avg_hold(tdsa_handle_t h, const void* iq, int64_t n_frames, int6
                          float* max_hold, float* min_hold, int32_t* hold_valid_host, int last_only,
                          float* db_out);
 
+/* tdsa_psd_db_avg_hold with the HackRF front end of tdsa_psd_db_batch_dc in front of it
+ * (hackrf_samples.py:351-381): silent frames update nothing and repeat the previous row;
+ * silent_out: device int32[n_frames]. Synchronises the stream once per chunk (reads the flags). */
+int tdsa_psd_db_avg_hold_dc(tdsa_handle_t h, const void* iq, int64_t n_frames, int64_t frame_stride,
+                            double dc_alpha, double* dc_state, int32_t* silent_out, int avg_mode, int avg_n,
+                            double* avg_state, int32_t* count_state_host, float* max_hold,
+                            float* min_hold, int32_t* hold_valid_host, int last_only, float* db_out);
+
 /* Config 3: Welch average + peak hold over a flat IQ stream:
  * segments s = 0 .. floor((n_samples - n_fft)/hop), each transformed as kernel 1;
  * avg_db = 10*log10(mean_s |X_s|^2 + floor) (TraceAverager 'lin' with n >= nseg,

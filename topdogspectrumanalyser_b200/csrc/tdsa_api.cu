@@ -363,7 +363,8 @@ int tdsa_psd_db_batch_dc(tdsa_handle_t p, const void* iq, int64_t n_frames, int6
   return run_fused(p, iq, n_frames, stride, dc, kEpiDb, db_out, nullptr, nullptr, false);
 }
 
-int tdsa_psd_db_avg_hold(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, int avg_mode, int avg_n,
+static int avg_hold_impl(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, bool with_dc,
+                         double dc_alpha, double* dc_state, int32_t* silent_out, int avg_mode, int avg_n,
                          double* avg_state, int32_t* count_state_host, float* max_hold, float* min_hold,
                          int32_t* hold_valid_host, int last_only, float* db_out) {
   int rc = check_batch(p, iq, n_frames, stride, db_out);
@@ -372,20 +373,47 @@ int tdsa_psd_db_avg_hold(tdsa_handle_t p, const void* iq, int64_t n_frames, int6
   if (averaging && (!avg_state || !count_state_host)) return fail(TDSA_ERR_INVALID, "averaging needs avg_state and count_state");
   if ((max_hold || min_hold) && !hold_valid_host) return fail(TDSA_ERR_INVALID, "holds need hold_valid");
   if (p->mode == TDSA_MODE_MAG20 && averaging) return fail(TDSA_ERR_INVALID, "mag20 branch is never averaged (hackrf_samples.py:378-383)");
+  if (with_dc && (!dc_state || !silent_out)) return fail(TDSA_ERR_INVALID, "dc path needs dc_state and silent_out");
   if (n_frames == 0) return TDSA_OK;
   // frames are folded in chunks so the float64 linear-power scratch stays bounded (<= 256 MiB)
   const int64_t chunk_max = std::max<int64_t>(1, ((int64_t)256 << 20) / ((int64_t)p->n * 8));
   int count = averaging ? *count_state_host : 0;
   int mxv = hold_valid_host ? hold_valid_host[0] : 0, mnv = hold_valid_host ? hold_valid_host[1] : 0;
+  std::vector<int32_t> silent_h;
   for (int64_t f0 = 0; f0 < n_frames; f0 += chunk_max) {
     const int64_t nf = std::min(chunk_max, n_frames - f0);
     rc = ensure_scratch(&p->scratch, &p->scratch_bytes, (size_t)nf * p->n * sizeof(double));
     if (rc) return rc;
     double* lin = (double*)p->scratch;
-    rc = run_fused(p, (const float2*)iq + f0 * stride, nf, stride, nullptr, kEpiLinear, nullptr, lin, nullptr, false);
+    const float2* src = (const float2*)iq + f0 * stride;
+    const double2* dc = nullptr;
+    int64_t live = nf;
+    if (with_dc) {
+      const size_t need = (size_t)nf * (sizeof(double2) * 2 + sizeof(double));
+      rc = ensure_scratch(&p->scratch2, &p->scratch2_bytes, need);
+      if (rc) return rc;
+      double2* mean = (double2*)p->scratch2;
+      double2* dcv = mean + nf;
+      double* pw = (double*)(dcv + nf);
+      const int grid = (int)std::min<int64_t>(nf, (int64_t)p->sm_count * 8);
+      frame_stats_kernel<<<grid, 256, 0, p->stream>>>(src, nf, stride, p->n, mean, pw);
+      count_launch();
+      dc_scan_kernel<<<1, 32, 0, p->stream>>>(mean, pw, nf, dc_alpha, dc_state, dcv, silent_out + f0);
+      count_launch();
+      CK(cudaGetLastError());
+      dc = dcv;
+      // the host-side scalars (count, valid) depend on how many frames were live
+      silent_h.resize(nf);
+      CK(cudaMemcpyAsync(silent_h.data(), silent_out + f0, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, p->stream));
+      CK(cudaStreamSynchronize(p->stream));
+      live = 0;
+      for (int32_t v : silent_h) live += v == 0;
+    }
+    rc = run_fused(p, src, nf, stride, dc, kEpiLinear, nullptr, lin, nullptr, false);
     if (rc) return rc;
     TraceScanArgs a;
-    a.lin = lin; a.n_frames = nf; a.width = p->n; a.avg_mode = avg_mode; a.avg_n = avg_n; a.count0 = count;
+    a.lin = lin; a.skip = with_dc ? silent_out + f0 : nullptr;
+    a.n_frames = nf; a.width = p->n; a.avg_mode = avg_mode; a.avg_n = avg_n; a.count0 = count;
     a.avg_state = avg_state; a.max_hold = max_hold; a.min_hold = min_hold; a.max_valid0 = mxv; a.min_valid0 = mnv;
     a.last_only = last_only;
     a.db_out = last_only ? db_out : db_out + f0 * p->n;
@@ -393,16 +421,33 @@ int tdsa_psd_db_avg_hold(tdsa_handle_t p, const void* iq, int64_t n_frames, int6
     trace_scan_kernel<<<(p->n + 255) / 256, 256, 0, p->stream>>>(a);
     count_launch();
     CK(cudaGetLastError());
-    if (averaging) {   // TraceAverager._count after nf more frames (signal_processing.py:46-58)
-      if (avg_mode == TDSA_AVG_LIN) count = (int)std::min<int64_t>((int64_t)avg_n, (int64_t)count + nf);
-      else count = std::max(count, 1);
+    if (live > 0) {
+      if (averaging) {   // TraceAverager._count after `live` more frames (signal_processing.py:46-58)
+        if (avg_mode == TDSA_AVG_LIN) count = (int)std::min<int64_t>((int64_t)avg_n, (int64_t)count + live);
+        else count = std::max(count, 1);
+      }
+      if (max_hold) mxv = 1;
+      if (min_hold) mnv = 1;
     }
-    if (max_hold) mxv = 1;
-    if (min_hold) mnv = 1;
   }
   if (averaging) *count_state_host = count;
   if (hold_valid_host) { hold_valid_host[0] = mxv; hold_valid_host[1] = mnv; }
   return TDSA_OK;
+}
+
+int tdsa_psd_db_avg_hold(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, int avg_mode, int avg_n,
+                         double* avg_state, int32_t* count_state_host, float* max_hold, float* min_hold,
+                         int32_t* hold_valid_host, int last_only, float* db_out) {
+  return avg_hold_impl(p, iq, n_frames, stride, false, 1.0, nullptr, nullptr, avg_mode, avg_n, avg_state,
+                       count_state_host, max_hold, min_hold, hold_valid_host, last_only, db_out);
+}
+
+int tdsa_psd_db_avg_hold_dc(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, double dc_alpha,
+                            double* dc_state, int32_t* silent_out, int avg_mode, int avg_n, double* avg_state,
+                            int32_t* count_state_host, float* max_hold, float* min_hold, int32_t* hold_valid_host,
+                            int last_only, float* db_out) {
+  return avg_hold_impl(p, iq, n_frames, stride, true, dc_alpha, dc_state, silent_out, avg_mode, avg_n, avg_state,
+                       count_state_host, max_hold, min_hold, hold_valid_host, last_only, db_out);
 }
 
 int tdsa_welch(tdsa_handle_t p, const void* iq_stream, int64_t n_samples, int64_t hop, float* avg_db, float* peak_db) {

@@ -69,6 +69,7 @@ __global__ void dc_scan_kernel(const double2* __restrict__ mean, const double* _
 // ---------------------------------------------------------------------------------------
 struct TraceScanArgs {
   const double* lin;       // [F][W] linear power (already scaled for PSD)
+  const int32_t* skip;     // [F] or null: frames flagged 1 leave all state untouched (hackrf silence hold)
   int64_t n_frames;
   int64_t width;
   int avg_mode;            // 0 off, 1 exp, 2 lin
@@ -96,7 +97,13 @@ __global__ void __launch_bounds__(256) trace_scan_kernel(const TraceScanArgs a) 
   float mn = (a.min_hold && mnv) ? a.min_hold[k] : 0.f;
   EpiParams ep;
   ep.db_out = nullptr; ep.lin_out = nullptr; ep.scale = 1.0; ep.floor = a.floor; ep.mode = a.mode;
+  float last_db = 0.0f;       // what a skipped frame repeats (hackrf_samples.py:351-355)
   for (int64_t f = 0; f < a.n_frames; ++f) {
+    if (a.skip != nullptr && a.skip[f]) {
+      if (!a.last_only) a.db_out[f * a.width + k] = last_db;
+      else if (f == a.n_frames - 1) a.db_out[k] = last_db;
+      continue;
+    }
     const double p = a.lin[f * a.width + k];
     double v = p;
     if (averaging) {
@@ -113,6 +120,7 @@ __global__ void __launch_bounds__(256) trace_scan_kernel(const TraceScanArgs a) 
       v = buf;
     }
     const float db = to_db<double>(v, ep);
+    last_db = db;
     if (!a.last_only) a.db_out[f * a.width + k] = db;
     else if (f == a.n_frames - 1) a.db_out[k] = db;
     if (a.max_hold) {

@@ -43,6 +43,38 @@ __device__ __forceinline__ float2 ldg_stream(const float2* p) {
   return v;
 }
 
+// ---- bulk-copy (TMA) staging: cp.async.bulk global -> shared, completion on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src_gmem), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <typename T> __device__ __forceinline__ void cmul(T& xr, T& xi, T wr, T wi) {
   T r = xr * wr - xi * wi;
   T i = xr * wi + xi * wr;
@@ -199,6 +231,12 @@ template <typename T, int LOG2N> struct Plan {
   static constexpr int TW_TOTAL = tw_offset(NPASS - 1);          // all non-last passes
   static constexpr int TW_SMEM = TW_TOTAL - N;                   // passes >= 1
   static constexpr size_t SMEM_BYTES = (size_t)(PHYS_SIZE + (TW_SMEM > 0 ? TW_SMEM : 0)) * 2 * sizeof(T);
+  // bulk-copy staging: NSTAGE buffers of one complex64 frame each + one mbarrier per stage
+  static constexpr size_t STAGE_BYTES = (size_t)N * 8;
+  static constexpr size_t STAGE_OFFSET = (SMEM_BYTES + 127) & ~(size_t)127;
+  static __host__ __device__ constexpr size_t smem_staged(int nstage) {
+    return STAGE_OFFSET + (size_t)nstage * STAGE_BYTES + 64;
+  }
 };
 
 __host__ __device__ constexpr int hexrev(int v, int digits) {
@@ -261,7 +299,10 @@ template <typename T> struct FftArgs {
 //           s2 = g & 255 of big frame g >> 8 (input complex T from big_head_kernel's scratch);
 //           bin klow of it is bin (s2 >> 4) + 16*(s2 & 15) + 256*klow of the 256*N-point frame.
 // TAIL = 2: same input, rows left in the permuted [g][klow] order (coalesced stores).
-template <typename T, int LOG2N, typename Epi, bool PERSIST_TW, int MIN_CTAS, int TAIL>
+// NSTAGE > 0 (TAIL == 0 only): frames are staged by cp.async.bulk into an NSTAGE-deep ring of
+//           shared-memory buffers, so frame i+NSTAGE streams in from HBM while frame i computes.
+//           Needs 16-byte aligned frames (even frame_stride); the launcher falls back to NSTAGE = 0.
+template <typename T, int LOG2N, typename Epi, bool PERSIST_TW, int MIN_CTAS, int TAIL, int NSTAGE>
 __global__ void __launch_bounds__(Plan<T, LOG2N>::THREADS, MIN_CTAS)
 fft_fused_kernel(const FftArgs<T> a) {
   using P = Plan<T, LOG2N>;
@@ -270,8 +311,28 @@ fft_fused_kernel(const FftArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CT* ex = reinterpret_cast<CT*>(smem_raw);
   CT* tws = ex + P::PHYS_SIZE;   // pass >= 1 twiddles
+  const float2* stage0 = reinterpret_cast<const float2*>(smem_raw + P::STAGE_OFFSET);
+  const uint32_t stage_u32 = smem_u32(smem_raw + P::STAGE_OFFSET);
+  const uint32_t bar_u32 = stage_u32 + (uint32_t)(NSTAGE * P::STAGE_BYTES);   // NSTAGE mbarriers behind the ring
+  (void)stage0; (void)bar_u32;
 
   const int t = threadIdx.x;
+  if constexpr (NSTAGE > 0) {
+    if (t == 0) {
+#pragma unroll
+      for (int s = 0; s < NSTAGE; ++s) mbar_init(bar_u32 + 8 * s, 1);
+      fence_mbar_init();
+#pragma unroll
+      for (int s = 0; s < NSTAGE; ++s) {
+        const int64_t fs = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+        if (fs < a.n_frames) {
+          mbar_arrive_expect_tx(bar_u32 + 8 * s, (uint32_t)P::STAGE_BYTES);
+          bulk_g2s(stage_u32 + (uint32_t)(s * P::STAGE_BYTES), a.iq + fs * a.frame_stride, (uint32_t)P::STAGE_BYTES,
+                   bar_u32 + 8 * s);
+        }
+      }
+    }
+  }
 
   // one-time: stage the small (pass >= 1) twiddle tables in shared memory
   if constexpr (P::TW_SMEM > 0) {
@@ -288,9 +349,10 @@ fft_fused_kernel(const FftArgs<T> a) {
 #pragma unroll
     for (int q = 1; q < 16; ++q) { CT w = a.tw[q * TH + t]; tw0r[q] = w.x; tw0i[q] = w.y; }
   }
-  if constexpr (P::TW_SMEM > 0) __syncthreads();
+  if constexpr (P::TW_SMEM > 0 || NSTAGE > 0) __syncthreads();   // tables staged, mbarriers initialised
 
-  for (int64_t f = blockIdx.x; f < a.n_frames; f += gridDim.x) {
+  int it = 0;   // frames this CTA has started (ring position)
+  for (int64_t f = blockIdx.x; f < a.n_frames; f += gridDim.x, ++it) {
     T re[16], im[16];
     // ---- pass 0: global -> registers, window, radix-16, twiddle ------------------------
     if constexpr (TAIL != 0) {
@@ -298,18 +360,28 @@ fft_fused_kernel(const FftArgs<T> a) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) { const CT x = src[j * TH]; re[j] = x.x; im[j] = x.y; }
     } else {
-      const float2* src = a.iq + f * a.frame_stride + t;
-      float2 v[16];
+      if constexpr (!PERSIST_TW) {          // issue the table loads before waiting on the frame
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = ldg_stream(src + j * TH);
+        for (int j = 0; j < 16; ++j) win[j] = a.window[t + j * TH];
+      }
       T dcr = T(0), dci = T(0);
       if (a.dc != nullptr) { double2 d = a.dc[f]; dcr = (T)d.x; dci = (T)d.y; }
+      float2 v[16];
+      if constexpr (NSTAGE > 0) {
+        const int stg = it % NSTAGE;
+        mbar_wait(bar_u32 + 8 * stg, (uint32_t)((it / NSTAGE) & 1));
+        const float2* src = stage0 + (size_t)stg * N + t;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = src[j * TH];
+      } else {
+        const float2* src = a.iq + f * a.frame_stride + t;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = ldg_stream(src + j * TH);
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        T w;
-        if constexpr (PERSIST_TW) w = win[j]; else w = a.window[t + j * TH];
-        re[j] = ((T)v[j].x - dcr) * w;
-        im[j] = ((T)v[j].y - dci) * w;
+        re[j] = ((T)v[j].x - dcr) * win[j];
+        im[j] = ((T)v[j].y - dci) * win[j];
       }
     }
     dft16<T>(re, im);
@@ -327,6 +399,19 @@ fft_fused_kernel(const FftArgs<T> a) {
         for (int q = 0; q < 16; ++q) ex[pb + P::phys(q * TH)] = mk<T>(re[q], im[q]);
       }
       __syncthreads();
+      if constexpr (NSTAGE > 0) {
+        // every thread has consumed this stage (its reads precede the barrier): refill it
+        if (t == 0) {
+          const int64_t fn = f + (int64_t)NSTAGE * gridDim.x;
+          if (fn < a.n_frames) {
+            const int stg = it % NSTAGE;
+            fence_proxy_async();
+            mbar_arrive_expect_tx(bar_u32 + 8 * stg, (uint32_t)P::STAGE_BYTES);
+            bulk_g2s(stage_u32 + (uint32_t)(stg * P::STAGE_BYTES), a.iq + fn * a.frame_stride, (uint32_t)P::STAGE_BYTES,
+                     bar_u32 + 8 * stg);
+          }
+        }
+      }
       // ---- middle passes (radix 16, in place, one butterfly per thread) -----------------
 #pragma unroll
       for (int i = 1; i < NPASS - 1; ++i) {

@@ -14,6 +14,7 @@ struct LaunchInfo {
   int smem = 0;
   int ctas_per_sm = 0;
   int grid = 0;
+  int stages = 0;
 };
 
 extern std::atomic<int64_t> g_launch_count;
@@ -22,28 +23,55 @@ extern std::atomic<int64_t> g_launch_count;
 template <typename T> struct MaxLog2 { static constexpr int value = sizeof(T) == 4 ? 14 : 13; };
 constexpr int kMinLog2 = 6;
 
+// How many staging buffers fit while keeping the CTAs/SM the register budget allows.
+template <typename T, int LOG2N> constexpr int pick_stages() {
+  using P = Plan<T, LOG2N>;
+  constexpr size_t kSmemPerSm = 227 * 1024;
+  constexpr int ctas = (P::THREADS >= 512) ? 1 : 2;
+  int best = 0;
+  if (LOG2N >= 9) {                            // tiny frames keep direct loads and many CTAs per SM
+    for (int st = 1; st <= (sizeof(T) == 4 ? 3 : 2); ++st)
+      if ((P::smem_staged(st) + 1024) * ctas <= kSmemPerSm) best = st;
+  }
+  return best;
+}
+
+template <typename T, int LOG2N, typename Epi, int TAIL, int NSTAGE>
+cudaError_t launch_staged(const FftArgs<T>& a, int sm_count, cudaStream_t stream, LaunchInfo* info, bool dry);
+
 template <typename T, int LOG2N, typename Epi, int TAIL>
 cudaError_t launch_one(const FftArgs<T>& a, int sm_count, cudaStream_t stream, LaunchInfo* info, bool dry) {
+  constexpr int kStages = (TAIL == 0) ? pick_stages<T, LOG2N>() : 0;
+  if constexpr (kStages > 0) {
+    const bool aligned = (((uintptr_t)a.iq & 15) == 0) && ((a.frame_stride & 1) == 0);
+    if (aligned || dry) return launch_staged<T, LOG2N, Epi, TAIL, kStages>(a, sm_count, stream, info, dry);
+  }
+  return launch_staged<T, LOG2N, Epi, TAIL, 0>(a, sm_count, stream, info, dry);
+}
+
+template <typename T, int LOG2N, typename Epi, int TAIL, int NSTAGE>
+cudaError_t launch_staged(const FftArgs<T>& a, int sm_count, cudaStream_t stream, LaunchInfo* info, bool dry) {
   using P = Plan<T, LOG2N>;
+  constexpr size_t kSmem = NSTAGE > 0 ? P::smem_staged(NSTAGE) : P::SMEM_BYTES;
   // float32: window and pass-0 twiddles stay in registers across frames (47 registers);
   // float64 would need 94, so that path reads them through L1/L2 instead.
   constexpr bool kPersist = sizeof(T) == 4 && P::THREADS <= 512;
   constexpr int kMinCtas = (P::THREADS >= 512) ? 1 : 2;
-  auto kern = fft_fused_kernel<T, LOG2N, Epi, kPersist, kMinCtas, TAIL>;
+  auto kern = fft_fused_kernel<T, LOG2N, Epi, kPersist, kMinCtas, TAIL, NSTAGE>;
   static int occ = -1;          // per instantiation, per process (single device type)
   if (occ < 0) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
     if (e != cudaSuccess) return e;
     int o = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, P::THREADS, P::SMEM_BYTES);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, P::THREADS, kSmem);
     if (e != cudaSuccess) return e;
     occ = std::max(o, 1);
   }
   const int64_t want = (int64_t)sm_count * occ;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.n_frames, want));
-  if (info) { info->threads = P::THREADS; info->smem = (int)P::SMEM_BYTES; info->ctas_per_sm = occ; info->grid = grid; }
+  if (info) { info->threads = P::THREADS; info->smem = (int)kSmem; info->ctas_per_sm = occ; info->grid = grid; info->stages = NSTAGE; }
   if (dry || a.n_frames <= 0) return cudaSuccess;
-  kern<<<grid, P::THREADS, P::SMEM_BYTES, stream>>>(a);
+  kern<<<grid, P::THREADS, kSmem, stream>>>(a);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }

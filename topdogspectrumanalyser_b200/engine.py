@@ -216,6 +216,22 @@ class SpectrumPlan:
             state.min_hold.data_ptr() if state.min_hold_enabled else None, state.valid, int(last_only), out.data_ptr()))
         return out
 
+    def psd_db_avg_hold_dc(self, iq: torch.Tensor, state: TraceState, dc_state: torch.Tensor, dc_alpha: float = 1.0,
+                           last_only: bool = False, out: Optional[torch.Tensor] = None):
+        """HackRF front end + trace state (hackrf_samples.py:351-381). Returns ``(db, silent_flags)``."""
+        b, stride = self._frames(iq, None, None)
+        rows = 1 if last_only else b
+        if out is None:
+            out = torch.empty((rows, self.n_fft), dtype=torch.float32, device=iq.device)
+        silent = torch.empty(b, dtype=torch.int32, device=iq.device)
+        self._bind()
+        L.check(self.lib.tdsa_psd_db_avg_hold_dc(
+            self._h, iq.data_ptr(), b, stride, float(dc_alpha), dc_state.data_ptr(), silent.data_ptr(),
+            L.AVG_IDS[state.avg_mode], state.avg_n, state.avg.data_ptr(), C.byref(state.count),
+            state.max_hold.data_ptr() if state.max_hold_enabled else None,
+            state.min_hold.data_ptr() if state.min_hold_enabled else None, state.valid, int(last_only), out.data_ptr()))
+        return out, silent
+
     def welch(self, stream: torch.Tensor, hop: int):
         """Config 3: ``(avg_db, peak_db)`` over overlapping segments of a flat complex64 stream."""
         if stream.dtype != torch.complex64 or not stream.is_cuda or not stream.is_contiguous():

@@ -140,6 +140,12 @@ int tdsa_psd_db_avg_hold_dc(tdsa_handle_t h, const void* iq, int64_t n_frames, i
                             double* avg_state, int32_t* count_state_host, float* max_hold,
                             float* min_hold, int32_t* hold_valid_host, int last_only, float* db_out);
 
+/* Config 4 (per sub-band rows): iq holds n_groups * frames_per_group contiguous frames; each
+ * group is averaged in the linear domain as TraceAverager('lin', n >= frames_per_group) does
+ * (signal_processing.py:56-59) and emitted as one dB row: db_rows float32 [n_groups][n_fft]. */
+int tdsa_group_avg_db(tdsa_handle_t h, const void* iq, int64_t n_groups, int64_t frames_per_group,
+                      float* db_rows);
+
 /* Config 3: Welch average + peak hold over a flat IQ stream:
  * segments s = 0 .. floor((n_samples - n_fft)/hop), each transformed as kernel 1;
  * avg_db = 10*log10(mean_s |X_s|^2 + floor) (TraceAverager 'lin' with n >= nseg,

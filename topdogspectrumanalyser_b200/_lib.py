@@ -46,6 +46,7 @@ SIGNATURES = {
     "tdsa_psd_db_avg_hold": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _pi32, _vp, _vp, _pi32, _i32, _vp]),
     "tdsa_psd_db_avg_hold_dc": (_i32, [_vp, _vp, _i64, _i64, _f64, _vp, _vp, _i32, _i32, _vp, _pi32, _vp, _vp, _pi32,
                                        _i32, _vp]),
+    "tdsa_group_avg_db": (_i32, [_vp, _vp, _i64, _i64, _vp]),
     "tdsa_welch": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "tdsa_trace_update": (_i32, [_vp, _i64, _i64, _f64, _i32, _i32, _vp, _pi32, _vp, _vp, _pi32, _vp, _vp, _vp]),
     "tdsa_stitch": (_i32, [_vp, _vp, _f64, _i64, _i64, _f64, _f64, _i64, _vp, _vp, _vp]),

@@ -199,7 +199,7 @@ static int run_big(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t strid
 // one launch of the fused path for frames already in device memory
 static int run_fused(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t stride, const double2* dc, int epi,
                      float* db, double* lin, LaunchInfo* info, bool dry) {
-  if (p->win_dirty) { int rc = upload_window(p); if (rc) return rc; }
+  if (p->win_dirty && !dry) { int rc = upload_window(p); if (rc) return rc; }
   if (is_big(p)) return run_big(p, iq, n_frames, stride, dc, epi, db, lin, info, dry);
   cudaError_t e;
   if (p->precision == TDSA_PREC_F32) {
@@ -448,6 +448,32 @@ int tdsa_psd_db_avg_hold_dc(tdsa_handle_t p, const void* iq, int64_t n_frames, i
                             int last_only, float* db_out) {
   return avg_hold_impl(p, iq, n_frames, stride, true, dc_alpha, dc_state, silent_out, avg_mode, avg_n, avg_state,
                        count_state_host, max_hold, min_hold, hold_valid_host, last_only, db_out);
+}
+
+int tdsa_group_avg_db(tdsa_handle_t p, const void* iq, int64_t n_groups, int64_t frames_per_group, float* db_rows) {
+  if (!p) return fail(TDSA_ERR_INVALID, "null plan");
+  if (n_groups < 0 || frames_per_group < 1) return fail(TDSA_ERR_INVALID, "bad group geometry");
+  if (p->mode == TDSA_MODE_MAG20) return fail(TDSA_ERR_INVALID, "group average works on power; use power or psd mode");
+  if (n_groups == 0) return TDSA_OK;
+  if (!iq || !db_rows) return fail(TDSA_ERR_INVALID, "null buffer");
+  const int64_t n = p->n;
+  const int64_t per_group = frames_per_group * n * (int64_t)sizeof(double);
+  const int64_t chunk = std::max<int64_t>(1, ((int64_t)256 << 20) / per_group);
+  for (int64_t g0 = 0; g0 < n_groups; g0 += chunk) {
+    const int64_t ng = std::min(chunk, n_groups - g0);
+    int rc = ensure_scratch(&p->scratch, &p->scratch_bytes, (size_t)(ng * per_group));
+    if (rc) return rc;
+    double* lin = (double*)p->scratch;
+    rc = run_fused(p, (const float2*)iq + g0 * frames_per_group * n, ng * frames_per_group, n, nullptr, kEpiLinear, nullptr,
+                   lin, nullptr, false);
+    if (rc) return rc;
+    const int64_t total = ng * n;
+    group_mean_db_kernel<<<(unsigned)((total + 255) / 256), 256, 0, p->stream>>>(lin, ng, frames_per_group, n, p->floor,
+                                                                              p->mode, db_rows + g0 * n);
+    count_launch();
+    CK(cudaGetLastError());
+  }
+  return TDSA_OK;
 }
 
 int tdsa_welch(tdsa_handle_t p, const void* iq_stream, int64_t n_samples, int64_t hop, float* avg_db, float* peak_db) {

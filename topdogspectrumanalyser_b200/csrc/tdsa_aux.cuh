@@ -319,6 +319,23 @@ __global__ void __launch_bounds__(256) welch_reduce_kernel(const double* __restr
   peak_state[k] = pk;
 }
 
+// Config 4: each group of `frames` consecutive rows is averaged as TraceAverager('lin', n >= frames)
+// does (signal_processing.py:56-59: buffer += (x - buffer)/count) and converted to one dB row.
+__global__ void __launch_bounds__(256) group_mean_db_kernel(const double* __restrict__ lin, int64_t n_groups,
+                                                           int64_t frames, int64_t width, double floor, int mode,
+                                                           float* __restrict__ db_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_groups * width) return;
+  const int64_t g = i / width, k = i - g * width;
+  const double* src = lin + g * frames * width + k;
+  double buf = src[0];
+  for (int64_t f = 1; f < frames; ++f)
+    buf = __dadd_rn(buf, __ddiv_rn(__dsub_rn(src[f * width], buf), (double)(f + 1)));
+  EpiParams ep;
+  ep.db_out = nullptr; ep.lin_out = nullptr; ep.scale = 1.0; ep.floor = floor; ep.mode = mode;
+  db_out[i] = to_db<double>(buf, ep);
+}
+
 // final: avg_db[k] = dB(sum/nseg); optional un-permute for the two-kernel large-FFT path:
 // permuted index i = s*M + klow with s = 16*k0 + k1  ->  k = k0 + 16*k1 + 256*klow.
 __global__ void __launch_bounds__(256) welch_finish_kernel(const double* __restrict__ sum_state,

@@ -3,6 +3,7 @@
 // the 126 MB L2) -> fft_fused_kernel<TAIL> on 256 M-point sub-transforms per frame.
 static int run_big(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t stride, const double2* dc, int epi, float* db,
                    double* lin, LaunchInfo* info, bool dry) {
+  if (p->win_dirty && !dry) { int rcw = upload_window(p); if (rcw) return rcw; }
   const int log2m = p->log2n - 8;
   const bool f32 = p->precision == TDSA_PREC_F32;
   const size_t csz = f32 ? sizeof(float2) : sizeof(double2);

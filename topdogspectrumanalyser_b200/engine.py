@@ -232,6 +232,17 @@ class SpectrumPlan:
             state.min_hold.data_ptr() if state.min_hold_enabled else None, state.valid, int(last_only), out.data_ptr()))
         return out, silent
 
+    def group_avg_db(self, iq: torch.Tensor) -> torch.Tensor:
+        """``iq[G, F, N]`` -> ``float32 [G, N]``: linear mean over the F frames of each group, then dB (config 4)."""
+        if iq.dtype != torch.complex64 or not iq.is_cuda or not iq.is_contiguous() or iq.dim() != 3 \
+                or iq.shape[2] != self.n_fft:
+            raise ValueError(f"iq must be a contiguous complex64 CUDA tensor [G, F, {self.n_fft}]")
+        g, f = int(iq.shape[0]), int(iq.shape[1])
+        out = torch.empty((g, self.n_fft), dtype=torch.float32, device=iq.device)
+        self._bind()
+        L.check(self.lib.tdsa_group_avg_db(self._h, iq.data_ptr(), g, f, out.data_ptr()))
+        return out
+
     def welch(self, stream: torch.Tensor, hop: int):
         """Config 3: ``(avg_db, peak_db)`` over overlapping segments of a flat complex64 stream."""
         if stream.dtype != torch.complex64 or not stream.is_cuda or not stream.is_contiguous():

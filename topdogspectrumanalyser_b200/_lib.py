@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtdsa.so")
+LIB_PATH = os.environ.get("TDSA_LIB", os.path.join(_HERE, "libtdsa.so"))   # TDSA_LIB: A/B builds of the same ABI
 
 # constants mirrored from include/tdsa.h
 WINDOW_HANN, WINDOW_HAMMING, WINDOW_RECT, WINDOW_BLACKMAN, WINDOW_CUSTOM = 0, 1, 2, 3, 4

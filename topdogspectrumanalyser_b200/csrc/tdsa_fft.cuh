@@ -265,8 +265,10 @@ template <typename T> __device__ __forceinline__ float to_db(T p, const EpiParam
     float m = sqrtf((float)p) + (float)ep.floor;
     return 2.0f * kDbPerLog2 * lg2_approx(m);
   }
-  T v = p * (T)ep.scale + (T)ep.floor;
-  return kDbPerLog2 * lg2_approx((float)v);
+  // scale in T, then narrow once; the floor (1e-10 / 1e-12) is added in float32: it only matters when the
+  // scaled power is itself that small, where float32 still resolves it to 6e-8 relative.
+  const float v = (float)(p * (T)ep.scale) + (float)ep.floor;
+  return kDbPerLog2 * lg2_approx(v);
 }
 
 struct EpiDb {
@@ -294,21 +296,44 @@ template <typename T> struct FftArgs {
   EpiParams ep;
 };
 
+// ---- named barriers (ids 1..4; id 0 is __syncthreads) ---------------------------------------
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // TAIL = 0: the whole transform (complex64 frames in, window applied).
 // TAIL = 1: second kernel of the two-kernel large-FFT path: "frame" g is sub-transform
 //           s2 = g & 255 of big frame g >> 8 (input complex T from big_head_kernel's scratch);
 //           bin klow of it is bin (s2 >> 4) + 16*(s2 & 15) + 256*klow of the 256*N-point frame.
 // TAIL = 2: same input, rows left in the permuted [g][klow] order (coalesced stores).
+// TWMODE: where the per-thread pass-0 constants (15 twiddles W_N^(t*q), 16 window values) live.
+//   0 = read from the tables every frame (L1/L2);
+//   1 = all of them in registers for the whole kernel (float32: 46 registers);
+//   2 = six base twiddles W^(t*{1,2,3,4,8,12}) in registers, the other nine formed per frame as
+//       W^(t*q0) * W^(t*4*q1) (one complex multiply each); window still read per frame (float64).
 // NSTAGE > 0 (TAIL == 0 only): frames are staged by cp.async.bulk into an NSTAGE-deep ring of
 //           shared-memory buffers, so frame i+NSTAGE streams in from HBM while frame i computes.
 //           Needs 16-byte aligned frames (even frame_stride); the launcher falls back to NSTAGE = 0.
-template <typename T, int LOG2N, typename Epi, bool PERSIST_TW, int MIN_CTAS, int TAIL, int NSTAGE>
-__global__ void __launch_bounds__(Plan<T, LOG2N>::THREADS, MIN_CTAS)
+// GROUPS = 2: the CTA holds two independent frame engines of THREADS threads each (own exchange
+//           buffer, staging ring and mbarriers).  Their butterfly phases are serialised against each
+//           other with a pair of named barriers, so while one group is in a register/FP phase the
+//           other is in a shared-memory exchange phase ("ping-pong"): the arithmetic pipe and the
+//           shared-memory pipe overlap instead of both groups hitting the same pipe in lock-step.
+template <typename T, int LOG2N, typename Epi, int TWMODE, int MIN_CTAS, int TAIL, int NSTAGE, int GROUPS, bool HAS_DC>
+__global__ void __launch_bounds__(Plan<T, LOG2N>::THREADS * GROUPS, MIN_CTAS)
 fft_fused_kernel(const FftArgs<T> a) {
   using P = Plan<T, LOG2N>;
   using CT = typename CplxOf<T>::type;
   constexpr int N = P::N, TH = P::THREADS, NPASS = P::NPASS;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr size_t GROUP_BYTES = (NSTAGE > 0 ? P::smem_staged(NSTAGE) : P::SMEM_BYTES) + 127 & ~(size_t)127;
+  extern __shared__ __align__(128) unsigned char smem_all[];
+
+  const int g = (GROUPS > 1) ? (int)(threadIdx.x / TH) : 0;
+  const int t = (int)threadIdx.x - g * TH;
+  unsigned char* smem_raw = smem_all + (size_t)g * GROUP_BYTES;
   CT* ex = reinterpret_cast<CT*>(smem_raw);
   CT* tws = ex + P::PHYS_SIZE;   // pass >= 1 twiddles
   const float2* stage0 = reinterpret_cast<const float2*>(smem_raw + P::STAGE_OFFSET);
@@ -316,7 +341,17 @@ fft_fused_kernel(const FftArgs<T> a) {
   const uint32_t bar_u32 = stage_u32 + (uint32_t)(NSTAGE * P::STAGE_BYTES);   // NSTAGE mbarriers behind the ring
   (void)stage0; (void)bar_u32;
 
-  const int t = threadIdx.x;
+  // frames are dealt round-robin to (CTA, group) units
+  const int64_t unit = (int64_t)blockIdx.x * GROUPS + g;
+  const int64_t unit_stride = (int64_t)gridDim.x * GROUPS;
+
+  auto group_sync = [&]() {
+    if constexpr (GROUPS > 1) bar_sync(1 + g, TH); else __syncthreads();
+  };
+  // compute token: acquire before a register/FP phase, hand to the other group after it
+  auto acquire = [&]() { if constexpr (GROUPS > 1) bar_sync(3 + g, 2 * TH); };
+  auto release = [&]() { if constexpr (GROUPS > 1) bar_arrive(3 + (1 - g), 2 * TH); };
+
   if constexpr (NSTAGE > 0) {
     if (t == 0) {
 #pragma unroll
@@ -324,7 +359,7 @@ fft_fused_kernel(const FftArgs<T> a) {
       fence_mbar_init();
 #pragma unroll
       for (int s = 0; s < NSTAGE; ++s) {
-        const int64_t fs = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+        const int64_t fs = unit + (int64_t)s * unit_stride;
         if (fs < a.n_frames) {
           mbar_arrive_expect_tx(bar_u32 + 8 * s, (uint32_t)P::STAGE_BYTES);
           bulk_g2s(stage_u32 + (uint32_t)(s * P::STAGE_BYTES), a.iq + fs * a.frame_stride, (uint32_t)P::STAGE_BYTES,
@@ -340,32 +375,52 @@ fft_fused_kernel(const FftArgs<T> a) {
   }
   // one-time: per-thread constants that do not change from frame to frame
   T win[16];
-  T tw0r[PERSIST_TW ? 16 : 1], tw0i[PERSIST_TW ? 16 : 1];
-  if constexpr (PERSIST_TW) {
+  T tw0r[TWMODE != 0 ? 16 : 1], tw0i[TWMODE != 0 ? 16 : 1];
+  if constexpr (TWMODE == 1) {
     if constexpr (TAIL == 0) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) win[j] = a.window[t + j * TH];
     }
 #pragma unroll
     for (int q = 1; q < 16; ++q) { CT w = a.tw[q * TH + t]; tw0r[q] = w.x; tw0i[q] = w.y; }
+  } else if constexpr (TWMODE == 2) {
+#pragma unroll
+    for (int q = 1; q < 16; ++q) {
+      if (q < 4 || (q & 3) == 0) { CT w = a.tw[q * TH + t]; tw0r[q] = w.x; tw0i[q] = w.y; }
+    }
   }
   if constexpr (P::TW_SMEM > 0 || NSTAGE > 0) __syncthreads();   // tables staged, mbarriers initialised
+  if constexpr (GROUPS > 1) {
+    if (g == 1) bar_arrive(3, 2 * TH);                           // group 0 owns the first compute phase
+  }
 
-  int it = 0;   // frames this CTA has started (ring position)
-  for (int64_t f = blockIdx.x; f < a.n_frames; f += gridDim.x, ++it) {
+  // Both groups run the same number of iterations so that the token hand-offs always pair up;
+  // a group without a frame in the last iteration only passes the token on.
+  const int64_t first_unit = (int64_t)blockIdx.x * GROUPS;
+  const int64_t iters = first_unit < a.n_frames ? (a.n_frames - first_unit + unit_stride - 1) / unit_stride : 0;
+
+  for (int64_t it64 = 0; it64 < iters; ++it64) {
+    const int it = (int)it64;
+    const int64_t f = unit + it64 * unit_stride;
+    if (GROUPS > 1 && f >= a.n_frames) {
+#pragma unroll
+      for (int ph = 0; ph < (NPASS > 2 ? NPASS : 2); ++ph) { acquire(); release(); }
+      continue;
+    }
     T re[16], im[16];
-    // ---- pass 0: global -> registers, window, radix-16, twiddle ------------------------
+    // ---- pass 0: global/staged -> registers, window, radix-16, twiddle ---------------------
     if constexpr (TAIL != 0) {
       const CT* src = a.in_ct + f * N + t;
 #pragma unroll
       for (int j = 0; j < 16; ++j) { const CT x = src[j * TH]; re[j] = x.x; im[j] = x.y; }
+      acquire();
     } else {
-      if constexpr (!PERSIST_TW) {          // issue the table loads before waiting on the frame
+      if constexpr (TWMODE != 1) {          // issue the table loads before waiting on the frame
 #pragma unroll
         for (int j = 0; j < 16; ++j) win[j] = a.window[t + j * TH];
       }
       T dcr = T(0), dci = T(0);
-      if (a.dc != nullptr) { double2 d = a.dc[f]; dcr = (T)d.x; dci = (T)d.y; }
+      if constexpr (HAS_DC) { double2 d = a.dc[f]; dcr = (T)d.x; dci = (T)d.y; }
       float2 v[16];
       if constexpr (NSTAGE > 0) {
         const int stg = it % NSTAGE;
@@ -378,84 +433,95 @@ fft_fused_kernel(const FftArgs<T> a) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = ldg_stream(src + j * TH);
       }
+      acquire();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        re[j] = ((T)v[j].x - dcr) * win[j];
-        im[j] = ((T)v[j].y - dci) * win[j];
+        if constexpr (HAS_DC) {
+          re[j] = ((T)v[j].x - dcr) * win[j];
+          im[j] = ((T)v[j].y - dci) * win[j];
+        } else {
+          re[j] = (T)v[j].x * win[j];
+          im[j] = (T)v[j].y * win[j];
+        }
       }
     }
     dft16<T>(re, im);
-    if constexpr (NPASS > 1) {
 #pragma unroll
-      for (int q = 1; q < 16; ++q) {
-        T wr, wi;
-        if constexpr (PERSIST_TW) { wr = tw0r[q]; wi = tw0i[q]; }
-        else { CT w = a.tw[q * TH + t]; wr = w.x; wi = w.y; }
-        cmul<T>(re[q], im[q], wr, wi);
-      }
-      {
-        const int pb = P::phys(t);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) ex[pb + P::phys(q * TH)] = mk<T>(re[q], im[q]);
-      }
-      __syncthreads();
-      if constexpr (NSTAGE > 0) {
-        // every thread has consumed this stage (its reads precede the barrier): refill it
-        if (t == 0) {
-          const int64_t fn = f + (int64_t)NSTAGE * gridDim.x;
-          if (fn < a.n_frames) {
-            const int stg = it % NSTAGE;
-            fence_proxy_async();
-            mbar_arrive_expect_tx(bar_u32 + 8 * stg, (uint32_t)P::STAGE_BYTES);
-            bulk_g2s(stage_u32 + (uint32_t)(stg * P::STAGE_BYTES), a.iq + fn * a.frame_stride, (uint32_t)P::STAGE_BYTES,
-                     bar_u32 + 8 * stg);
-          }
-        }
-      }
-      // ---- middle passes (radix 16, in place, one butterfly per thread) -----------------
-#pragma unroll
-      for (int i = 1; i < NPASS - 1; ++i) {
-        constexpr int dummy = 0; (void)dummy;
-        const int L = N >> (4 * i), S = N >> (4 * i + 4);
-        const int c = t & (S - 1), s = t / S;
-        const int pb = P::phys(s * L + c);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { CT x = ex[pb + P::phys(j * S)]; re[j] = x.x; im[j] = x.y; }
-        dft16<T>(re, im);
-        const CT* twi = tws + (P::tw_offset(i) - N);
-#pragma unroll
-        for (int q = 1; q < 16; ++q) { CT w = twi[q * S + c]; cmul<T>(re[q], im[q], w.x, w.y); }
-#pragma unroll
-        for (int q = 0; q < 16; ++q) ex[pb + P::phys(q * S)] = mk<T>(re[q], im[q]);
-        __syncthreads();
-      }
-      // ---- last pass: radix R_LAST, NB_LAST butterflies per thread, digit-reversed reads --
-      constexpr int R = P::R_LAST, NB = P::NB_LAST;
-#pragma unroll
-      for (int u = 0; u < NB; ++u) {
-        const int b = t + TH * u;
-        const int pb = P::phys(hexrev(b, P::REV_DIGITS) * R);
-#pragma unroll
-        for (int j = 0; j < R; ++j) { CT x = ex[pb + P::phys(j)]; re[u * R + j] = x.x; im[u * R + j] = x.y; }
-      }
-      dft_last<T, R>(re, im);
-#pragma unroll
-      for (int u = 0; u < NB; ++u) {
-#pragma unroll
-        for (int q = 0; q < R; ++q) {
-          const int k = t + TH * u + (N / R) * q;
-          const int e = u * R + q;
-          const T pw = re[e] * re[e] + im[e] * im[e];
-          if constexpr (TAIL == 1) {
-            const int s2 = (int)(f & 255);
-            Epi::template store<T>(a.ep, f >> 8, N * 256, (s2 >> 4) + 16 * (s2 & 15) + 256 * k, pw);
-          } else {
-            Epi::template store<T>(a.ep, f, N, k, pw);
-          }
-        }
-      }
-      __syncthreads();   // exchange buffer is reused by the next frame's pass 0
+    for (int q = 1; q < 16; ++q) {
+      T wr, wi;
+      if constexpr (TWMODE == 1) { wr = tw0r[q]; wi = tw0i[q]; }
+      else if constexpr (TWMODE == 2) {
+        if (q < 4 || (q & 3) == 0) { wr = tw0r[q]; wi = tw0i[q]; }
+        else { wr = tw0r[q & 3]; wi = tw0i[q & 3]; cmul<T>(wr, wi, tw0r[q & 12], tw0i[q & 12]); }
+      } else { CT w = a.tw[q * TH + t]; wr = w.x; wi = w.y; }
+      cmul<T>(re[q], im[q], wr, wi);
     }
+    release();
+    {
+      const int pb = P::phys(t);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) ex[pb + P::phys(q * TH)] = mk<T>(re[q], im[q]);
+    }
+    group_sync();
+    if constexpr (NSTAGE > 0) {
+      // every thread of the group has consumed this stage (its reads precede the barrier): refill it
+      if (t == 0) {
+        const int64_t fn = f + (int64_t)NSTAGE * unit_stride;
+        if (fn < a.n_frames) {
+          const int stg = it % NSTAGE;
+          fence_proxy_async();
+          mbar_arrive_expect_tx(bar_u32 + 8 * stg, (uint32_t)P::STAGE_BYTES);
+          bulk_g2s(stage_u32 + (uint32_t)(stg * P::STAGE_BYTES), a.iq + fn * a.frame_stride, (uint32_t)P::STAGE_BYTES,
+                   bar_u32 + 8 * stg);
+        }
+      }
+    }
+    // ---- middle passes (radix 16, in place, one butterfly per thread) -----------------------
+#pragma unroll
+    for (int i = 1; i < NPASS - 1; ++i) {
+      const int L = N >> (4 * i), S = N >> (4 * i + 4);
+      const int c = t & (S - 1), s = t / S;
+      const int pb = P::phys(s * L + c);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { CT x = ex[pb + P::phys(j * S)]; re[j] = x.x; im[j] = x.y; }
+      acquire();
+      dft16<T>(re, im);
+      const CT* twi = tws + (P::tw_offset(i) - N);
+#pragma unroll
+      for (int q = 1; q < 16; ++q) { CT w = twi[q * S + c]; cmul<T>(re[q], im[q], w.x, w.y); }
+      release();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) ex[pb + P::phys(q * S)] = mk<T>(re[q], im[q]);
+      group_sync();
+    }
+    // ---- last pass: radix R_LAST, NB_LAST butterflies per thread, digit-reversed reads --------
+    constexpr int R = P::R_LAST, NB = P::NB_LAST;
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const int b = t + TH * u;
+      const int pb = P::phys(hexrev(b, P::REV_DIGITS) * R);
+#pragma unroll
+      for (int j = 0; j < R; ++j) { CT x = ex[pb + P::phys(j)]; re[u * R + j] = x.x; im[u * R + j] = x.y; }
+    }
+    acquire();
+    dft_last<T, R>(re, im);
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const int k = t + TH * u + (N / R) * q;
+        const int e = u * R + q;
+        const T pw = re[e] * re[e] + im[e] * im[e];
+        if constexpr (TAIL == 1) {
+          const int s2 = (int)(f & 255);
+          Epi::template store<T>(a.ep, f >> 8, N * 256, (s2 >> 4) + 16 * (s2 & 15) + 256 * k, pw);
+        } else {
+          Epi::template store<T>(a.ep, f, N, k, pw);
+        }
+      }
+    }
+    release();
+    group_sync();   // exchange buffer is reused by the next frame's pass 0
   }
 }
 

@@ -15,19 +15,22 @@ import sys
 import numpy as np
 
 
+LOGR = 4          # digit width: 4 = radix 16 / 16 points per thread, 3 = radix 8 / 8 points per thread
+
+
 def plan(n):
     lg = n.bit_length() - 1
-    radices = [16] * (lg // 4)
-    if lg % 4:
-        radices.append(1 << (lg % 4))
+    radices = [1 << LOGR] * (lg // LOGR)
+    if lg % LOGR:
+        radices.append(1 << (lg % LOGR))
     return radices
 
 
 def hexrev(v, digits):
     out = 0
     for _ in range(digits):
-        out = (out << 4) | (v & 15)
-        v >>= 4
+        out = (out << LOGR) | (v & ((1 << LOGR) - 1))
+        v >>= LOGR
     return out
 
 
@@ -38,13 +41,13 @@ def phys(p, pads):
 def accesses(n):
     """Yield (pass_index, kind, lane_positions[T]) for each register slot j of each pass."""
     radices = plan(n)
-    t_count = n // 16
+    t_count = n >> LOGR
     t = np.arange(t_count)
     length = n
     m = len(radices)
     for i, r in enumerate(radices):
         s_i = length // r
-        nb = 16 // r
+        nb = (1 << LOGR) // r
         last = i == m - 1
         for u in range(nb):
             b = t + t_count * u
@@ -70,11 +73,11 @@ def model_fft(x, window=None):
     buf = x.astype(np.complex128).copy()
     length = n
     m = len(radices)
-    t_count = n // 16
+    t_count = n >> LOGR
     out = np.zeros(n, dtype=np.complex128)
     for i, r in enumerate(radices):
         s_i = length // r
-        nb = 16 // r
+        nb = (1 << LOGR) // r
         last = i == m - 1
         new = buf.copy()
         for u in range(nb):
@@ -159,12 +162,14 @@ def search(n, elem_bytes):
 
 
 if __name__ == "__main__":
+    if "r8" in sys.argv:
+        LOGR = 3
     rng = np.random.default_rng(0)
     for n in (64, 128, 256, 512, 1024, 2048, 4096, 8192):
         x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
         err = np.max(np.abs(model_fft(x) - np.fft.fft(x)))
         print(f"N={n:5d} plan={plan(n)} max|err|={err:.2e}")
-    if len(sys.argv) > 1 and sys.argv[1] == "banks":
+    if "banks" in sys.argv:
         for n in (512, 1024, 2048, 4096, 8192, 16384):
             for eb in (8, 16):
                 (key, pads, worst) = search(n, eb)

@@ -1,7 +1,8 @@
 #!/bin/bash
-# A/B: run the quick timing for the default library and every variants/libtdsa_*.so
+# A/B timing of the default library and every variants/libtdsa_*.so (diagnostic builds print wrong results by design)
 mkdir -p gpurun_out
-echo "== default"; timeout 300 python tools/gpu_dev.py quick 2>&1 | grep -E "^N=  4096|^time N=4096|^time N=1024|FAILED|Error"
+echo "== default"; timeout 300 python tools/gpu_dev.py quick 2>&1 | grep -E "^time N=(4096|1024)|FAILED|Error"
 for lib in variants/libtdsa_*.so; do
-  echo "== $lib"; TDSA_LIB=$PWD/$lib timeout 300 python tools/gpu_dev.py quick 2>&1 | grep -E "^N=  4096|^time N=4096|^time N=1024|FAILED|Error"
+  [ -f "$lib" ] || continue
+  echo "== $lib"; TDSA_LIB=$PWD/$lib timeout 300 python tools/gpu_dev.py quick 2>&1 | grep -E "^time N=(4096|1024)|FAILED|Error"
 done

@@ -146,20 +146,21 @@ static void twiddle(int64_t m, int64_t L, double* re, double* im) {
 
 // Tables for an in-place DIF of 2^log2n points: radix-16 passes 0..npass-2 need
 // W_{L_i}^{c*q}; table i is laid out [q][c], c in [0, L_i/16).
-static int64_t tw_total(int log2n) {
-  const int npass = (log2n + 3) / 4;
+static int64_t tw_total(int log2n, int logr) {
+  const int npass = (log2n + logr - 1) / logr;
   int64_t t = 0;
-  for (int i = 0; i < npass - 1; ++i) t += (int64_t)1 << (log2n - 4 * i);
+  for (int i = 0; i < npass - 1; ++i) t += (int64_t)1 << (log2n - logr * i);
   return t;
 }
 
-static void build_twiddles(int log2n, std::vector<double2>& t64) {
-  const int npass = (log2n + 3) / 4;
+// logr = 4: radix-16 passes (table i is [16][L_i/16]); logr = 3: radix-8 passes ([8][L_i/8]).
+static void build_twiddles(int log2n, int logr, std::vector<double2>& t64) {
+  const int npass = (log2n + logr - 1) / logr;
   t64.clear();
-  t64.reserve(tw_total(log2n));
+  t64.reserve(tw_total(log2n, logr));
   for (int i = 0; i < npass - 1; ++i) {
-    const int64_t L = (int64_t)1 << (log2n - 4 * i), S = L >> 4;
-    for (int q = 0; q < 16; ++q)
+    const int64_t L = (int64_t)1 << (log2n - logr * i), S = L >> logr;
+    for (int q = 0; q < (1 << logr); ++q)
       for (int64_t c = 0; c < S; ++c) {
         double2 w;
         twiddle(c * q, L, &w.x, &w.y);
@@ -168,18 +169,17 @@ static void build_twiddles(int log2n, std::vector<double2>& t64) {
   }
 }
 
-static int upload_twiddles(int log2n, double2** d64, float2** d32) {
+// the float32 and float64 kernels of one size may use different digit widths, so each gets its own table
+static int upload_twiddles(int log2n, int logr64, int logr32, double2** d64, float2** d32) {
   std::vector<double2> t64;
-  build_twiddles(log2n, t64);
-  const size_t cnt = t64.size() ? t64.size() : 1;
-  std::vector<float2> t32(cnt);
+  build_twiddles(log2n, logr64, t64);
+  CK(cudaMalloc(d64, sizeof(double2) * std::max<size_t>(t64.size(), 1)));
+  if (!t64.empty()) CK(cudaMemcpy(*d64, t64.data(), sizeof(double2) * t64.size(), cudaMemcpyHostToDevice));
+  if (logr32 != logr64) build_twiddles(log2n, logr32, t64);
+  std::vector<float2> t32(std::max<size_t>(t64.size(), 1));
   for (size_t i = 0; i < t64.size(); ++i) t32[i] = make_float2((float)t64[i].x, (float)t64[i].y);
-  CK(cudaMalloc(d64, sizeof(double2) * cnt));
-  CK(cudaMalloc(d32, sizeof(float2) * cnt));
-  if (!t64.empty()) {
-    CK(cudaMemcpy(*d64, t64.data(), sizeof(double2) * t64.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(*d32, t32.data(), sizeof(float2) * t64.size(), cudaMemcpyHostToDevice));
-  }
+  CK(cudaMalloc(d32, sizeof(float2) * t32.size()));
+  if (!t64.empty()) CK(cudaMemcpy(*d32, t32.data(), sizeof(float2) * t64.size(), cudaMemcpyHostToDevice));
   return TDSA_OK;
 }
 
@@ -250,11 +250,11 @@ int tdsa_create(int n_fft, int window_id, int window_norm, int mode, double log_
   do {
     if (cudaMalloc(&p->d_win64, sizeof(double) * n_fft) != cudaSuccess ||
         cudaMalloc(&p->d_win32, sizeof(float) * n_fft) != cudaSuccess) { rc = fail(TDSA_ERR_NOMEM, "window alloc failed"); break; }
-    rc = upload_twiddles(p->log2n, &p->d_tw64, &p->d_tw32);
+    rc = upload_twiddles(p->log2n, effective_logr_f64(p->log2n), effective_logr_f32(p->log2n), &p->d_tw64, &p->d_tw32);
     if (rc) break;
     if (p->log2n > MaxLog2<float>::value || p->log2n > MaxLog2<double>::value) {
       // tables for the inner (N/256)-point transform of the two-kernel path
-      rc = upload_twiddles(p->log2n - 8, &p->d_twin64, &p->d_twin32);
+      rc = upload_twiddles(p->log2n - 8, 4, 4, &p->d_twin64, &p->d_twin32);
       if (rc) break;
     }
   } while (0);

@@ -20,6 +20,15 @@
 
 namespace tdsa {
 
+// radix-8 padding table (filled from tools/fft_plan_model.py r8 banks); generic fallback otherwise
+// frames prefetched into L2 ahead of the shared-memory staging ring (cp.async.bulk.prefetch.L2)
+#ifndef TDSA_L2_AHEAD
+#define TDSA_L2_AHEAD 0   // measured: 0, 2 and 4 frames ahead are within noise of each other at N=4096
+#endif
+#ifndef TDSA_PADS_R8
+#define TDSA_PADS_R8(LOG2N, WIDE) pads_r8(LOG2N, WIDE)
+#endif
+
 // ---------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------
@@ -72,6 +81,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
                "l"(src_gmem), "r"(bytes), "r"(bar)
                : "memory");
 }
+// L2 prefetch of a whole frame: deepens the prefetch distance beyond what fits in shared memory
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -83,10 +96,11 @@ template <typename T> __device__ __forceinline__ void cmul(T& xr, T& xi, T wr, T
 }
 
 // ---------------------------------------------------------------------------------------
-// butterflies (forward DFT, W = exp(-2*pi*i/R)); all indices are compile-time after unrolling
+// butterflies (forward DFT, W = exp(-2*pi*i/R)); all indices are compile-time after unrolling,
+// so the re[]/im[] arrays live in registers
 // ---------------------------------------------------------------------------------------
 template <typename T, int I0, int I1, int I2, int I3>
-__device__ __forceinline__ void r4(T (&re)[16], T (&im)[16]) {
+__device__ __forceinline__ void r4(T* re, T* im) {
   T t0r = re[I0] + re[I2], t0i = im[I0] + im[I2];
   T t1r = re[I0] - re[I2], t1i = im[I0] - im[I2];
   T t2r = re[I1] + re[I3], t2i = im[I1] + im[I3];
@@ -97,7 +111,7 @@ __device__ __forceinline__ void r4(T (&re)[16], T (&im)[16]) {
   re[I3] = t1r - t3i; im[I3] = t1i + t3r;   // t1 + i*t3
 }
 
-template <typename T, int A, int B> __device__ __forceinline__ void swp(T (&re)[16], T (&im)[16]) {
+template <typename T, int A, int B> __device__ __forceinline__ void swp(T* re, T* im) {
   T r = re[A]; re[A] = re[B]; re[B] = r;
   T i = im[A]; im[A] = im[B]; im[B] = i;
 }
@@ -120,8 +134,8 @@ template <typename T> __device__ __forceinline__ void mul_mi(T& xr, T& xi) {
   xr = r; xi = i;
 }
 
-// 16-point DFT over all 16 registers, natural order in and out: a[q] = sum_j a[j] W16^(jq).
-template <typename T> __device__ __forceinline__ void dft16(T (&re)[16], T (&im)[16]) {
+// 16-point DFT over registers [0, 16), natural order in and out: a[q] = sum_j a[j] W16^(jq).
+template <typename T> __device__ __forceinline__ void dft16(T* re, T* im) {
   const T c1 = T(0.92387953251128675613);   // cos(pi/8)
   const T s1 = T(0.38268343236508977173);   // sin(pi/8)
   // stage A: over j1 (stride 4); a[j0 + 4*q0] = B[j0][q0]
@@ -152,17 +166,17 @@ template <typename T> __device__ __forceinline__ void dft16(T (&re)[16], T (&im)
 // R-point DFTs (R = 2, 4, 8) over registers [O, O+R), natural order in and out.
 template <typename T, int R, int O> struct DftSmall;
 template <typename T, int O> struct DftSmall<T, 2, O> {
-  static __device__ __forceinline__ void run(T (&re)[16], T (&im)[16]) {
+  static __device__ __forceinline__ void run(T* re, T* im) {
     T ar = re[O] + re[O + 1], ai = im[O] + im[O + 1];
     T br = re[O] - re[O + 1], bi = im[O] - im[O + 1];
     re[O] = ar; im[O] = ai; re[O + 1] = br; im[O + 1] = bi;
   }
 };
 template <typename T, int O> struct DftSmall<T, 4, O> {
-  static __device__ __forceinline__ void run(T (&re)[16], T (&im)[16]) { r4<T, O, O + 1, O + 2, O + 3>(re, im); }
+  static __device__ __forceinline__ void run(T* re, T* im) { r4<T, O, O + 1, O + 2, O + 3>(re, im); }
 };
 template <typename T, int O> struct DftSmall<T, 8, O> {
-  static __device__ __forceinline__ void run(T (&re)[16], T (&im)[16]) {
+  static __device__ __forceinline__ void run(T* re, T* im) {
     // DIF radix-2 split: u_j = a_j + a_{j+4} (even outputs), v_j = (a_j - a_{j+4}) W8^j (odd outputs)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -175,7 +189,7 @@ template <typename T, int O> struct DftSmall<T, 8, O> {
     mul_w8_3<T>(re[O + 7], im[O + 7]);
     r4<T, O, O + 1, O + 2, O + 3>(re, im);          // X[2m]   at O+m
     r4<T, O + 4, O + 5, O + 6, O + 7>(re, im);      // X[2m+1] at O+4+m
-    // interleave: out[2m] = a[m], out[2m+1] = a[4+m]  -> permutation (0 2 4 6 1 3 5 7)^-1
+    // interleave: out[2m] = a[m], out[2m+1] = a[4+m]
     T r1 = re[O + 1], r2 = re[O + 2], r3 = re[O + 3], r4_ = re[O + 4], r5 = re[O + 5], r6 = re[O + 6];
     T i1 = im[O + 1], i2 = im[O + 2], i3 = im[O + 3], i4_ = im[O + 4], i5 = im[O + 5], i6 = im[O + 6];
     re[O + 1] = r4_; im[O + 1] = i4_;
@@ -187,49 +201,81 @@ template <typename T, int O> struct DftSmall<T, 8, O> {
   }
 };
 
-template <typename T, int R> __device__ __forceinline__ void dft_last(T (&re)[16], T (&im)[16]) {
-  if constexpr (R == 16) {
-    dft16<T>(re, im);
-  } else if constexpr (R == 8) {
+// P-point DFT over all P registers of a thread (P = 16 or 8)
+template <typename T, int P> __device__ __forceinline__ void dft_full(T* re, T* im) {
+  if constexpr (P == 16) dft16<T>(re, im); else DftSmall<T, 8, 0>::run(re, im);
+}
+
+// last pass: P/R independent R-point DFTs over consecutive register groups
+template <typename T, int P, int R> __device__ __forceinline__ void dft_last(T* re, T* im) {
+  if constexpr (R == P) {
+    dft_full<T, P>(re, im);
+  } else if constexpr (R == 8) {       // P == 16
     DftSmall<T, 8, 0>::run(re, im); DftSmall<T, 8, 8>::run(re, im);
   } else if constexpr (R == 4) {
     DftSmall<T, 4, 0>::run(re, im); DftSmall<T, 4, 4>::run(re, im);
-    DftSmall<T, 4, 8>::run(re, im); DftSmall<T, 4, 12>::run(re, im);
+    if constexpr (P == 16) { DftSmall<T, 4, 8>::run(re, im); DftSmall<T, 4, 12>::run(re, im); }
   } else {
     DftSmall<T, 2, 0>::run(re, im);  DftSmall<T, 2, 2>::run(re, im);
     DftSmall<T, 2, 4>::run(re, im);  DftSmall<T, 2, 6>::run(re, im);
-    DftSmall<T, 2, 8>::run(re, im);  DftSmall<T, 2, 10>::run(re, im);
-    DftSmall<T, 2, 12>::run(re, im); DftSmall<T, 2, 14>::run(re, im);
+    if constexpr (P == 16) {
+      DftSmall<T, 2, 8>::run(re, im);  DftSmall<T, 2, 10>::run(re, im);
+      DftSmall<T, 2, 12>::run(re, im); DftSmall<T, 2, 14>::run(re, im);
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// compile-time plan for one (element type, size)
+// compile-time plan for one (element type, size, digit width)
+//   LOGR = 4: radix 16, 16 points per thread (N/16 threads per frame)
+//   LOGR = 3: radix 8,   8 points per thread (N/8 threads per frame): half the registers per thread,
+//             twice the warps per frame, one more exchange pass
 // ---------------------------------------------------------------------------------------
-template <typename T, int LOG2N> struct Plan {
+struct PadSpec { int s0, c0, s1, c1, s2, c2; };   // phys(p) = p + c0*(p>>s0) + c1*(p>>s1) + c2*(p>>s2)
+
+constexpr PadSpec pads_r8(int log2n, bool wide) {
+  if (log2n == 9) return {6, 1, 0, 0, 0, 0};
+  if (log2n == 10) return wide ? PadSpec{5, 2, 7, 1, 0, 0} : PadSpec{4, 1, 8, 2, 0, 0};
+  if (log2n == 11) return wide ? PadSpec{8, 1, 0, 0, 0, 0} : PadSpec{5, 4, 9, 1, 0, 0};
+  if (log2n == 12) return wide ? PadSpec{9, 1, 0, 0, 0, 0} : PadSpec{6, 8, 9, 1, 0, 0};   // conflict-free
+  return {3, 1, log2n - 3, 1, 0, 0};
+}
+
+// Padded exchange layouts found by tools/fft_plan_model.py ("banks" / "r8 banks"): zero shared-memory
+// bank conflicts for every pass at the listed sizes; other sizes get a generic (correct) padding.
+template <int LOG2N, bool WIDE, int LOGR> constexpr PadSpec pad_spec() {
+  if (LOGR == 4) {
+    if (LOG2N == 12) return {8, 1, 0, 0, 0, 0};
+    if (LOG2N == 11 && WIDE) return {7, 1, 0, 0, 0, 0};
+    if (LOG2N <= 11) return {4, 1, WIDE ? 7 : 8, 1, 0, 0};
+    return {4, 1, LOG2N - 4, 1, 0, 0};
+  }
+  return TDSA_PADS_R8(LOG2N, WIDE);
+}
+
+template <typename T, int LOG2N, int LOGR = 4> struct Plan {
   static constexpr int N = 1 << LOG2N;
-  static constexpr int THREADS = N / 16;
-  static constexpr int NPASS = (LOG2N + 3) / 4;
-  static constexpr int R_LAST = (LOG2N % 4) ? (1 << (LOG2N % 4)) : 16;
-  static constexpr int NB_LAST = 16 / R_LAST;          // butterflies per thread in the last pass
-  static constexpr int REV_DIGITS = NPASS - 1;         // hex digits reversed in the last pass
+  static constexpr int P = 1 << LOGR;                  // points per thread = radix of the full passes
+  static constexpr int THREADS = N >> LOGR;
+  static constexpr int NPASS = (LOG2N + LOGR - 1) / LOGR;
+  static constexpr int R_LAST = (LOG2N % LOGR) ? (1 << (LOG2N % LOGR)) : P;
+  static constexpr int NB_LAST = P / R_LAST;           // butterflies per thread in the last pass
+  static constexpr int REV_DIGITS = NPASS - 1;         // digits reversed in the last pass
   static constexpr bool WIDE = sizeof(T) == 8;         // 16-byte exchange elements
-  // padded exchange layout: phys(p) = p + PAD4*(p >> 4) + (p >> HB); table found by
-  // tools/fft_plan_model.py ("banks"): zero bank conflicts for every pass at every size.
-  static constexpr int PAD4 = (LOG2N == 12) ? 0 : ((LOG2N == 11 && WIDE) ? 0 : 1);
-  static constexpr int HB = (LOG2N <= 11) ? (WIDE ? 7 : 8) : (LOG2N == 12 ? 8 : LOG2N - 4);
-  static __host__ __device__ constexpr int phys(int p) { return p + PAD4 * (p >> 4) + (p >> HB); }
+  static constexpr PadSpec PAD = pad_spec<LOG2N, WIDE, LOGR>();
+  static __host__ __device__ constexpr int phys(int p) {
+    return p + PAD.c0 * (p >> PAD.s0) + (PAD.c1 ? PAD.c1 * (p >> PAD.s1) : 0) + (PAD.c2 ? PAD.c2 * (p >> PAD.s2) : 0);
+  }
   static constexpr int PHYS_SIZE = phys(N - 1) + 1;
-  // twiddle tables for passes 1..NPASS-2 live in shared memory: 16 * S_i entries each
-  static __host__ __device__ constexpr int len(int i) { return N >> (4 * i); }        // L_i
-  static __host__ __device__ constexpr int stride(int i) { return N >> (4 * i + 4); } // S_i (radix-16 pass)
+  static __host__ __device__ constexpr int len(int i) { return N >> (LOGR * i); }             // L_i
+  static __host__ __device__ constexpr int stride(int i) { return N >> (LOGR * (i + 1)); }    // S_i
   static __host__ __device__ constexpr int tw_offset(int i) {   // entries before pass i's table
     int o = 0;
     for (int k = 0; k < i; ++k) o += len(k);
     return o;
   }
   static constexpr int TW_TOTAL = tw_offset(NPASS - 1);          // all non-last passes
-  static constexpr int TW_SMEM = TW_TOTAL - N;                   // passes >= 1
+  static constexpr int TW_SMEM = TW_TOTAL - N;                   // passes >= 1 (kept in shared memory)
   static constexpr size_t SMEM_BYTES = (size_t)(PHYS_SIZE + (TW_SMEM > 0 ? TW_SMEM : 0)) * 2 * sizeof(T);
   // bulk-copy staging: NSTAGE buffers of one complex64 frame each + one mbarrier per stage
   static constexpr size_t STAGE_BYTES = (size_t)N * 8;
@@ -239,9 +285,9 @@ template <typename T, int LOG2N> struct Plan {
   }
 };
 
-__host__ __device__ constexpr int hexrev(int v, int digits) {
+template <int LOGR> __host__ __device__ constexpr int digitrev(int v, int digits) {
   int o = 0;
-  for (int d = 0; d < digits; ++d) { o = (o << 4) | (v & 15); v >>= 4; }
+  for (int d = 0; d < digits; ++d) { o = (o << LOGR) | (v & ((1 << LOGR) - 1)); v >>= LOGR; }
   return o;
 }
 
@@ -322,13 +368,15 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
 //           other with a pair of named barriers, so while one group is in a register/FP phase the
 //           other is in a shared-memory exchange phase ("ping-pong"): the arithmetic pipe and the
 //           shared-memory pipe overlap instead of both groups hitting the same pipe in lock-step.
-template <typename T, int LOG2N, typename Epi, int TWMODE, int MIN_CTAS, int TAIL, int NSTAGE, int GROUPS, bool HAS_DC>
-__global__ void __launch_bounds__(Plan<T, LOG2N>::THREADS * GROUPS, MIN_CTAS)
+template <typename T, int LOG2N, typename Epi, int TWMODE, int MIN_CTAS, int TAIL, int NSTAGE, int GROUPS, bool HAS_DC,
+          int LOGR>
+__global__ void __launch_bounds__(Plan<T, LOG2N, LOGR>::THREADS * GROUPS, MIN_CTAS)
 fft_fused_kernel(const FftArgs<T> a) {
-  using P = Plan<T, LOG2N>;
+  using P = Plan<T, LOG2N, LOGR>;
   using CT = typename CplxOf<T>::type;
-  constexpr int N = P::N, TH = P::THREADS, NPASS = P::NPASS;
-  constexpr size_t GROUP_BYTES = (NSTAGE > 0 ? P::smem_staged(NSTAGE) : P::SMEM_BYTES) + 127 & ~(size_t)127;
+  constexpr int N = P::N, TH = P::THREADS, NPASS = P::NPASS, PP = P::P;
+  constexpr size_t GROUP_BYTES = ((NSTAGE > 0 ? P::smem_staged(NSTAGE) : P::SMEM_BYTES) + 127) & ~(size_t)127;
+  constexpr int kL2Ahead = TDSA_L2_AHEAD;   // frames prefetched into L2 beyond the shared-memory ring
   extern __shared__ __align__(128) unsigned char smem_all[];
 
   const int g = (GROUPS > 1) ? (int)(threadIdx.x / TH) : 0;
@@ -366,6 +414,11 @@ fft_fused_kernel(const FftArgs<T> a) {
                    bar_u32 + 8 * s);
         }
       }
+#pragma unroll
+      for (int s = NSTAGE; s < NSTAGE + kL2Ahead; ++s) {
+        const int64_t fs = unit + (int64_t)s * unit_stride;
+        if (fs < a.n_frames) bulk_prefetch_l2(a.iq + fs * a.frame_stride, (uint32_t)P::STAGE_BYTES);
+      }
     }
   }
 
@@ -374,18 +427,18 @@ fft_fused_kernel(const FftArgs<T> a) {
     for (int i = t; i < P::TW_SMEM; i += TH) tws[i] = a.tw[N + i];
   }
   // one-time: per-thread constants that do not change from frame to frame
-  T win[16];
-  T tw0r[TWMODE != 0 ? 16 : 1], tw0i[TWMODE != 0 ? 16 : 1];
+  T win[PP];
+  T tw0r[TWMODE != 0 ? PP : 1], tw0i[TWMODE != 0 ? PP : 1];
   if constexpr (TWMODE == 1) {
     if constexpr (TAIL == 0) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) win[j] = a.window[t + j * TH];
+      for (int j = 0; j < PP; ++j) win[j] = a.window[t + j * TH];
     }
 #pragma unroll
-    for (int q = 1; q < 16; ++q) { CT w = a.tw[q * TH + t]; tw0r[q] = w.x; tw0i[q] = w.y; }
+    for (int q = 1; q < PP; ++q) { CT w = a.tw[q * TH + t]; tw0r[q] = w.x; tw0i[q] = w.y; }
   } else if constexpr (TWMODE == 2) {
 #pragma unroll
-    for (int q = 1; q < 16; ++q) {
+    for (int q = 1; q < PP; ++q) {
       if (q < 4 || (q & 3) == 0) { CT w = a.tw[q * TH + t]; tw0r[q] = w.x; tw0i[q] = w.y; }
     }
   }
@@ -404,38 +457,41 @@ fft_fused_kernel(const FftArgs<T> a) {
     const int64_t f = unit + it64 * unit_stride;
     if (GROUPS > 1 && f >= a.n_frames) {
 #pragma unroll
-      for (int ph = 0; ph < (NPASS > 2 ? NPASS : 2); ++ph) { acquire(); release(); }
+      for (int ph = 0; ph < NPASS; ++ph) { acquire(); release(); }
       continue;
     }
-    T re[16], im[16];
-    // ---- pass 0: global/staged -> registers, window, radix-16, twiddle ---------------------
+    T re[PP], im[PP];
+    // ---- pass 0: global/staged -> registers, window, full-radix DFT, twiddle ----------------
     if constexpr (TAIL != 0) {
       const CT* src = a.in_ct + f * N + t;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { const CT x = src[j * TH]; re[j] = x.x; im[j] = x.y; }
+      for (int j = 0; j < PP; ++j) { const CT x = src[j * TH]; re[j] = x.x; im[j] = x.y; }
       acquire();
     } else {
       if constexpr (TWMODE != 1) {          // issue the table loads before waiting on the frame
 #pragma unroll
-        for (int j = 0; j < 16; ++j) win[j] = a.window[t + j * TH];
+        for (int j = 0; j < PP; ++j) win[j] = a.window[t + j * TH];
       }
       T dcr = T(0), dci = T(0);
       if constexpr (HAS_DC) { double2 d = a.dc[f]; dcr = (T)d.x; dci = (T)d.y; }
-      float2 v[16];
+      float2 v[PP];
       if constexpr (NSTAGE > 0) {
         const int stg = it % NSTAGE;
+#ifdef TDSA_DEBUG_SKIP_MEM      // diagnostic build: the ring is filled once and never refilled
+        if (it < NSTAGE)
+#endif
         mbar_wait(bar_u32 + 8 * stg, (uint32_t)((it / NSTAGE) & 1));
         const float2* src = stage0 + (size_t)stg * N + t;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = src[j * TH];
+        for (int j = 0; j < PP; ++j) v[j] = src[j * TH];
       } else {
         const float2* src = a.iq + f * a.frame_stride + t;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = ldg_stream(src + j * TH);
+        for (int j = 0; j < PP; ++j) v[j] = ldg_stream(src + j * TH);
       }
       acquire();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < PP; ++j) {
         if constexpr (HAS_DC) {
           re[j] = ((T)v[j].x - dcr) * win[j];
           im[j] = ((T)v[j].y - dci) * win[j];
@@ -445,14 +501,34 @@ fft_fused_kernel(const FftArgs<T> a) {
         }
       }
     }
-    dft16<T>(re, im);
+#ifdef TDSA_DEBUG_SKIP_MATH     // diagnostic build: memory pipeline only (results are wrong by design)
+    if (a.n_frames >= 0) {
 #pragma unroll
-    for (int q = 1; q < 16; ++q) {
+      for (int q = 0; q < PP; ++q) Epi::template store<T>(a.ep, f, N, t + TH * q, re[q] * re[q] + im[q] * im[q]);
+      group_sync();
+      if constexpr (NSTAGE > 0) {
+        if (t == 0) {
+          const int64_t fn = f + (int64_t)NSTAGE * unit_stride;
+          if (fn < a.n_frames) {
+            const int stg = it % NSTAGE;
+            fence_proxy_async();
+            mbar_arrive_expect_tx(bar_u32 + 8 * stg, (uint32_t)P::STAGE_BYTES);
+            bulk_g2s(stage_u32 + (uint32_t)(stg * P::STAGE_BYTES), a.iq + fn * a.frame_stride, (uint32_t)P::STAGE_BYTES,
+                     bar_u32 + 8 * stg);
+          }
+        }
+      }
+      continue;
+    }
+#endif
+    dft_full<T, PP>(re, im);
+#pragma unroll
+    for (int q = 1; q < PP; ++q) {
       T wr, wi;
       if constexpr (TWMODE == 1) { wr = tw0r[q]; wi = tw0i[q]; }
       else if constexpr (TWMODE == 2) {
         if (q < 4 || (q & 3) == 0) { wr = tw0r[q]; wi = tw0i[q]; }
-        else { wr = tw0r[q & 3]; wi = tw0i[q & 3]; cmul<T>(wr, wi, tw0r[q & 12], tw0i[q & 12]); }
+        else { wr = tw0r[q & 3]; wi = tw0i[q & 3]; cmul<T>(wr, wi, tw0r[q & ~3], tw0i[q & ~3]); }
       } else { CT w = a.tw[q * TH + t]; wr = w.x; wi = w.y; }
       cmul<T>(re[q], im[q], wr, wi);
     }
@@ -460,11 +536,12 @@ fft_fused_kernel(const FftArgs<T> a) {
     {
       const int pb = P::phys(t);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) ex[pb + P::phys(q * TH)] = mk<T>(re[q], im[q]);
+      for (int q = 0; q < PP; ++q) ex[pb + P::phys(q * TH)] = mk<T>(re[q], im[q]);
     }
     group_sync();
     if constexpr (NSTAGE > 0) {
       // every thread of the group has consumed this stage (its reads precede the barrier): refill it
+#ifndef TDSA_DEBUG_SKIP_MEM
       if (t == 0) {
         const int64_t fn = f + (int64_t)NSTAGE * unit_stride;
         if (fn < a.n_frames) {
@@ -474,24 +551,27 @@ fft_fused_kernel(const FftArgs<T> a) {
           bulk_g2s(stage_u32 + (uint32_t)(stg * P::STAGE_BYTES), a.iq + fn * a.frame_stride, (uint32_t)P::STAGE_BYTES,
                    bar_u32 + 8 * stg);
         }
+        const int64_t fp = f + (int64_t)(NSTAGE + kL2Ahead) * unit_stride;   // one more frame into L2
+        if (kL2Ahead > 0 && fp < a.n_frames) bulk_prefetch_l2(a.iq + fp * a.frame_stride, (uint32_t)P::STAGE_BYTES);
       }
+#endif
     }
-    // ---- middle passes (radix 16, in place, one butterfly per thread) -----------------------
+    // ---- middle passes (full radix, in place, one butterfly per thread) ----------------------
 #pragma unroll
     for (int i = 1; i < NPASS - 1; ++i) {
-      const int L = N >> (4 * i), S = N >> (4 * i + 4);
+      const int L = N >> (LOGR * i), S = N >> (LOGR * (i + 1));
       const int c = t & (S - 1), s = t / S;
       const int pb = P::phys(s * L + c);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { CT x = ex[pb + P::phys(j * S)]; re[j] = x.x; im[j] = x.y; }
+      for (int j = 0; j < PP; ++j) { CT x = ex[pb + P::phys(j * S)]; re[j] = x.x; im[j] = x.y; }
       acquire();
-      dft16<T>(re, im);
+      dft_full<T, PP>(re, im);
       const CT* twi = tws + (P::tw_offset(i) - N);
 #pragma unroll
-      for (int q = 1; q < 16; ++q) { CT w = twi[q * S + c]; cmul<T>(re[q], im[q], w.x, w.y); }
+      for (int q = 1; q < PP; ++q) { CT w = twi[q * S + c]; cmul<T>(re[q], im[q], w.x, w.y); }
       release();
 #pragma unroll
-      for (int q = 0; q < 16; ++q) ex[pb + P::phys(q * S)] = mk<T>(re[q], im[q]);
+      for (int q = 0; q < PP; ++q) ex[pb + P::phys(q * S)] = mk<T>(re[q], im[q]);
       group_sync();
     }
     // ---- last pass: radix R_LAST, NB_LAST butterflies per thread, digit-reversed reads --------
@@ -499,12 +579,12 @@ fft_fused_kernel(const FftArgs<T> a) {
 #pragma unroll
     for (int u = 0; u < NB; ++u) {
       const int b = t + TH * u;
-      const int pb = P::phys(hexrev(b, P::REV_DIGITS) * R);
+      const int pb = P::phys(digitrev<LOGR>(b, P::REV_DIGITS) * R);
 #pragma unroll
       for (int j = 0; j < R; ++j) { CT x = ex[pb + P::phys(j)]; re[u * R + j] = x.x; im[u * R + j] = x.y; }
     }
     acquire();
-    dft_last<T, R>(re, im);
+    dft_last<T, PP, R>(re, im);
 #pragma unroll
     for (int u = 0; u < NB; ++u) {
 #pragma unroll
@@ -516,6 +596,9 @@ fft_fused_kernel(const FftArgs<T> a) {
           const int s2 = (int)(f & 255);
           Epi::template store<T>(a.ep, f >> 8, N * 256, (s2 >> 4) + 16 * (s2 & 15) + 256 * k, pw);
         } else {
+#ifdef TDSA_DEBUG_SKIP_MEM
+          if (pw == T(-1.0))      // never true: keeps the arithmetic alive without the store traffic
+#endif
           Epi::template store<T>(a.ep, f, N, k, pw);
         }
       }

@@ -4,6 +4,7 @@ namespace tdsa {
 cudaError_t launch_fft_f32(int log2n, int epi, const FftArgs<float>& a, int sm, cudaStream_t s, LaunchInfo* info, bool dry) {
   return launch_fft_impl<float>(log2n, epi, a, sm, s, info, dry);
 }
+int effective_logr_f32(int log2n) { return effective_logr<float>(log2n); }
 }  // namespace tdsa
 
 #include "tdsa_big.cuh"

@@ -4,6 +4,7 @@ namespace tdsa {
 cudaError_t launch_fft_f64(int log2n, int epi, const FftArgs<double>& a, int sm, cudaStream_t s, LaunchInfo* info, bool dry) {
   return launch_fft_impl<double>(log2n, epi, a, sm, s, info, dry);
 }
+int effective_logr_f64(int log2n) { return effective_logr<double>(log2n); }
 }  // namespace tdsa
 
 #include "tdsa_big.cuh"

@@ -1,5 +1,7 @@
-// tdsa_launch.cuh — host-side dispatch of fft_fused_kernel over (size, epilogue).
+// tdsa_launch.cuh — host-side dispatch of fft_fused_kernel over (size, epilogue, staging, radix).
 #pragma once
+#include <stdlib.h>
+
 #include <algorithm>
 #include <atomic>
 
@@ -15,6 +17,7 @@ struct LaunchInfo {
   int ctas_per_sm = 0;
   int grid = 0;
   int stages = 0;
+  int logr = 4;
 };
 
 extern std::atomic<int64_t> g_launch_count;
@@ -22,13 +25,15 @@ extern std::atomic<int64_t> g_launch_count;
 // Largest single-CTA size per element type (shared-memory bound): f32 2^14, f64 2^13.
 template <typename T> struct MaxLog2 { static constexpr int value = sizeof(T) == 4 ? 14 : 13; };
 constexpr int kMinLog2 = 6;
+// radix-8 (8 points per thread) instantiations exist for these sizes
+constexpr int kMinLog2R8 = 9, kMaxLog2R8 = 13;
 
 // ---- tuning knobs (overridable at build time for A/B runs; defaults are the measured best) -------
 #ifndef TDSA_F32_TWMODE
-#define TDSA_F32_TWMODE 1      // 1: window + all pass-0 twiddles in registers, 2: six base twiddles
+#define TDSA_F32_TWMODE 1      // 1: window + all pass-0 twiddles in registers, 2: base twiddles only
 #endif
 #ifndef TDSA_F32_CTAS
-#define TDSA_F32_CTAS 2        // CTAs per SM the float32 256-thread kernels are register-bounded for
+#define TDSA_F32_CTAS 2        // CTAs per SM the float32 256-thread radix-16 kernels are register-bounded for
 #endif
 #ifndef TDSA_F64_TWMODE
 #define TDSA_F64_TWMODE 2
@@ -36,16 +41,30 @@ constexpr int kMinLog2 = 6;
 #ifndef TDSA_MAX_STAGES_F32
 #define TDSA_MAX_STAGES_F32 3
 #endif
+// MEASURED (round 1, N=4096 float64): the ping-pong CTA ran 180 us vs 167 us for two independent
+// CTAs per SM, because one 8-warp group alone cannot keep the FP64 pipe full; so it stays off.
+#ifndef TDSA_PINGPONG
+#define TDSA_PINGPONG 0
+#endif
+// default digit width per precision for sizes where both exist (runtime override: TDSA_LOGR_F32/F64)
+#ifndef TDSA_DEFAULT_LOGR_F32
+#define TDSA_DEFAULT_LOGR_F32 4
+#endif
+#ifndef TDSA_DEFAULT_LOGR_F64
+#define TDSA_DEFAULT_LOGR_F64 4
+#endif
 
-template <typename T, int LOG2N> constexpr int target_ctas() {
-  return (Plan<T, LOG2N>::THREADS >= 512) ? 1 : ((sizeof(T) == 4 && Plan<T, LOG2N>::THREADS == 256) ? TDSA_F32_CTAS : 2);
+template <typename T, int LOG2N, int LOGR> constexpr int target_ctas() {
+  constexpr int th = Plan<T, LOG2N, LOGR>::THREADS;
+  if (LOGR == 3) return th >= 1024 ? 1 : (1024 / th > 8 ? 8 : 1024 / th);      // 64 registers per thread
+  return (th >= 512) ? 1 : ((sizeof(T) == 4 && th == 256) ? TDSA_F32_CTAS : 2);
 }
 
 // How many staging buffers fit while keeping the CTAs/SM the register budget allows.
-template <typename T, int LOG2N> constexpr int pick_stages() {
-  using P = Plan<T, LOG2N>;
+template <typename T, int LOG2N, int LOGR> constexpr int pick_stages() {
+  using P = Plan<T, LOG2N, LOGR>;
   constexpr size_t kSmemPerSm = 227 * 1024;
-  constexpr int ctas = target_ctas<T, LOG2N>();
+  constexpr int ctas = target_ctas<T, LOG2N, LOGR>();
   int best = 0;
   if (LOG2N >= 9) {                            // tiny frames keep direct loads and many CTAs per SM
     for (int st = 1; st <= (sizeof(T) == 4 ? TDSA_MAX_STAGES_F32 : 2); ++st)
@@ -54,55 +73,22 @@ template <typename T, int LOG2N> constexpr int pick_stages() {
   return best;
 }
 
-template <typename T, int LOG2N, typename Epi, int TAIL, int NSTAGE>
-cudaError_t launch_staged(const FftArgs<T>& a, int sm_count, cudaStream_t stream, LaunchInfo* info, bool dry);
-
-// float64 at 256 threads per frame: one 512-thread CTA per SM holding two ping-pong frame groups
-// (see fft_fused_kernel, GROUPS); everything else keeps independent CTAs.
-// MEASURED (round 1, N=4096 float64): the ping-pong CTA ran 180 us vs 167 us for two independent
-// CTAs per SM, because one 8-warp group alone cannot keep the FP64 pipe full; so it stays off.
-#ifndef TDSA_PINGPONG
-#define TDSA_PINGPONG 0
-#endif
 template <typename T, int LOG2N, int TAIL> constexpr int pick_groups() {
-  return (TDSA_PINGPONG && sizeof(T) == 8 && TAIL == 0 && Plan<T, LOG2N>::THREADS == 256) ? 2 : 1;
+  return (TDSA_PINGPONG && sizeof(T) == 8 && TAIL == 0 && Plan<T, LOG2N, 4>::THREADS == 256) ? 2 : 1;
 }
 
-template <typename T, int LOG2N, typename Epi, int TAIL>
-cudaError_t launch_one(const FftArgs<T>& a, int sm_count, cudaStream_t stream, LaunchInfo* info, bool dry) {
-  constexpr int kStages = (TAIL == 0) ? pick_stages<T, LOG2N>() : 0;
-  if constexpr (kStages > 0) {
-    const bool aligned = (((uintptr_t)a.iq & 15) == 0) && ((a.frame_stride & 1) == 0);
-    if (aligned || dry) return launch_staged<T, LOG2N, Epi, TAIL, kStages>(a, sm_count, stream, info, dry);
-  }
-  return launch_staged<T, LOG2N, Epi, TAIL, 0>(a, sm_count, stream, info, dry);
-}
-
-template <typename T, int LOG2N, typename Epi, int TAIL, int NSTAGE, bool HAS_DC>
-cudaError_t launch_dc(const FftArgs<T>& a, int sm_count, cudaStream_t stream, LaunchInfo* info, bool dry);
-
-template <typename T, int LOG2N, typename Epi, int TAIL, int NSTAGE>
-cudaError_t launch_staged(const FftArgs<T>& a, int sm_count, cudaStream_t stream, LaunchInfo* info, bool dry) {
-  // the DC-removal variant (hackrf front end) only exists for the dB / linear epilogues of whole transforms
-  if constexpr (TAIL == 0) {
-    if (a.dc != nullptr) return launch_dc<T, LOG2N, Epi, TAIL, NSTAGE, true>(a, sm_count, stream, info, dry);
-  }
-  return launch_dc<T, LOG2N, Epi, TAIL, NSTAGE, false>(a, sm_count, stream, info, dry);
-}
-
-template <typename T, int LOG2N, typename Epi, int TAIL, int NSTAGE, bool HAS_DC>
-cudaError_t launch_dc(const FftArgs<T>& a, int sm_count, cudaStream_t stream, LaunchInfo* info, bool dry) {
-  using P = Plan<T, LOG2N>;
-  constexpr int kGroups = pick_groups<T, LOG2N, TAIL>();
+template <typename T, int LOG2N, typename Epi, int TAIL, int NSTAGE, bool HAS_DC, int LOGR>
+cudaError_t launch_final(const FftArgs<T>& a, int sm_count, cudaStream_t stream, LaunchInfo* info, bool dry) {
+  using P = Plan<T, LOG2N, LOGR>;
+  constexpr int kGroups = (LOGR == 4) ? pick_groups<T, LOG2N, TAIL>() : 1;
   constexpr size_t kSmemGroup = ((NSTAGE > 0 ? P::smem_staged(NSTAGE) : P::SMEM_BYTES) + 127) & ~(size_t)127;
   constexpr size_t kSmem = kSmemGroup * kGroups;
   constexpr int kThreads = P::THREADS * kGroups;
-  // float32: window and pass-0 twiddles stay in registers across frames (47 registers);
-  // float64 would need 94, so that path reads them through L1/L2 instead.
-  // float64 keeps six base twiddles (24 registers) and forms the rest; large CTAs read tables.
-  constexpr int kPersist = (P::THREADS > 512) ? 0 : (sizeof(T) == 4 ? TDSA_F32_TWMODE : TDSA_F64_TWMODE);
-  constexpr int kMinCtas = (kThreads >= 512) ? 1 : target_ctas<T, LOG2N>();
-  auto kern = fft_fused_kernel<T, LOG2N, Epi, kPersist, kMinCtas, TAIL, NSTAGE, kGroups, HAS_DC>;
+  // float32: window and pass-0 twiddles stay in registers across frames; float64 keeps base twiddles
+  // and forms the rest; CTAs of more than 512 threads read the tables (64-register budget).
+  constexpr int kTwMode = (kThreads > 512) ? 0 : (sizeof(T) == 4 ? TDSA_F32_TWMODE : TDSA_F64_TWMODE);
+  constexpr int kMinCtas = (kGroups > 1) ? 1 : target_ctas<T, LOG2N, LOGR>();
+  auto kern = fft_fused_kernel<T, LOG2N, Epi, kTwMode, kMinCtas, TAIL, NSTAGE, kGroups, HAS_DC, LOGR>;
   static int occ = -1;          // per instantiation, per process (single device type)
   if (occ < 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
@@ -114,28 +100,66 @@ cudaError_t launch_dc(const FftArgs<T>& a, int sm_count, cudaStream_t stream, La
   }
   const int64_t want = (int64_t)sm_count * occ;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((a.n_frames + kGroups - 1) / kGroups, want));
-  if (info) { info->threads = kThreads; info->smem = (int)kSmem; info->ctas_per_sm = occ; info->grid = grid; info->stages = NSTAGE; }
+  if (info) {
+    info->threads = kThreads; info->smem = (int)kSmem; info->ctas_per_sm = occ; info->grid = grid;
+    info->stages = NSTAGE; info->logr = LOGR;
+  }
   if (dry || a.n_frames <= 0) return cudaSuccess;
   kern<<<grid, kThreads, kSmem, stream>>>(a);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
 }
 
+// DC removal (hackrf front end) and bulk-copy staging are only compiled for whole transforms (TAIL == 0).
+template <typename T, int LOG2N, typename Epi, int TAIL, int LOGR>
+cudaError_t launch_one(const FftArgs<T>& a, int sm_count, cudaStream_t stream, LaunchInfo* info, bool dry) {
+  if constexpr (TAIL == 0) {
+    constexpr int kStages = pick_stages<T, LOG2N, LOGR>();
+    const bool aligned = (((uintptr_t)a.iq & 15) == 0) && ((a.frame_stride & 1) == 0);
+    if constexpr (kStages > 0) {
+      if (aligned || dry) {
+        if (a.dc != nullptr) return launch_final<T, LOG2N, Epi, 0, kStages, true, LOGR>(a, sm_count, stream, info, dry);
+        return launch_final<T, LOG2N, Epi, 0, kStages, false, LOGR>(a, sm_count, stream, info, dry);
+      }
+    }
+    if (a.dc != nullptr) return launch_final<T, LOG2N, Epi, 0, 0, true, LOGR>(a, sm_count, stream, info, dry);
+    return launch_final<T, LOG2N, Epi, 0, 0, false, LOGR>(a, sm_count, stream, info, dry);
+  } else {
+    return launch_final<T, LOG2N, Epi, TAIL, 0, false, LOGR>(a, sm_count, stream, info, dry);
+  }
+}
+
 // Tail kernels exist for inner sizes 2^6 .. 2^12 (N = 2^14 .. 2^20).
 constexpr int kMaxTailLog2 = 12;
 
+template <typename T> int runtime_logr() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv(sizeof(T) == 4 ? "TDSA_LOGR_F32" : "TDSA_LOGR_F64");
+    v = e ? atoi(e) : (sizeof(T) == 4 ? TDSA_DEFAULT_LOGR_F32 : TDSA_DEFAULT_LOGR_F64);
+    if (v != 3 && v != 4) v = 4;
+  }
+  return v;
+}
+
 template <typename T, int LOG2N>
 cudaError_t launch_epi(int epi, const FftArgs<T>& a, int sm_count, cudaStream_t stream, LaunchInfo* info, bool dry) {
+  if constexpr (LOG2N >= kMinLog2R8 && LOG2N <= kMaxLog2R8) {
+    if (runtime_logr<T>() == 3) {
+      if (epi == kEpiDb) return launch_one<T, LOG2N, EpiDb, 0, 3>(a, sm_count, stream, info, dry);
+      if (epi == kEpiLinear) return launch_one<T, LOG2N, EpiLinear, 0, 3>(a, sm_count, stream, info, dry);
+    }
+  }
   switch (epi) {
-    case kEpiDb: return launch_one<T, LOG2N, EpiDb, 0>(a, sm_count, stream, info, dry);
-    case kEpiLinear: return launch_one<T, LOG2N, EpiLinear, 0>(a, sm_count, stream, info, dry);
+    case kEpiDb: return launch_one<T, LOG2N, EpiDb, 0, 4>(a, sm_count, stream, info, dry);
+    case kEpiLinear: return launch_one<T, LOG2N, EpiLinear, 0, 4>(a, sm_count, stream, info, dry);
     default: break;
   }
   if constexpr (LOG2N <= kMaxTailLog2) {
     switch (epi) {
-      case kEpiDbTail: return launch_one<T, LOG2N, EpiDb, 1>(a, sm_count, stream, info, dry);
-      case kEpiLinearTail: return launch_one<T, LOG2N, EpiLinear, 1>(a, sm_count, stream, info, dry);
-      case kEpiLinearPermuted: return launch_one<T, LOG2N, EpiLinear, 2>(a, sm_count, stream, info, dry);
+      case kEpiDbTail: return launch_one<T, LOG2N, EpiDb, 1, 4>(a, sm_count, stream, info, dry);
+      case kEpiLinearTail: return launch_one<T, LOG2N, EpiLinear, 1, 4>(a, sm_count, stream, info, dry);
+      case kEpiLinearPermuted: return launch_one<T, LOG2N, EpiLinear, 2, 4>(a, sm_count, stream, info, dry);
       default: break;
     }
   }
@@ -156,9 +180,16 @@ cudaError_t launch_fft_impl(int log2n, int epi, const FftArgs<T>& a, int sm, cud
   return Dispatch<T, kMinLog2>::run(log2n, epi, a, sm, s, info, dry);
 }
 
+// which digit width launch_fft_* will use for this size (the twiddle tables must match)
+template <typename T> int effective_logr(int log2n) {
+  return (log2n >= kMinLog2R8 && log2n <= kMaxLog2R8 && runtime_logr<T>() == 3) ? 3 : 4;
+}
+
 // defined in tdsa_fft_f32.cu / tdsa_fft_f64.cu
 cudaError_t launch_fft_f32(int log2n, int epi, const FftArgs<float>& a, int sm, cudaStream_t s, LaunchInfo* info, bool dry);
 cudaError_t launch_fft_f64(int log2n, int epi, const FftArgs<double>& a, int sm, cudaStream_t s, LaunchInfo* info, bool dry);
+int effective_logr_f32(int log2n);
+int effective_logr_f64(int log2n);
 // head kernel of the two-kernel path (tdsa_big.cuh), defined next to the matching precision
 template <typename T> struct BigArgs;
 cudaError_t launch_big_head_f32(const BigArgs<float>& a, int sm, cudaStream_t s);

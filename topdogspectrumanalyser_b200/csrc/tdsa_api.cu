@@ -59,6 +59,7 @@ struct tdsa_plan {
   bool win_dirty = true;
   // large-FFT (two-kernel) tables: inner plan size M = N/256
   double2* d_twin64 = nullptr; float2* d_twin32 = nullptr;    // twiddles of the M-point inner transform
+  double2* d_twh64 = nullptr; float2* d_twh32 = nullptr;      // DIF tables of big_head_kernel (passes 0, 1)
   // scratch (grown on demand)
   void* scratch = nullptr; size_t scratch_bytes = 0;
   void* scratch2 = nullptr; size_t scratch2_bytes = 0;
@@ -144,23 +145,47 @@ static void twiddle(int64_t m, int64_t L, double* re, double* im) {
   *im = -S;
 }
 
-// Tables for an in-place DIF of 2^log2n points: radix-16 passes 0..npass-2 need
-// W_{L_i}^{c*q}; table i is laid out [q][c], c in [0, L_i/16).
-static int64_t tw_total(int log2n, int logr) {
-  const int npass = (log2n + logr - 1) / logr;
-  int64_t t = 0;
-  for (int i = 0; i < npass - 1; ++i) t += (int64_t)1 << (log2n - logr * i);
-  return t;
-}
-
-// logr = 4: radix-16 passes (table i is [16][L_i/16]); logr = 3: radix-8 passes ([8][L_i/8]).
+// Pre-twiddle tables of fft_fused_kernel (decimation-in-time placement, see Plan in tdsa_fft.cuh):
+// for pass i = 1 .. npass-1 with radix R_i, P^i already-fixed output digits K and input stride
+// S_i = N / (P^i * R_i): entry [j][K] = W_N^(j * S_i * K).  logr = 4: P = 16; logr = 3: P = 8.
 static void build_twiddles(int log2n, int logr, std::vector<double2>& t64) {
   const int npass = (log2n + logr - 1) / logr;
+  const int64_t n = (int64_t)1 << log2n;
+  if (npass > 3) {   // decimation-in-frequency placement (see Plan::DIT): table i = [q][c], W_{L_i}^(c*q)
+    t64.clear();
+    for (int i = 0; i < npass - 1; ++i) {
+      const int64_t L = (int64_t)1 << (log2n - logr * i), S = L >> logr;
+      for (int q = 0; q < (1 << logr); ++q)
+        for (int64_t c = 0; c < S; ++c) {
+          double2 w;
+          twiddle(c * q, L, &w.x, &w.y);
+          t64.push_back(w);
+        }
+    }
+    return;
+  }
+  const int r_last = (log2n % logr) ? (1 << (log2n % logr)) : (1 << logr);
   t64.clear();
-  t64.reserve(tw_total(log2n, logr));
-  for (int i = 0; i < npass - 1; ++i) {
-    const int64_t L = (int64_t)1 << (log2n - logr * i), S = L >> logr;
-    for (int q = 0; q < (1 << logr); ++q)
+  for (int i = 1; i < npass; ++i) {
+    const int64_t r = (i == npass - 1) ? r_last : ((int64_t)1 << logr);
+    const int64_t kc = (int64_t)1 << (logr * i);
+    const int64_t s = n / (kc * r);
+    for (int64_t j = 0; j < r; ++j)
+      for (int64_t k = 0; k < kc; ++k) {
+        double2 w;
+        twiddle((j * s * k) % n, n, &w.x, &w.y);
+        t64.push_back(w);
+      }
+  }
+}
+
+// Post-twiddle tables of big_head_kernel (passes 0 and 1 of the N-point in-place DIF):
+// table 0: [q][c], c < N/16: W_N^(c*q); table 1: [q][c1], c1 < N/256: W_{N/16}^(c1*q).
+static void build_twiddles_head(int log2n, std::vector<double2>& t64) {
+  t64.clear();
+  for (int i = 0; i < 2; ++i) {
+    const int64_t L = (int64_t)1 << (log2n - 4 * i), S = L >> 4;
+    for (int q = 0; q < 16; ++q)
       for (int64_t c = 0; c < S; ++c) {
         double2 w;
         twiddle(c * q, L, &w.x, &w.y);
@@ -169,18 +194,29 @@ static void build_twiddles(int log2n, int logr, std::vector<double2>& t64) {
   }
 }
 
+static int upload_pair(const std::vector<double2>& t64, double2** d64, float2** d32, bool want64, bool want32) {
+  const size_t cnt = std::max<size_t>(t64.size(), 1);
+  if (want64) {
+    CK(cudaMalloc(d64, sizeof(double2) * cnt));
+    if (!t64.empty()) CK(cudaMemcpy(*d64, t64.data(), sizeof(double2) * t64.size(), cudaMemcpyHostToDevice));
+  }
+  if (want32) {
+    std::vector<float2> t32(cnt);
+    for (size_t i = 0; i < t64.size(); ++i) t32[i] = make_float2((float)t64[i].x, (float)t64[i].y);
+    CK(cudaMalloc(d32, sizeof(float2) * cnt));
+    if (!t64.empty()) CK(cudaMemcpy(*d32, t32.data(), sizeof(float2) * t64.size(), cudaMemcpyHostToDevice));
+  }
+  return TDSA_OK;
+}
+
 // the float32 and float64 kernels of one size may use different digit widths, so each gets its own table
 static int upload_twiddles(int log2n, int logr64, int logr32, double2** d64, float2** d32) {
   std::vector<double2> t64;
   build_twiddles(log2n, logr64, t64);
-  CK(cudaMalloc(d64, sizeof(double2) * std::max<size_t>(t64.size(), 1)));
-  if (!t64.empty()) CK(cudaMemcpy(*d64, t64.data(), sizeof(double2) * t64.size(), cudaMemcpyHostToDevice));
-  if (logr32 != logr64) build_twiddles(log2n, logr32, t64);
-  std::vector<float2> t32(std::max<size_t>(t64.size(), 1));
-  for (size_t i = 0; i < t64.size(); ++i) t32[i] = make_float2((float)t64[i].x, (float)t64[i].y);
-  CK(cudaMalloc(d32, sizeof(float2) * t32.size()));
-  if (!t64.empty()) CK(cudaMemcpy(*d32, t32.data(), sizeof(float2) * t64.size(), cudaMemcpyHostToDevice));
-  return TDSA_OK;
+  int rc = upload_pair(t64, d64, d32, true, logr32 == logr64);
+  if (rc || logr32 == logr64) return rc;
+  build_twiddles(log2n, logr32, t64);
+  return upload_pair(t64, d64, d32, false, true);
 }
 
 static EpiParams make_epi(const tdsa_plan* p, float* db, double* lin) {
@@ -256,6 +292,10 @@ int tdsa_create(int n_fft, int window_id, int window_norm, int mode, double log_
       // tables for the inner (N/256)-point transform of the two-kernel path
       rc = upload_twiddles(p->log2n - 8, 4, 4, &p->d_twin64, &p->d_twin32);
       if (rc) break;
+      std::vector<double2> th;
+      build_twiddles_head(p->log2n, th);
+      rc = upload_pair(th, &p->d_twh64, &p->d_twh32, true, true);
+      if (rc) break;
     }
   } while (0);
   if (rc) { tdsa_destroy(p); return rc; }
@@ -266,7 +306,7 @@ int tdsa_create(int n_fft, int window_id, int window_norm, int mode, double log_
 int tdsa_destroy(tdsa_handle_t p) {
   if (!p) return TDSA_OK;
   cudaFree(p->d_win64); cudaFree(p->d_win32); cudaFree(p->d_tw64); cudaFree(p->d_tw32);
-  cudaFree(p->d_twin64); cudaFree(p->d_twin32);
+  cudaFree(p->d_twin64); cudaFree(p->d_twin32); cudaFree(p->d_twh64); cudaFree(p->d_twh32);
   cudaFree(p->scratch); cudaFree(p->scratch2);
   for (int i = 0; i < 2; ++i) {
     cudaFree(p->d_in[i]); cudaFree(p->d_out[i]);

@@ -30,7 +30,7 @@ static int run_big(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t strid
     if (f32) {
       BigArgs<float> a;
       a.iq = (const float2*)iq + f0 * stride; a.n_frames = nf; a.frame_stride = stride; a.window = p->d_win32;
-      a.tw = p->d_tw32; a.dc = dc ? dc + f0 : nullptr; a.y = (float2*)p->scratch2; a.log2n = p->log2n;
+      a.tw = p->d_twh32; a.dc = dc ? dc + f0 : nullptr; a.y = (float2*)p->scratch2; a.log2n = p->log2n;
       e = launch_big_head_f32(a, p->sm_count, p->stream);
       if (e == cudaSuccess) {
         FftArgs<float> t;
@@ -41,7 +41,7 @@ static int run_big(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t strid
     } else {
       BigArgs<double> a;
       a.iq = (const float2*)iq + f0 * stride; a.n_frames = nf; a.frame_stride = stride; a.window = p->d_win64;
-      a.tw = p->d_tw64; a.dc = dc ? dc + f0 : nullptr; a.y = (double2*)p->scratch2; a.log2n = p->log2n;
+      a.tw = p->d_twh64; a.dc = dc ? dc + f0 : nullptr; a.y = (double2*)p->scratch2; a.log2n = p->log2n;
       e = launch_big_head_f64(a, p->sm_count, p->stream);
       if (e == cudaSuccess) {
         FftArgs<double> t;

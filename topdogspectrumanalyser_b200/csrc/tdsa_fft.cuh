@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace tdsa {
 
 // radix-8 padding table (filled from tools/fft_plan_model.py r8 banks); generic fallback otherwise
@@ -134,33 +136,78 @@ template <typename T> __device__ __forceinline__ void mul_mi(T& xr, T& xi) {
   xr = r; xi = i;
 }
 
+template <typename T> __device__ __forceinline__ T fm(T a, T b, T c);
+template <> __device__ __forceinline__ float fm<float>(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+template <> __device__ __forceinline__ double fm<double>(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+// Radix-4 butterfly whose inputs carry twiddles: a[Ik] stands for w[Ik]*a[Ik] (w[I0] == 1 when W0_ONE).
+// The twiddle multiplies are folded into the first radix-2 level:
+//   z0 = w0*a0;  t0 = z0 + w2*a2 (4 FMA);  t1 = 2*z0 - t0 (2 FMA)   — 10 ops instead of 12 per pair.
+template <typename T, int I0, int I1, int I2, int I3, bool W0_ONE>
+__device__ __forceinline__ void r4_tw(T* re, T* im, const T* wr, const T* wi) {
+  T z0r, z0i;
+  if constexpr (W0_ONE) { z0r = re[I0]; z0i = im[I0]; }
+  else { z0r = fm<T>(re[I0], wr[I0], -(im[I0] * wi[I0])); z0i = fm<T>(re[I0], wi[I0], im[I0] * wr[I0]); }
+  const T t0r = fm<T>(re[I2], wr[I2], fm<T>(-im[I2], wi[I2], z0r));
+  const T t0i = fm<T>(re[I2], wi[I2], fm<T>(im[I2], wr[I2], z0i));
+  const T t1r = fm<T>(T(2), z0r, -t0r), t1i = fm<T>(T(2), z0i, -t0i);
+  const T z1r = fm<T>(re[I1], wr[I1], -(im[I1] * wi[I1])), z1i = fm<T>(re[I1], wi[I1], im[I1] * wr[I1]);
+  const T t2r = fm<T>(re[I3], wr[I3], fm<T>(-im[I3], wi[I3], z1r));
+  const T t2i = fm<T>(re[I3], wi[I3], fm<T>(im[I3], wr[I3], z1i));
+  const T t3r = fm<T>(T(2), z1r, -t2r), t3i = fm<T>(T(2), z1i, -t2i);
+  re[I0] = t0r + t2r; im[I0] = t0i + t2i;
+  re[I2] = t0r - t2r; im[I2] = t0i - t2i;
+  re[I1] = t1r + t3i; im[I1] = t1i - t3r;   // t1 - i*t3
+  re[I3] = t1r - t3i; im[I3] = t1i + t3r;   // t1 + i*t3
+}
+
+// Second half of the 16-point DFT: four radix-4 butterflies over j0 whose inputs B[j0][q0] = a[4*q0 + j0]
+// carry the constant twiddles W16^(j0*q0), folded in the same way; then the 4x4 transpose to natural order.
+template <typename T> __device__ __forceinline__ void dft16_stage_b(T* re, T* im) {
+  constexpr T c1 = T(0.92387953251128675613);   // cos(pi/8)
+  constexpr T s1 = T(0.38268343236508977173);   // sin(pi/8)
+  constexpr T h = T(0.70710678118654752440);    // sqrt(1/2)
+  r4<T, 0, 1, 2, 3>(re, im);                                      // q0 = 0: no twiddles
+  {                                                               // q0 = 1: 1, W16^1, W16^2, W16^3
+    const T wr[4] = {T(1), c1, h, s1}, wi[4] = {T(0), -s1, -h, -c1};
+    r4_tw<T, 0, 1, 2, 3, true>(re + 4, im + 4, wr, wi);
+  }
+  {                                                               // q0 = 2: 1, W16^2, -i, W16^6
+    const T t0r = re[8] + im[10], t0i = im[8] - re[10];           // a8 + (-i)*a10
+    const T t1r = re[8] - im[10], t1i = im[8] + re[10];
+    const T u9r = re[9] + im[9], u9i = im[9] - re[9];             // (1 - i)*a9   (times h below)
+    const T u11r = im[11] - re[11], u11i = -(re[11] + im[11]);    // (-1 - i)*a11 (times h below)
+    const T sr = u9r + u11r, si = u9i + u11i, dr = u9r - u11r, di = u9i - u11i;
+    re[8] = fm<T>(h, sr, t0r);   im[8] = fm<T>(h, si, t0i);       // t0 + t2
+    re[10] = fm<T>(-h, sr, t0r); im[10] = fm<T>(-h, si, t0i);     // t0 - t2
+    re[9] = fm<T>(h, di, t1r);   im[9] = fm<T>(-h, dr, t1i);      // t1 - i*t3
+    re[11] = fm<T>(-h, di, t1r); im[11] = fm<T>(h, dr, t1i);      // t1 + i*t3
+  }
+  {                                                               // q0 = 3: 1, W16^3, W16^6, W16^9
+    const T wr[4] = {T(1), s1, -h, -c1}, wi[4] = {T(0), -c1, -h, s1};
+    r4_tw<T, 0, 1, 2, 3, true>(re + 12, im + 12, wr, wi);
+  }
+  swp<T, 1, 4>(re, im);  swp<T, 2, 8>(re, im);  swp<T, 3, 12>(re, im);
+  swp<T, 6, 9>(re, im);  swp<T, 7, 13>(re, im); swp<T, 11, 14>(re, im);
+}
+
 // 16-point DFT over registers [0, 16), natural order in and out: a[q] = sum_j a[j] W16^(jq).
 template <typename T> __device__ __forceinline__ void dft16(T* re, T* im) {
-  const T c1 = T(0.92387953251128675613);   // cos(pi/8)
-  const T s1 = T(0.38268343236508977173);   // sin(pi/8)
   // stage A: over j1 (stride 4); a[j0 + 4*q0] = B[j0][q0]
   r4<T, 0, 4, 8, 12>(re, im);
   r4<T, 1, 5, 9, 13>(re, im);
   r4<T, 2, 6, 10, 14>(re, im);
   r4<T, 3, 7, 11, 15>(re, im);
-  // twiddle B[j0][q0] *= W16^(j0*q0)
-  cmul<T>(re[5], im[5], c1, -s1);           // j0=1,q0=1 : W16^1
-  mul_w8_1<T>(re[9], im[9]);                // j0=1,q0=2 : W16^2
-  cmul<T>(re[13], im[13], s1, -c1);         // j0=1,q0=3 : W16^3
-  mul_w8_1<T>(re[6], im[6]);                // j0=2,q0=1 : W16^2
-  mul_mi<T>(re[10], im[10]);                // j0=2,q0=2 : W16^4
-  mul_w8_3<T>(re[14], im[14]);              // j0=2,q0=3 : W16^6
-  cmul<T>(re[7], im[7], s1, -c1);           // j0=3,q0=1 : W16^3
-  mul_w8_3<T>(re[11], im[11]);              // j0=3,q0=2 : W16^6
-  cmul<T>(re[15], im[15], -c1, s1);         // j0=3,q0=3 : W16^9
-  // stage B: over j0; a[4*q0 + q1] = A[q0 + 4*q1]
-  r4<T, 0, 1, 2, 3>(re, im);
-  r4<T, 4, 5, 6, 7>(re, im);
-  r4<T, 8, 9, 10, 11>(re, im);
-  r4<T, 12, 13, 14, 15>(re, im);
-  // 4x4 transpose to natural order
-  swp<T, 1, 4>(re, im);  swp<T, 2, 8>(re, im);  swp<T, 3, 12>(re, im);
-  swp<T, 6, 9>(re, im);  swp<T, 7, 13>(re, im); swp<T, 11, 14>(re, im);
+  dft16_stage_b<T>(re, im);
+}
+
+// Same transform of the twiddled inputs w[j]*a[j] (w[0] == 1), the twiddles folded into stage A.
+template <typename T> __device__ __forceinline__ void dft16_pretw(T* re, T* im, const T* wr, const T* wi) {
+  r4_tw<T, 0, 4, 8, 12, true>(re, im, wr, wi);
+  r4_tw<T, 1, 5, 9, 13, false>(re, im, wr, wi);
+  r4_tw<T, 2, 6, 10, 14, false>(re, im, wr, wi);
+  r4_tw<T, 3, 7, 11, 15, false>(re, im, wr, wi);
+  dft16_stage_b<T>(re, im);
 }
 
 // R-point DFTs (R = 2, 4, 8) over registers [O, O+R), natural order in and out.
@@ -204,6 +251,17 @@ template <typename T, int O> struct DftSmall<T, 8, O> {
 // P-point DFT over all P registers of a thread (P = 16 or 8)
 template <typename T, int P> __device__ __forceinline__ void dft_full(T* re, T* im) {
   if constexpr (P == 16) dft16<T>(re, im); else DftSmall<T, 8, 0>::run(re, im);
+}
+
+// P-point DFT of pre-twiddled inputs (w[0] == 1): fused for P == 16, plain multiplies otherwise
+template <typename T, int P> __device__ __forceinline__ void dft_full_pretw(T* re, T* im, const T* wr, const T* wi) {
+  if constexpr (P == 16) {
+    dft16_pretw<T>(re, im, wr, wi);
+  } else {
+#pragma unroll
+    for (int j = 1; j < P; ++j) cmul<T>(re[j], im[j], wr[j], wi[j]);
+    dft_full<T, P>(re, im);
+  }
 }
 
 // last pass: P/R independent R-point DFTs over consecutive register groups
@@ -269,14 +327,29 @@ template <typename T, int LOG2N, int LOGR = 4> struct Plan {
   static constexpr int PHYS_SIZE = phys(N - 1) + 1;
   static __host__ __device__ constexpr int len(int i) { return N >> (LOGR * i); }             // L_i
   static __host__ __device__ constexpr int stride(int i) { return N >> (LOGR * (i + 1)); }    // S_i
-  static __host__ __device__ constexpr int tw_offset(int i) {   // entries before pass i's table
+  // Twiddles sit on the INPUT side of passes 1..NPASS-1 (decimation-in-time placement): input j of a
+  // butterfly whose already-known output digits are K = k0 + P*k1 + ... is multiplied by W_N^(j*S_i*K).
+  // Table of pass i: [j < R_i][K < P^i]; tables are concatenated in pass order starting at pass 1.
+  static __host__ __device__ constexpr int radix(int i) { return i == NPASS - 1 ? R_LAST : P; }
+  static __host__ __device__ constexpr int kcount(int i) { return 1 << (LOGR * i); }            // P^i
+  static __host__ __device__ constexpr int tw_offset(int i) {   // entries before pass i's table (i >= 1)
+    int o = 0;
+    for (int k = 1; k < i; ++k) o += radix(k) * kcount(k);
+    return o;
+  }
+  // Plans of more than three passes keep the decimation-in-frequency placement instead (twiddle
+  // W_{L_i}^(c*q) on OUTPUT q of pass i, table i = [q][c], c < S_i): there the DIT tables of the late
+  // passes would be too large for shared memory, while the DIF tables of passes >= 1 are small.
+  static constexpr bool DIT = NPASS <= 3;
+  static __host__ __device__ constexpr int dif_offset(int i) {
     int o = 0;
     for (int k = 0; k < i; ++k) o += len(k);
     return o;
   }
-  static constexpr int TW_TOTAL = tw_offset(NPASS - 1);          // all non-last passes
-  static constexpr int TW_SMEM = TW_TOTAL - N;                   // passes >= 1 (kept in shared memory)
-  static constexpr size_t SMEM_BYTES = (size_t)(PHYS_SIZE + (TW_SMEM > 0 ? TW_SMEM : 0)) * 2 * sizeof(T);
+  static constexpr int TW_TOTAL = DIT ? tw_offset(NPASS) : dif_offset(NPASS - 1);
+  // shared-memory resident tables: DIT: pass 1's P*P table when it is a middle pass; DIF: passes >= 1
+  static constexpr int TW_SMEM = DIT ? ((NPASS >= 3) ? P * P : 0) : (dif_offset(NPASS - 1) - N);
+  static constexpr size_t SMEM_BYTES = (size_t)(PHYS_SIZE + TW_SMEM) * 2 * sizeof(T);
   // bulk-copy staging: NSTAGE buffers of one complex64 frame each + one mbarrier per stage
   static constexpr size_t STAGE_BYTES = (size_t)N * 8;
   static constexpr size_t STAGE_OFFSET = (SMEM_BYTES + 127) & ~(size_t)127;
@@ -304,26 +377,32 @@ struct EpiParams {
   int mode;
 };
 
-// dB from linear power. T-typed so the float64 path adds the floor before narrowing.
-template <typename T> __device__ __forceinline__ float to_db(T p, const EpiParams& ep) {
+// dB from linear power; MAG20 is a compile-time flag so the per-element path has no branch.
+template <typename T, bool MAG20> __device__ __forceinline__ float to_db_m(T p, const EpiParams& ep) {
   const float kDbPerLog2 = 3.01029995663981195f;   // 10*log10(2)
-  if (ep.mode == kModeMag20) {
-    float m = sqrtf((float)p) + (float)ep.floor;
+  if constexpr (MAG20) {
+    const float m = sqrtf((float)p) + (float)ep.floor;
     return 2.0f * kDbPerLog2 * lg2_approx(m);
+  } else {
+    // scale in T, then narrow once; the floor (1e-10 / 1e-12) is added in float32: it only matters when the
+    // scaled power is itself that small, where float32 still resolves it to 6e-8 relative.
+    const float v = (float)(p * (T)ep.scale) + (float)ep.floor;
+    return kDbPerLog2 * lg2_approx(v);
   }
-  // scale in T, then narrow once; the floor (1e-10 / 1e-12) is added in float32: it only matters when the
-  // scaled power is itself that small, where float32 still resolves it to 6e-8 relative.
-  const float v = (float)(p * (T)ep.scale) + (float)ep.floor;
-  return kDbPerLog2 * lg2_approx(v);
+}
+template <typename T> __device__ __forceinline__ float to_db(T p, const EpiParams& ep) {
+  return ep.mode == kModeMag20 ? to_db_m<T, true>(p, ep) : to_db_m<T, false>(p, ep);
 }
 
 struct EpiDb {
-  template <typename T> static __device__ __forceinline__ void store(const EpiParams& ep, int64_t f, int n, int k, T p) {
-    ep.db_out[f * n + k] = to_db<T>(p, ep);
+  template <typename T, bool MAG20>
+  static __device__ __forceinline__ void store(const EpiParams& ep, int64_t f, int n, int k, T p) {
+    ep.db_out[f * n + k] = to_db_m<T, MAG20>(p, ep);
   }
 };
 struct EpiLinear {
-  template <typename T> static __device__ __forceinline__ void store(const EpiParams& ep, int64_t f, int n, int k, T p) {
+  template <typename T, bool MAG20>
+  static __device__ __forceinline__ void store(const EpiParams& ep, int64_t f, int n, int k, T p) {
     ep.lin_out[f * n + k] = (double)p * ep.scale;
   }
 };
@@ -336,7 +415,7 @@ template <typename T> struct FftArgs {
   int64_t n_frames;
   int64_t frame_stride;        // in complex samples
   const T* window;             // T[N], includes the (-1)^n fftshift factor
-  const typename CplxOf<T>::type* tw;   // twiddles for passes 0..NPASS-2, [pass][q][c]
+  const typename CplxOf<T>::type* tw;   // pre-twiddle tables of passes 1..NPASS-1, each [j][K] (see Plan)
   const double2* dc;           // optional per-frame DC estimate to subtract (hackrf path) or nullptr
   const typename CplxOf<T>::type* in_ct;   // TAIL kernels: complex T input [n_frames][N] (no window)
   EpiParams ep;
@@ -422,30 +501,47 @@ fft_fused_kernel(const FftArgs<T> a) {
     }
   }
 
-  // one-time: stage the small (pass >= 1) twiddle tables in shared memory
+  // one-time: the small tables into shared memory (DIT: pass 1's [j][K]; DIF: the tables of passes >= 1)
+  constexpr bool DIT = P::DIT;
   if constexpr (P::TW_SMEM > 0) {
-    for (int i = t; i < P::TW_SMEM; i += TH) tws[i] = a.tw[N + i];
+    for (int i = t; i < P::TW_SMEM; i += TH) tws[i] = a.tw[(DIT ? 0 : N) + i];
   }
-  // one-time: per-thread constants that do not change from frame to frame
+  // one-time: per-thread constants that do not change from frame to frame: the window values of
+  // pass 0 and the pre-twiddles of the LAST pass, W_N^(j * b) with b = t + TH*u (register index u*R + j)
+  constexpr int R = P::R_LAST, NB = P::NB_LAST;
+  constexpr int KLAST = N / R;                                   // entries per j in the last pass's table
+  // the per-thread table: DIT = last pass's pre-twiddles [j][b]; DIF = pass 0's post-twiddles [q][t]
+  const CT* tw_last = DIT ? a.tw + P::tw_offset(NPASS - 1) : a.tw;
+  // base-twiddle mode needs 16 twiddles W^(j*x) per thread: a radix-16 last pass (DIT) or pass 0 (DIF);
+  // otherwise fall back to registers for small CTAs (registers to spare) or per-frame loads
+  constexpr int TWM = (TWMODE == 2 && (DIT ? R != 16 : PP != 16)) ? (TH <= 128 ? 1 : 0) : TWMODE;
   T win[PP];
-  T tw0r[TWMODE != 0 ? PP : 1], tw0i[TWMODE != 0 ? PP : 1];
-  if constexpr (TWMODE == 1) {
+  T twlr[TWM != 0 ? PP : 1], twli[TWM != 0 ? PP : 1];
+  if constexpr (TWM == 1) {
     if constexpr (TAIL == 0) {
 #pragma unroll
       for (int j = 0; j < PP; ++j) win[j] = a.window[t + j * TH];
     }
+    if constexpr (DIT) {
 #pragma unroll
-    for (int q = 1; q < PP; ++q) { CT w = a.tw[q * TH + t]; tw0r[q] = w.x; tw0i[q] = w.y; }
-  } else if constexpr (TWMODE == 2) {
+      for (int u = 0; u < NB; ++u)
 #pragma unroll
-    for (int q = 1; q < PP; ++q) {
-      if (q < 4 || (q & 3) == 0) { CT w = a.tw[q * TH + t]; tw0r[q] = w.x; tw0i[q] = w.y; }
+        for (int j = 1; j < R; ++j) { const CT w = tw_last[j * KLAST + t + TH * u]; twlr[u * R + j] = w.x; twli[u * R + j] = w.y; }
+    } else {
+#pragma unroll
+      for (int q = 1; q < PP; ++q) { const CT w = tw_last[q * TH + t]; twlr[q] = w.x; twli[q] = w.y; }
+    }
+  } else if constexpr (TWM == 2) {
+#pragma unroll
+    for (int j = 1; j < 16; ++j) {
+      if (j < 4 || (j & 3) == 0) { const CT w = tw_last[j * (DIT ? KLAST : TH) + t]; twlr[j] = w.x; twli[j] = w.y; }
     }
   }
   if constexpr (P::TW_SMEM > 0 || NSTAGE > 0) __syncthreads();   // tables staged, mbarriers initialised
   if constexpr (GROUPS > 1) {
     if (g == 1) bar_arrive(3, 2 * TH);                           // group 0 owns the first compute phase
   }
+  const bool mag20 = a.ep.mode == kModeMag20;
 
   // Both groups run the same number of iterations so that the token hand-offs always pair up;
   // a group without a frame in the last iteration only passes the token on.
@@ -461,14 +557,14 @@ fft_fused_kernel(const FftArgs<T> a) {
       continue;
     }
     T re[PP], im[PP];
-    // ---- pass 0: global/staged -> registers, window, full-radix DFT, twiddle ----------------
+    // ---- pass 0: global/staged -> registers, window, full-radix DFT (no twiddles) -------------
     if constexpr (TAIL != 0) {
       const CT* src = a.in_ct + f * N + t;
 #pragma unroll
       for (int j = 0; j < PP; ++j) { const CT x = src[j * TH]; re[j] = x.x; im[j] = x.y; }
       acquire();
     } else {
-      if constexpr (TWMODE != 1) {          // issue the table loads before waiting on the frame
+      if constexpr (TWM != 1) {             // issue the table loads before waiting on the frame
 #pragma unroll
         for (int j = 0; j < PP; ++j) win[j] = a.window[t + j * TH];
       }
@@ -477,7 +573,7 @@ fft_fused_kernel(const FftArgs<T> a) {
       float2 v[PP];
       if constexpr (NSTAGE > 0) {
         const int stg = it % NSTAGE;
-#ifdef TDSA_DEBUG_SKIP_MEM      // diagnostic build: the ring is filled once and never refilled
+#if defined(TDSA_DEBUG_SKIP_MEM) || defined(TDSA_DEBUG_SKIP_LOAD)   // diagnostic: ring filled once, never refilled
         if (it < NSTAGE)
 #endif
         mbar_wait(bar_u32 + 8 * stg, (uint32_t)((it / NSTAGE) & 1));
@@ -501,36 +597,18 @@ fft_fused_kernel(const FftArgs<T> a) {
         }
       }
     }
-#ifdef TDSA_DEBUG_SKIP_MATH     // diagnostic build: memory pipeline only (results are wrong by design)
-    if (a.n_frames >= 0) {
-#pragma unroll
-      for (int q = 0; q < PP; ++q) Epi::template store<T>(a.ep, f, N, t + TH * q, re[q] * re[q] + im[q] * im[q]);
-      group_sync();
-      if constexpr (NSTAGE > 0) {
-        if (t == 0) {
-          const int64_t fn = f + (int64_t)NSTAGE * unit_stride;
-          if (fn < a.n_frames) {
-            const int stg = it % NSTAGE;
-            fence_proxy_async();
-            mbar_arrive_expect_tx(bar_u32 + 8 * stg, (uint32_t)P::STAGE_BYTES);
-            bulk_g2s(stage_u32 + (uint32_t)(stg * P::STAGE_BYTES), a.iq + fn * a.frame_stride, (uint32_t)P::STAGE_BYTES,
-                     bar_u32 + 8 * stg);
-          }
-        }
-      }
-      continue;
-    }
-#endif
     dft_full<T, PP>(re, im);
+    if constexpr (!DIT) {                    // DIF: post-twiddle W_N^(t*q)
 #pragma unroll
-    for (int q = 1; q < PP; ++q) {
-      T wr, wi;
-      if constexpr (TWMODE == 1) { wr = tw0r[q]; wi = tw0i[q]; }
-      else if constexpr (TWMODE == 2) {
-        if (q < 4 || (q & 3) == 0) { wr = tw0r[q]; wi = tw0i[q]; }
-        else { wr = tw0r[q & 3]; wi = tw0i[q & 3]; cmul<T>(wr, wi, tw0r[q & ~3], tw0i[q & ~3]); }
-      } else { CT w = a.tw[q * TH + t]; wr = w.x; wi = w.y; }
-      cmul<T>(re[q], im[q], wr, wi);
+      for (int q = 1; q < PP; ++q) {
+        T wr, wi;
+        if constexpr (TWM == 1) { wr = twlr[q]; wi = twli[q]; }
+        else if constexpr (TWM == 2) {
+          if (q < 4 || (q & 3) == 0) { wr = twlr[q]; wi = twli[q]; }
+          else { wr = twlr[q & 3]; wi = twli[q & 3]; cmul<T>(wr, wi, twlr[q & ~3], twli[q & ~3]); }
+        } else { const CT w = tw_last[q * TH + t]; wr = w.x; wi = w.y; }
+        cmul<T>(re[q], im[q], wr, wi);
+      }
     }
     release();
     {
@@ -541,7 +619,7 @@ fft_fused_kernel(const FftArgs<T> a) {
     group_sync();
     if constexpr (NSTAGE > 0) {
       // every thread of the group has consumed this stage (its reads precede the barrier): refill it
-#ifndef TDSA_DEBUG_SKIP_MEM
+#if !defined(TDSA_DEBUG_SKIP_MEM) && !defined(TDSA_DEBUG_SKIP_LOAD)
       if (t == 0) {
         const int64_t fn = f + (int64_t)NSTAGE * unit_stride;
         if (fn < a.n_frames) {
@@ -556,26 +634,38 @@ fft_fused_kernel(const FftArgs<T> a) {
       }
 #endif
     }
-    // ---- middle passes (full radix, in place, one butterfly per thread) ----------------------
+    // ---- middle passes (full radix, in place, one butterfly per thread, pre-twiddled inputs) ---
 #pragma unroll
     for (int i = 1; i < NPASS - 1; ++i) {
       const int L = N >> (LOGR * i), S = N >> (LOGR * (i + 1));
       const int c = t & (S - 1), s = t / S;
       const int pb = P::phys(s * L + c);
+      if constexpr (DIT) {
+        const int K = digitrev<LOGR>(s, i);                      // output digits fixed by passes 0..i-1
+        const CT* tab = tws + K;                                 // DIT plans have one middle pass (i == 1)
+        T wr[PP], wi[PP];
+        wr[0] = T(1); wi[0] = T(0);
 #pragma unroll
-      for (int j = 0; j < PP; ++j) { CT x = ex[pb + P::phys(j * S)]; re[j] = x.x; im[j] = x.y; }
-      acquire();
-      dft_full<T, PP>(re, im);
-      const CT* twi = tws + (P::tw_offset(i) - N);
+        for (int j = 1; j < PP; ++j) { const CT w = tab[j * P::kcount(i)]; wr[j] = w.x; wi[j] = w.y; }
 #pragma unroll
-      for (int q = 1; q < PP; ++q) { CT w = twi[q * S + c]; cmul<T>(re[q], im[q], w.x, w.y); }
+        for (int j = 0; j < PP; ++j) { CT x = ex[pb + P::phys(j * S)]; re[j] = x.x; im[j] = x.y; }
+        acquire();
+        dft_full_pretw<T, PP>(re, im, wr, wi);
+      } else {
+#pragma unroll
+        for (int j = 0; j < PP; ++j) { CT x = ex[pb + P::phys(j * S)]; re[j] = x.x; im[j] = x.y; }
+        acquire();
+        dft_full<T, PP>(re, im);
+        const CT* twi_ = tws + (P::dif_offset(i) - N);
+#pragma unroll
+        for (int q = 1; q < PP; ++q) { const CT w = twi_[q * S + c]; cmul<T>(re[q], im[q], w.x, w.y); }
+      }
       release();
 #pragma unroll
       for (int q = 0; q < PP; ++q) ex[pb + P::phys(q * S)] = mk<T>(re[q], im[q]);
       group_sync();
     }
-    // ---- last pass: radix R_LAST, NB_LAST butterflies per thread, digit-reversed reads --------
-    constexpr int R = P::R_LAST, NB = P::NB_LAST;
+    // ---- last pass: radix R, NB butterflies per thread, digit-reversed reads, pre-twiddled ------
 #pragma unroll
     for (int u = 0; u < NB; ++u) {
       const int b = t + TH * u;
@@ -584,25 +674,50 @@ fft_fused_kernel(const FftArgs<T> a) {
       for (int j = 0; j < R; ++j) { CT x = ex[pb + P::phys(j)]; re[u * R + j] = x.x; im[u * R + j] = x.y; }
     }
     acquire();
-    dft_last<T, PP, R>(re, im);
+    if constexpr (!DIT) {
+      dft_last<T, PP, R>(re, im);
+    } else {
+      T wr[PP], wi[PP];
 #pragma unroll
-    for (int u = 0; u < NB; ++u) {
+      for (int u = 0; u < NB; ++u) {
+        wr[u * R] = T(1); wi[u * R] = T(0);
 #pragma unroll
-      for (int q = 0; q < R; ++q) {
-        const int k = t + TH * u + (N / R) * q;
-        const int e = u * R + q;
-        const T pw = re[e] * re[e] + im[e] * im[e];
-        if constexpr (TAIL == 1) {
-          const int s2 = (int)(f & 255);
-          Epi::template store<T>(a.ep, f >> 8, N * 256, (s2 >> 4) + 16 * (s2 & 15) + 256 * k, pw);
-        } else {
-#ifdef TDSA_DEBUG_SKIP_MEM
-          if (pw == T(-1.0))      // never true: keeps the arithmetic alive without the store traffic
-#endif
-          Epi::template store<T>(a.ep, f, N, k, pw);
+        for (int j = 1; j < R; ++j) {
+          const int e = u * R + j;
+          if constexpr (TWM == 1) { wr[e] = twlr[e]; wi[e] = twli[e]; }
+          else if constexpr (TWM == 2) {
+            if (j < 4 || (j & 3) == 0) { wr[e] = twlr[j]; wi[e] = twli[j]; }
+            else { wr[e] = twlr[j & 3]; wi[e] = twli[j & 3]; cmul<T>(wr[e], wi[e], twlr[j & ~3], twli[j & ~3]); }
+          } else { const CT w = tw_last[j * KLAST + t + TH * u]; wr[e] = w.x; wi[e] = w.y; }
         }
       }
+      if constexpr (R == 16 && PP == 16) {
+        dft16_pretw<T>(re, im, wr, wi);
+      } else {
+#pragma unroll
+        for (int e = 0; e < PP; ++e) { if (e % R != 0) cmul<T>(re[e], im[e], wr[e], wi[e]); }
+        dft_last<T, PP, R>(re, im);
+      }
     }
+    auto emit = [&](auto mag_tag) {
+      constexpr bool MAG = decltype(mag_tag)::value;
+#pragma unroll
+      for (int u = 0; u < NB; ++u) {
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          const int k = t + TH * u + (N / R) * q;
+          const int e = u * R + q;
+          const T pw = re[e] * re[e] + im[e] * im[e];
+          if constexpr (TAIL == 1) {
+            const int s2 = (int)(f & 255);
+            Epi::template store<T, MAG>(a.ep, f >> 8, N * 256, (s2 >> 4) + 16 * (s2 & 15) + 256 * k, pw);
+          } else {
+            Epi::template store<T, MAG>(a.ep, f, N, k, pw);
+          }
+        }
+      }
+    };
+    if (mag20) emit(std::true_type{}); else emit(std::false_type{});
     release();
     group_sync();   // exchange buffer is reused by the next frame's pass 0
   }

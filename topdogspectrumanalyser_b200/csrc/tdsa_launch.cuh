@@ -73,8 +73,10 @@ template <typename T, int LOG2N, int LOGR> constexpr int pick_stages() {
   return best;
 }
 
+// TDSA_PINGPONG: 0 = off, 1 = float64 only, 2 = float32 only, 3 = both (N/16 == 256 threads per frame only)
 template <typename T, int LOG2N, int TAIL> constexpr int pick_groups() {
-  return (TDSA_PINGPONG && sizeof(T) == 8 && TAIL == 0 && Plan<T, LOG2N, 4>::THREADS == 256) ? 2 : 1;
+  constexpr bool on = (sizeof(T) == 8) ? (TDSA_PINGPONG & 1) : (TDSA_PINGPONG & 2);
+  return (on && TAIL == 0 && Plan<T, LOG2N, 4>::THREADS == 256) ? 2 : 1;
 }
 
 template <typename T, int LOG2N, typename Epi, int TAIL, int NSTAGE, bool HAS_DC, int LOGR>

@@ -164,6 +164,49 @@ int tdsa_trace_update(const float* rows, int64_t n_rows, int64_t width, double c
                       float* max_hold, float* min_hold, int32_t* hold_valid_host, float* rows_out,
                       void* cuda_stream, int32_t* row_flags_scratch);
 
+/* tdsa_trace_update with the tare ("normalisation") stage of display_data_processor.py:329-369 between the
+ * cal offset and the holds: while collecting, 10^(dB/10) of each row is accumulated in tare_buf; after
+ * tare_target rows (UIConstants.TARE_NUM_SAMPLES = 32) the baseline 10*log10(max(mean, 1e-30)) is captured
+ * into tare_baseline and subtracted from that row on. tare_flags_host: HOST int32[2] {collecting, active};
+ * tare_count_host: HOST int32 (TareState.count). tare_buf / tare_baseline: device float64[width]. */
+int tdsa_trace_update_tare(const float* rows, int64_t n_rows, int64_t width, double cal_offset_db,
+                           int avg_mode, int avg_n, double* avg_state, int32_t* count_state_host,
+                           float* max_hold, float* min_hold, int32_t* hold_valid_host, float* rows_out,
+                           void* cuda_stream, int32_t* row_flags_scratch, int32_t* tare_flags_host,
+                           int32_t* tare_count_host, int tare_target, double* tare_buf,
+                           double* tare_baseline);
+
+/* Waterfall colour map, core/export_manager.py:72-79: index = uint8(clip((x - lo)/max(hi - lo, 1e-9), 0, 1) * 255)
+ * in float32, rgba_out[i] = lut_rgba[index] (lut: device uint8[256][4]; rgba_out: device uint8[n][4]). */
+int tdsa_colormap_rgba(const float* rows, int64_t n, float lo_db, float hi_db, const uint8_t* lut_rgba,
+                       uint8_t* rgba_out, void* cuda_stream);
+
+/* Density (persistence) histogram, displays/density_display.py:306-319: hist float32 [width][512] over
+ * -200..+100 dB; hist *= float32(decay) when decay < 1, then +1 in the bin of every non-NaN live_db value. */
+int tdsa_density_update(const float* live_db, int64_t width, double decay, float* hist, void* cuda_stream);
+
+/* Band power between two markers, core/marker_manager.py:308-318; out: device float64[1] (NaN if no bin). */
+int tdsa_band_power(const double* bins, const float* levels, int64_t width, double f_lo, double f_hi,
+                    double* out, void* cuda_stream);
+
+/* Top-n peak list, core/display_data_processor.py:432-471 (_find_top_peaks: strict local maxima by
+ * decreasing power, min separation in bins and min valley excursion in dB). width <= 16384, n <= 16.
+ * idx_out int32[n], pwr_out float32[n], count_out int32[1], all device. */
+int tdsa_top_peaks(const float* power, int64_t width, int n, int min_sep_bins, float min_excursion_db,
+                   int32_t* idx_out, float* pwr_out, int32_t* count_out, void* cuda_stream);
+
+/* hackrf_sweep wire formats -> row arrays for tdsa_stitch (HOST functions, no GPU involved).
+ * CSV (datasources/hackrf_sweep.py:135-146): "date, time, hz_low, hz_high, bin_width, num_samples, dB...";
+ * binary -B (datasources/hackrf_sweep_binary_reference.py:29-43): uint32 length, uint64 lo, uint64 hi, float32[].
+ * Outputs (host): lo_hz/hi_hz double[max_rows], values float32[max_rows][max_bins], n_bins int32[max_rows].
+ * Malformed lines / records are skipped like the reference does; *consumed_out = bytes fully parsed. */
+int tdsa_parse_sweep_csv_host(const char* text, int64_t len, int64_t max_rows, int64_t max_bins, double* lo_hz,
+                              double* hi_hz, float* values, int32_t* n_bins, int64_t* n_rows_out,
+                              int64_t* consumed_out);
+int tdsa_parse_sweep_binary_host(const uint8_t* buf, int64_t len, int64_t max_rows, int64_t max_bins,
+                                 double* lo_hz, double* hi_hz, float* values, int32_t* n_bins,
+                                 int64_t* n_rows_out, int64_t* consumed_out);
+
 /* hackrf_sweep stitch, datasources/hackrf_sweep.py:135-168: rows (float32 [n_rows][bins_per_row])
  * with per-row hz_low and a common row width row_hz are placed at bin centres
  * lo + bw/2 + i*bw, sorted by frequency and linearly interpolated (np.interp semantics,

@@ -231,9 +231,62 @@ def gen_stitch():
     feed()                          # wrap -> stitch of the first pass
     full = src.get_data()
     parsed = np.stack([np.array([float(f"{v:.2f}") for v in r], dtype=np.float32) for r in rows])
+    # the same pass as wire data: CSV text (with a malformed line and a short line the reference skips) and -B records
+    lines = []
+    for r, lo, hi in zip(rows, los, his):
+        lines.append(", ".join(["2026-01-01", "00:00:00", str(lo), str(hi), "100000.00", "20"] + [f"{v:.2f}" for v in r]))
+    csv_text = "\n".join(lines[:3] + ["garbage, line", "2026-01-01, 00:00:00, 1, 2, x, 20, notafloat"] + lines[3:]) + "\n"
+    import struct
+    binary = b"".join(struct.pack("<IQQ", 16 + 4 * len(r), lo, hi) + np.asarray(p, dtype="<f4").tobytes()
+                      for r, p, lo, hi in zip(rows, parsed, los, his))
     np.savez_compressed(os.path.join(OUT, "sweep_stitch.npz"), meta=META, start=start, stop=stop,
                         bin_size=bin_size, rows=parsed, lo=np.array(los), hi=np.array(his),
-                        grid=src.frequency_grid, before_wrap=first, stitched=full)
+                        grid=src.frequency_grid, before_wrap=first, stitched=full,
+                        csv_text=np.frombuffer(csv_text.encode(), dtype=np.uint8),
+                        binary=np.frombuffer(binary, dtype=np.uint8))
+
+
+def gen_analytics():
+    """Colour map (export_manager.py:72-79), density histogram (density_display.py:306-319) and band power
+    (marker_manager.py:308-318): the three formulas are executed here with numpy exactly as written there
+    (those modules import Qt at module level, so their classes cannot be instantiated in this container)."""
+    rng = np.random.default_rng(81)
+    arr = rng.normal(-70.0, 25.0, (6, 64)).astype(np.float32)
+    arr[0, 0] = np.float32(-100.0); arr[0, 1] = np.float32(-20.0)
+    wf_min_db, wf_max_db = -100.0, -20.0
+    lut = rng.integers(0, 256, (256, 4), dtype=np.uint8)
+    norm = np.clip((arr - wf_min_db) / max(wf_max_db - wf_min_db, 1e-9), 0.0, 1.0)
+    rgba = np.ascontiguousarray(lut[(norm * 255).astype(np.uint8)], dtype=np.uint8)
+    # density histogram, three frames, decay "medium"
+    _AMP_BINS, _AMP_MIN, _AMP_RNG, decay = 512, -200.0, 300.0, 0.96
+    frames = rng.normal(-80.0, 30.0, (3, 48)).astype(np.float32)
+    frames[1, 3] = np.nan; frames[2, 5] = np.float32(-200.2); frames[2, 6] = np.float32(120.0)
+    hist = np.zeros((48, _AMP_BINS), dtype=np.float32)
+    hists = []
+    for live in frames:
+        live_db = live.astype(np.float64)
+        n = len(live_db)
+        if decay < 1.0:
+            hist *= decay
+        valid = ~np.isnan(live_db)
+        raw_idx = np.full(n, -1, dtype=np.int32)
+        raw_idx[valid] = ((live_db[valid] - _AMP_MIN) / _AMP_RNG * _AMP_BINS).astype(np.int32)
+        in_range = (raw_idx >= 0) & (raw_idx < _AMP_BINS)
+        fi = np.where(in_range)[0]
+        if len(fi):
+            hist[fi, raw_idx[fi]] += 1.0
+        hists.append(hist.copy())
+    # band power
+    bins = np.linspace(88e6, 108e6, 2048)
+    levels = rng.normal(-90.0, 6.0, 2048).astype(np.float32)
+    lo, hi = 95e6, 99.5e6
+    mask = (bins >= lo) & (bins <= hi)
+    bin_width = (bins[-1] - bins[0]) / max(len(bins) - 1, 1)
+    total = np.sum(10.0 ** (levels[mask].astype(np.float64) / 10.0)) * bin_width
+    bp = 10.0 * np.log10(max(total, 1e-30))
+    np.savez_compressed(os.path.join(OUT, "analytics.npz"), meta=META, cm_rows=arr, cm_lo=wf_min_db, cm_hi=wf_max_db,
+                        cm_lut=lut, cm_rgba=rgba, dens_frames=frames, dens_hists=np.stack(hists),
+                        bp_bins=bins, bp_levels=levels, bp_lo=lo, bp_hi=hi, bp_value=bp)
 
 
 def gen_waterfall():
@@ -272,6 +325,7 @@ if __name__ == "__main__":
     gen_averager()
     gen_holds_tare_sweepavg()
     gen_stitch()
+    gen_analytics()
     gen_waterfall()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -89,3 +89,33 @@ def test_datasource_interface_without_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             src.start()
+
+
+def test_sweep_csv_and_binary_parsers(golden):
+    """Wire formats -> rows: same values the reference's _parse extracts (hackrf_sweep.py:138-146)."""
+    from topdogspectrumanalyser_b200 import sweep_io
+    g = golden("sweep_stitch.npz")
+    text = g["csv_text"].tobytes()
+    lo, hi, vals, nb, used = sweep_io.parse_csv(text, max_rows=64, max_bins=64)
+    assert used == len(text)
+    assert len(lo) == len(g["lo"])                      # the two malformed lines are skipped
+    np.testing.assert_array_equal(lo, g["lo"].astype(np.float64))
+    np.testing.assert_array_equal(hi, g["hi"].astype(np.float64))
+    assert set(nb.tolist()) == {50}
+    np.testing.assert_array_equal(vals[:, :50], g["rows"])
+    # an incomplete last line is left for the next call
+    cut = text[:len(text) - 7]
+    lo2, _, _, _, used2 = sweep_io.parse_csv(cut, max_rows=64, max_bins=64)
+    assert len(lo2) == len(lo) - 1 and cut[used2 - 1:used2] == b"\n"
+    # binary -B records
+    blob = g["binary"].tobytes()
+    lo3, hi3, vals3, nb3, used3 = sweep_io.parse_binary(blob, max_rows=64, max_bins=64)
+    assert used3 == len(blob)
+    np.testing.assert_array_equal(lo3, lo)
+    np.testing.assert_array_equal(hi3, hi)
+    np.testing.assert_array_equal(vals3[:, :50], g["rows"])
+    lo4, _, _, _, used4 = sweep_io.parse_binary(blob[:-3], max_rows=64, max_bins=64)
+    assert len(lo4) == len(lo) - 1 and used4 < len(blob) - 3
+    # rows wider than max_bins are dropped, never truncated silently
+    lo5, _, _, _, _ = sweep_io.parse_csv(text, max_rows=64, max_bins=10)
+    assert len(lo5) == 0

@@ -49,6 +49,16 @@ SIGNATURES = {
     "tdsa_group_avg_db": (_i32, [_vp, _vp, _i64, _i64, _vp]),
     "tdsa_welch": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "tdsa_trace_update": (_i32, [_vp, _i64, _i64, _f64, _i32, _i32, _vp, _pi32, _vp, _vp, _pi32, _vp, _vp, _vp]),
+    "tdsa_trace_update_tare": (_i32, [_vp, _i64, _i64, _f64, _i32, _i32, _vp, _pi32, _vp, _vp, _pi32, _vp, _vp, _vp,
+                                      _pi32, _pi32, _i32, _vp, _vp]),
+    "tdsa_colormap_rgba": (_i32, [_vp, _i64, C.c_float, C.c_float, _vp, _vp, _vp]),
+    "tdsa_density_update": (_i32, [_vp, _i64, _f64, _vp, _vp]),
+    "tdsa_band_power": (_i32, [_vp, _vp, _i64, _f64, _f64, _vp, _vp]),
+    "tdsa_top_peaks": (_i32, [_vp, _i64, _i32, _i32, C.c_float, _vp, _vp, _vp, _vp]),
+    "tdsa_parse_sweep_csv_host": (_i32, [C.c_char_p, _i64, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64),
+                                         C.POINTER(C.c_int64)]),
+    "tdsa_parse_sweep_binary_host": (_i32, [C.c_char_p, _i64, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64),
+                                            C.POINTER(C.c_int64)]),
     "tdsa_stitch": (_i32, [_vp, _vp, _f64, _i64, _i64, _f64, _f64, _i64, _vp, _vp, _vp]),
     "tdsa_ring_push": (_i32, [_vp, _i64, _vp, _i64, _i64, C.POINTER(C.c_int64), _vp]),
     "tdsa_h2d_async": (_i32, [_vp, _vp, C.c_size_t, _vp, _vp]),

@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -548,14 +549,19 @@ int tdsa_welch(tdsa_handle_t p, const void* iq_stream, int64_t n_samples, int64_
   return TDSA_OK;
 }
 
-int tdsa_trace_update(const float* rows, int64_t n_rows, int64_t width, double cal_offset_db, int avg_mode, int avg_n,
-                      double* avg_state, int32_t* count_state_host, float* max_hold, float* min_hold,
-                      int32_t* hold_valid_host, float* rows_out, void* cuda_stream, int32_t* row_flags_scratch) {
+static int trace_update_impl(const float* rows, int64_t n_rows, int64_t width, double cal_offset_db, int avg_mode, int avg_n,
+                             double* avg_state, int32_t* count_state_host, float* max_hold, float* min_hold,
+                             int32_t* hold_valid_host, float* rows_out, void* cuda_stream, int32_t* row_flags_scratch,
+                             int32_t* tare_flags_host, int32_t* tare_count_host, int tare_target, double* tare_buf,
+                             double* tare_baseline) {
   if (!rows || n_rows < 0 || width < 1) return fail(TDSA_ERR_INVALID, "bad rows");
   if (!row_flags_scratch) return fail(TDSA_ERR_INVALID, "row_flags_scratch (int32[n_rows], device) is required");
   const bool averaging = avg_mode != TDSA_AVG_OFF && avg_n > 1;
   if (averaging && (!avg_state || !count_state_host)) return fail(TDSA_ERR_INVALID, "averaging needs avg_state and count_state");
   if ((max_hold || min_hold) && !hold_valid_host) return fail(TDSA_ERR_INVALID, "holds need hold_valid");
+  const bool tare = tare_flags_host && (tare_flags_host[0] || tare_flags_host[1]);
+  if (tare && (!tare_count_host || !tare_buf || !tare_baseline || tare_target < 1))
+    return fail(TDSA_ERR_INVALID, "tare needs count, buffer, baseline and a target >= 1");
   if (n_rows == 0) return TDSA_OK;
   cudaStream_t s = (cudaStream_t)cuda_stream;
   CK(cudaMemsetAsync(row_flags_scratch, 0, sizeof(int32_t) * n_rows, s));
@@ -569,6 +575,8 @@ int tdsa_trace_update(const float* rows, int64_t n_rows, int64_t width, double c
   a.max_valid0 = hold_valid_host ? hold_valid_host[0] : 0;
   a.min_valid0 = hold_valid_host ? hold_valid_host[1] : 0;
   a.has_value = row_flags_scratch; a.rows_out = rows_out;
+  a.tare_mode = tare ? ((tare_flags_host[0] ? 1 : 0) | (tare_flags_host[1] ? 2 : 0)) : 0;
+  a.tare_count0 = tare ? *tare_count_host : 0; a.tare_target = tare_target; a.tare_buf = tare_buf; a.tare_baseline = tare_baseline;
   trace_update_kernel<<<(unsigned)((width + 255) / 256), 256, 0, s>>>(a);
   count_launch();
   CK(cudaGetLastError());
@@ -579,6 +587,11 @@ int tdsa_trace_update(const float* rows, int64_t n_rows, int64_t width, double c
   int64_t live = 0;
   for (int32_t v : flags) live += v != 0;
   if (live > 0) {
+    if (tare && tare_flags_host[0]) {            // TareState bookkeeping, display_data_processor.py:335-358
+      const int64_t c = (int64_t)*tare_count_host + live;
+      if (c >= tare_target) { tare_flags_host[0] = 0; tare_flags_host[1] = 1; *tare_count_host = 0; }
+      else *tare_count_host = (int32_t)c;
+    }
     if (averaging) {
       int c = *count_state_host;
       if (avg_mode == TDSA_AVG_LIN) c = (int)std::min<int64_t>(avg_n, (int64_t)c + live);
@@ -590,6 +603,145 @@ int tdsa_trace_update(const float* rows, int64_t n_rows, int64_t width, double c
       if (min_hold) hold_valid_host[1] = 1;
     }
   }
+  return TDSA_OK;
+}
+
+int tdsa_trace_update(const float* rows, int64_t n_rows, int64_t width, double cal_offset_db, int avg_mode, int avg_n,
+                      double* avg_state, int32_t* count_state_host, float* max_hold, float* min_hold,
+                      int32_t* hold_valid_host, float* rows_out, void* cuda_stream, int32_t* row_flags_scratch) {
+  return trace_update_impl(rows, n_rows, width, cal_offset_db, avg_mode, avg_n, avg_state, count_state_host, max_hold,
+                           min_hold, hold_valid_host, rows_out, cuda_stream, row_flags_scratch, nullptr, nullptr, 0, nullptr,
+                           nullptr);
+}
+
+int tdsa_trace_update_tare(const float* rows, int64_t n_rows, int64_t width, double cal_offset_db, int avg_mode, int avg_n,
+                           double* avg_state, int32_t* count_state_host, float* max_hold, float* min_hold,
+                           int32_t* hold_valid_host, float* rows_out, void* cuda_stream, int32_t* row_flags_scratch,
+                           int32_t* tare_flags_host, int32_t* tare_count_host, int tare_target, double* tare_buf,
+                           double* tare_baseline) {
+  return trace_update_impl(rows, n_rows, width, cal_offset_db, avg_mode, avg_n, avg_state, count_state_host, max_hold,
+                           min_hold, hold_valid_host, rows_out, cuda_stream, row_flags_scratch, tare_flags_host,
+                           tare_count_host, tare_target, tare_buf, tare_baseline);
+}
+
+int tdsa_colormap_rgba(const float* rows, int64_t n, float lo_db, float hi_db, const uint8_t* lut_rgba, uint8_t* rgba_out,
+                       void* cuda_stream) {
+  if (!rows || !lut_rgba || !rgba_out || n < 0) return fail(TDSA_ERR_INVALID, "bad argument");
+  if (n == 0) return TDSA_OK;
+  const float den = fmaxf(hi_db - lo_db, 1e-9f);
+  colormap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(rows, n, lo_db, den, (const uchar4*)lut_rgba,
+                                                                                   (uchar4*)rgba_out);
+  count_launch();
+  CK(cudaGetLastError());
+  return TDSA_OK;
+}
+
+int tdsa_density_update(const float* live_db, int64_t width, double decay, float* hist, void* cuda_stream) {
+  if (!live_db || !hist || width < 1) return fail(TDSA_ERR_INVALID, "bad argument");
+  density_update_kernel<<<(unsigned)width, 256, 0, (cudaStream_t)cuda_stream>>>(live_db, width, (float)decay, decay < 1.0 ? 1 : 0, hist);
+  count_launch();
+  CK(cudaGetLastError());
+  return TDSA_OK;
+}
+
+int tdsa_band_power(const double* bins, const float* levels, int64_t width, double f_lo, double f_hi, double* out,
+                    void* cuda_stream) {
+  if (!bins || !levels || !out || width < 1) return fail(TDSA_ERR_INVALID, "bad argument");
+  band_power_kernel<<<1, 256, 0, (cudaStream_t)cuda_stream>>>(bins, levels, width, std::min(f_lo, f_hi), std::max(f_lo, f_hi), out);
+  count_launch();
+  CK(cudaGetLastError());
+  return TDSA_OK;
+}
+
+int tdsa_top_peaks(const float* power, int64_t width, int n, int min_sep_bins, float min_excursion_db, int32_t* idx_out,
+                   float* pwr_out, int32_t* count_out, void* cuda_stream) {
+  if (!power || !idx_out || !pwr_out || !count_out) return fail(TDSA_ERR_INVALID, "null argument");
+  if (n < 1 || n > 16) return fail(TDSA_ERR_INVALID, "n must be in [1, 16]");
+  if (width > 16384) return fail(TDSA_ERR_UNSUPPORTED, "top_peaks supports rows of up to 16384 bins");
+  constexpr int kSmem = 8192 * 8;
+  static bool once = false;
+  if (!once) { CK(cudaFuncSetAttribute(top_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); once = true; }
+  if (width < 3) { CK(cudaMemsetAsync(count_out, 0, sizeof(int32_t), (cudaStream_t)cuda_stream)); return TDSA_OK; }
+  top_peaks_kernel<<<1, 1024, kSmem, (cudaStream_t)cuda_stream>>>(power, (int)width, n, min_sep_bins, min_excursion_db, idx_out,
+                                                               pwr_out, count_out);
+  count_launch();
+  CK(cudaGetLastError());
+  return TDSA_OK;
+}
+
+// ---- hackrf_sweep wire formats (host side; replaces the per-field Python float() loop of hackrf_sweep.py:138-146) ----
+// CSV line: date, time, hz_low, hz_high, bin_width, num_samples, dB, dB, ...  Lines with fewer than 7 fields or a
+// field that does not parse are skipped, like the reference's ValueError handler (:167-168).
+int tdsa_parse_sweep_csv_host(const char* text, int64_t len, int64_t max_rows, int64_t max_bins, double* lo_hz, double* hi_hz,
+                              float* values, int32_t* n_bins, int64_t* n_rows_out, int64_t* consumed_out) {
+  if (!text || !lo_hz || !hi_hz || !values || !n_bins || !n_rows_out) return fail(TDSA_ERR_INVALID, "null argument");
+  int64_t rows = 0, pos = 0, consumed = 0;
+  std::string field;
+  while (pos < len && rows < max_rows) {
+    int64_t eol = pos;
+    while (eol < len && text[eol] != '\n') ++eol;
+    if (eol == len) break;                          // incomplete last line: leave it for the next call
+    // split [pos, eol) on commas
+    int nf = 0;
+    bool ok = true;
+    int64_t nb = 0;
+    long long lo = 0, hi = 0;
+    int64_t fs = pos;
+    for (int64_t i = pos; i <= eol && ok; ++i) {
+      if (i == eol || text[i] == ',') {
+        int64_t a = fs, b = i;
+        while (a < b && (text[a] == ' ' || text[a] == '\t' || text[a] == '\r')) ++a;
+        while (b > a && (text[b - 1] == ' ' || text[b - 1] == '\t' || text[b - 1] == '\r')) --b;
+        field.assign(text + a, (size_t)(b - a));
+        char* end = nullptr;
+        if (nf == 2 || nf == 3) {                   // int(fields[2]), int(fields[3])
+          const long long v = strtoll(field.c_str(), &end, 10);
+          if (field.empty() || *end != '\0') ok = false;
+          (nf == 2 ? lo : hi) = v;
+        } else if (nf >= 6) {                       // float(v) for v in fields[6:]
+          const double v = strtod(field.c_str(), &end);
+          if (field.empty() || *end != '\0') ok = false;
+          else if (nb < max_bins) values[rows * max_bins + nb] = (float)v;
+          ++nb;
+        }
+        ++nf;
+        fs = i + 1;
+      }
+    }
+    consumed = eol + 1;
+    pos = eol + 1;
+    if (!ok || nf < 7 || nb == 0 || nb > max_bins) continue;
+    lo_hz[rows] = (double)lo; hi_hz[rows] = (double)hi; n_bins[rows] = (int32_t)nb;
+    ++rows;
+  }
+  *n_rows_out = rows;
+  if (consumed_out) *consumed_out = consumed;
+  return TDSA_OK;
+}
+
+// Binary (-B) records, hackrf_sweep_binary_reference.py:29-43: uint32 record_length, then uint64 hz_low,
+// uint64 hz_high, float32[] dB (little-endian). Incomplete trailing records are left for the next call.
+int tdsa_parse_sweep_binary_host(const uint8_t* buf, int64_t len, int64_t max_rows, int64_t max_bins, double* lo_hz,
+                                 double* hi_hz, float* values, int32_t* n_bins, int64_t* n_rows_out, int64_t* consumed_out) {
+  if (!buf || !lo_hz || !hi_hz || !values || !n_bins || !n_rows_out) return fail(TDSA_ERR_INVALID, "null argument");
+  int64_t rows = 0, pos = 0;
+  while (rows < max_rows && pos + 4 <= len) {
+    uint32_t rec;
+    memcpy(&rec, buf + pos, 4);
+    if (pos + 4 + (int64_t)rec > len) break;
+    const uint8_t* r = buf + pos + 4;
+    pos += 4 + (int64_t)rec;
+    if (rec < 16) continue;
+    const int64_t nb = ((int64_t)rec - 16) / 4;
+    if (nb == 0 || nb > max_bins) continue;       // step_data.size == 0 -> return (:40-41)
+    uint64_t lo, hi;
+    memcpy(&lo, r, 8); memcpy(&hi, r + 8, 8);
+    lo_hz[rows] = (double)lo; hi_hz[rows] = (double)hi; n_bins[rows] = (int32_t)nb;
+    memcpy(values + rows * max_bins, r + 16, (size_t)nb * 4);
+    ++rows;
+  }
+  *n_rows_out = rows;
+  if (consumed_out) *consumed_out = pos;
   return TDSA_OK;
 }
 

@@ -161,6 +161,10 @@ struct TraceUpdateArgs {
   int max_valid0, min_valid0;
   const int32_t* has_value;   // per row
   float* rows_out;            // [n_rows][width] or null
+  // tare (display_data_processor.py:329-369): bit 0 of tare_mode = collecting, bit 1 = baseline active
+  int tare_mode, tare_count0, tare_target;
+  double* tare_buf;           // [width] running sum of 10^(dB/10) while collecting
+  double* tare_baseline;      // [width] dB baseline once captured
 };
 
 __global__ void __launch_bounds__(256) trace_update_kernel(const TraceUpdateArgs a) {
@@ -174,6 +178,10 @@ __global__ void __launch_bounds__(256) trace_update_kernel(const TraceUpdateArgs
   float mx = (a.max_hold && mxv) ? a.max_hold[k] : 0.f;
   float mn = (a.min_hold && mnv) ? a.min_hold[k] : 0.f;
   bool touched = false;
+  bool collecting = (a.tare_mode & 1) != 0, tare_active = (a.tare_mode & 2) != 0, captured = false;
+  int tcount = a.tare_count0;
+  double tbuf = (collecting && tcount > 0) ? a.tare_buf[k] : 0.0;
+  double base = tare_active ? a.tare_baseline[k] : 0.0;
   for (int64_t r = 0; r < a.n_rows; ++r) {
     double x = (double)a.rows[r * a.width + k];
     if (a.cal != 0.0) x += a.cal;
@@ -181,6 +189,15 @@ __global__ void __launch_bounds__(256) trace_update_kernel(const TraceUpdateArgs
       if (a.rows_out) a.rows_out[r * a.width + k] = (float)x;
       continue;
     }
+    if (collecting) {                    // accumulate the linear baseline, capture it after tare_target frames
+      const double lin = pow(10.0, x / 10.0);
+      if (tcount == 0) { tbuf = lin; tcount = 1; } else { tbuf += lin; ++tcount; }
+      if (tcount >= a.tare_target) {
+        base = 10.0 * log10(fmax(tbuf / (double)tcount, 1e-30));
+        tare_active = true; collecting = false; captured = true;
+      }
+    }
+    if (tare_active) x -= base;
     if (averaging) {
       const double lin = pow(10.0, x / 10.0);
       if (count == 0) {
@@ -210,6 +227,149 @@ __global__ void __launch_bounds__(256) trace_update_kernel(const TraceUpdateArgs
   if (averaging && touched) a.avg_state[k] = buf;
   if (a.max_hold && mxv) a.max_hold[k] = mx;
   if (a.min_hold && mnv) a.min_hold[k] = mn;
+  if (collecting) a.tare_buf[k] = tbuf;
+  if (captured) a.tare_baseline[k] = base;
+}
+
+// ---------------------------------------------------------------------------------------
+// Waterfall colour map, core/export_manager.py:72-79: norm = clip((x - lo)/max(hi - lo, 1e-9), 0, 1) in
+// float32, index = uint8(norm*255) (truncation), RGBA = lut[index].  NaN rows map to index 0.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colormap_kernel(const float* __restrict__ rows, int64_t n, float lo, float inv_den_num,
+                                                      const uchar4* __restrict__ lut, uchar4* __restrict__ rgba) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = __fdiv_rn(__fsub_rn(rows[i], lo), inv_den_num);   // inv_den_num holds max(hi - lo, 1e-9)
+  v = fminf(fmaxf(v, 0.0f), 1.0f);                            // NaN -> 0 (np.clip keeps NaN; uint8(NaN) is 0 on x86)
+  const int idx = (int)__fmul_rn(v, 255.0f);
+  rgba[i] = lut[idx & 255];
+}
+
+// ---------------------------------------------------------------------------------------
+// Density histogram with decay, displays/density_display.py:306-319: hist[W][512] float32;
+// hist *= float32(decay) when decay < 1; bin = int32((db + 200)/300*512) in float64, +1 if in range.
+// One thread per (frequency bin, 4 amplitude bins) for the decay, then the increment.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) density_update_kernel(const float* __restrict__ live_db, int64_t width, float decay,
+                                                            int apply_decay, float* __restrict__ hist) {
+  constexpr int kBins = 512;
+  const int64_t f = blockIdx.x;                      // one CTA per frequency bin row: 512 floats
+  if (f >= width) return;
+  float* row = hist + f * kBins;
+  if (apply_decay) {
+    for (int b = threadIdx.x; b < kBins; b += blockDim.x) row[b] = __fmul_rn(row[b], decay);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float db = live_db[f];
+    if (!isnan(db)) {
+      const double v = __dmul_rn(__ddiv_rn(__dsub_rn((double)db, -200.0), 300.0), 512.0);
+      // astype(int32) truncates toward zero, so (-1, 0) lands in bin 0; everything else outside [0, 512) is dropped
+      if (v > -1.0 && v < 512.0) { const int idx = (int)v; row[idx] = __fadd_rn(row[idx], 1.0f); }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Band power, core/marker_manager.py:308-318: 10*log10(max(sum(10^(levels[mask]/10)) * bin_width, 1e-30))
+// over bins with lo <= f <= hi. Single CTA; returns NaN when the mask is empty (reference returns None).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) band_power_kernel(const double* __restrict__ bins, const float* __restrict__ levels,
+                                                        int64_t width, double lo, double hi, double* __restrict__ out) {
+  __shared__ double s_sum[8];
+  __shared__ int s_any[8];
+  double acc = 0.0;
+  int any = 0;
+  for (int64_t i = threadIdx.x; i < width; i += blockDim.x) {
+    const double f = bins[i];
+    if (f >= lo && f <= hi) { acc += pow(10.0, (double)levels[i] / 10.0); any = 1; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); any |= __shfl_xor_sync(0xffffffffu, any, o); }
+  if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = acc; s_any[threadIdx.x >> 5] = any; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0; int a = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t += s_sum[w]; a |= s_any[w]; }
+    const double bw = (bins[width - 1] - bins[0]) / (double)(width > 1 ? width - 1 : 1);
+    out[0] = a ? 10.0 * log10(fmax(t * bw, 1e-30)) : nan("");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Top-n peak search, core/display_data_processor.py:432-471: strict local maxima, visited in order of
+// decreasing power; a candidate is rejected if it is closer than min_sep bins to a selected peak or if the
+// valley between them is not at least min_exc dB below BOTH peaks. One CTA; width <= 16384.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) top_peaks_kernel(const float* __restrict__ power, int width, int n_want, int min_sep,
+                                                        float min_exc, int32_t* __restrict__ out_idx, float* __restrict__ out_pwr,
+                                                        int32_t* __restrict__ out_count) {
+  extern __shared__ unsigned char raw[];
+  float* key = reinterpret_cast<float*>(raw);                 // candidate powers, padded to cap with -inf
+  int32_t* val = reinterpret_cast<int32_t*>(key + 8192);      // candidate bin indices
+  __shared__ int s_n;
+  __shared__ float s_red[32];
+  __shared__ int s_sel_idx[16];
+  __shared__ float s_sel_pwr[16];
+  const int t = threadIdx.x, nt = blockDim.x;
+  if (t == 0) s_n = 0;
+  for (int i = t; i < 8192; i += nt) { key[i] = -INFINITY; val[i] = -1; }
+  __syncthreads();
+  for (int i = 1 + t; i < width - 1; i += nt) {
+    const float p = power[i];
+    if (p > power[i - 1] && p > power[i + 1]) {
+      const int slot = atomicAdd(&s_n, 1);
+      if (slot < 8192) { key[slot] = p; val[slot] = i; }
+    }
+  }
+  __syncthreads();
+  const int ncand = min(s_n, 8192);
+  int cap = 1;
+  while (cap < ncand) cap <<= 1;
+  // bitonic sort, descending by (power, then lower index first for determinism)
+  for (int k = 2; k <= cap; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = t; i < cap; i += nt) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool desc = (i & k) == 0;
+          const float a = key[i], b = key[l];
+          const int ia = val[i], ib = val[l];
+          const bool a_first = (a > b) || (a == b && ia < ib);     // should a precede b in descending order
+          if (desc ? !a_first : a_first) { key[i] = b; key[l] = a; val[i] = ib; val[l] = ia; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  int nsel = 0;
+  for (int ci = 0; ci < ncand && nsel < n_want; ++ci) {
+    const int idx = val[ci];
+    const float pw = key[ci];
+    bool reject = false;
+    for (int sidx = 0; sidx < nsel && !reject; ++sidx) {
+      const int sel = s_sel_idx[sidx];
+      const float spw = s_sel_pwr[sidx];
+      if (abs(idx - sel) < min_sep) { reject = true; break; }
+      const int lo = min(idx, sel), hi = max(idx, sel);
+      float m = INFINITY;
+      for (int i = lo + t; i <= hi; i += nt) m = fminf(m, power[i]);   // np.min propagates NaN; fminf ignores it
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if ((t & 31) == 0) s_red[t >> 5] = m;
+      __syncthreads();
+      float valley = INFINITY;
+      for (int w = 0; w < (nt >> 5); ++w) valley = fminf(valley, s_red[w]);
+      __syncthreads();
+      if (pw - valley < min_exc || spw - valley < min_exc) reject = true;
+    }
+    if (!reject) {
+      if (t == 0) { s_sel_idx[nsel] = idx; s_sel_pwr[nsel] = pw; out_idx[nsel] = idx; out_pwr[nsel] = pw; }
+      ++nsel;
+      __syncthreads();
+    }
+  }
+  if (t == 0) out_count[0] = nsel;
 }
 
 // ---------------------------------------------------------------------------------------

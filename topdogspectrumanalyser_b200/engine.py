@@ -71,6 +71,26 @@ class TraceState:
         self.min_hold = torch.zeros(self.width, dtype=torch.float32, device=self.device)
         self.count = C.c_int32(0)
         self.valid = (C.c_int32 * 2)(0, 0)
+        # tare / normalisation (core/tare_state.py; display_data_processor.py:329-369)
+        self.tare_buf = torch.zeros(self.width, dtype=torch.float64, device=self.device)
+        self.tare_baseline = torch.zeros(self.width, dtype=torch.float64, device=self.device)
+        self.tare_flags = (C.c_int32 * 2)(0, 0)          # {collecting, active}
+        self.tare_count = C.c_int32(0)
+
+    TARE_NUM_SAMPLES = 32                                 # utils/constants.py:141
+
+    def start_tare(self) -> None:
+        """Begin collecting a baseline (TareState(collecting=True))."""
+        self.tare_flags[0], self.tare_flags[1] = 1, 0
+        self.tare_count.value = 0
+
+    def clear_tare(self) -> None:
+        self.tare_flags[0], self.tare_flags[1] = 0, 0
+        self.tare_count.value = 0
+
+    @property
+    def tare_active(self) -> bool:
+        return bool(self.tare_flags[1])
 
     def set_averaging(self, mode: str, n: int) -> None:       # TraceAverager.set_mode, :19-28
         self.avg_mode, self.avg_n = mode, max(1, int(n))
@@ -282,11 +302,13 @@ def trace_update(rows: torch.Tensor, state: TraceState, cal_offset_db: float = 0
     if out is None:
         out = torch.empty_like(rows)
     flags = torch.empty(max(r, 1), dtype=torch.int32, device=rows.device)
-    L.check(lib.tdsa_trace_update(rows.data_ptr(), r, w, float(cal_offset_db), L.AVG_IDS[state.avg_mode], state.avg_n,
-                                  state.avg.data_ptr(), C.byref(state.count),
-                                  state.max_hold.data_ptr() if state.max_hold_enabled else None,
-                                  state.min_hold.data_ptr() if state.min_hold_enabled else None, state.valid,
-                                  out.data_ptr(), _stream_ptr(), flags.data_ptr()))
+    L.check(lib.tdsa_trace_update_tare(rows.data_ptr(), r, w, float(cal_offset_db), L.AVG_IDS[state.avg_mode], state.avg_n,
+                                       state.avg.data_ptr(), C.byref(state.count),
+                                       state.max_hold.data_ptr() if state.max_hold_enabled else None,
+                                       state.min_hold.data_ptr() if state.min_hold_enabled else None, state.valid,
+                                       out.data_ptr(), _stream_ptr(), flags.data_ptr(), state.tare_flags,
+                                       C.byref(state.tare_count), state.TARE_NUM_SAMPLES, state.tare_buf.data_ptr(),
+                                       state.tare_baseline.data_ptr()))
     return out
 
 

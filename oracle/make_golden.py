@@ -148,6 +148,25 @@ def gen_hackrf():
     out.update(mag20=db, bins=bins, window=win)
     out["psd"], _, _ = run_hackrf(iq, 1024, fs, fc, psd=True)
     out["avg_exp4"], _, _ = run_hackrf(iq, 1024, fs, fc, avg=("exp", 4))
+    # consume policy (_consume_samples, hackrf_samples.py:254-305): chunks are index ramps so positions are visible
+    src = HackrfSamplesDataSource(int(fs), int(fc))
+    src.CONSUME_TIMEOUT = 0.05
+    def chunk(k):
+        return (np.arange(65536, dtype=np.float32) + 100000.0 * k).astype(np.complex64)
+    script, heads = [], []
+    def read(n):
+        r = src._consume_samples(n)
+        script.append(("read", n))
+        heads.append([-1.0, -1.0, 0] if r is None else [float(r[0].real), float(r[-1].real), len(r)])
+    src._sample_queue.put(chunk(0)); script.append(("put", 0))
+    read(1024); read(1024); read(4096)
+    for k in (1, 2, 3):
+        src._sample_queue.put(chunk(k)); script.append(("put", k))
+    read(2048); read(65536 - 2048 - 10); read(1024)          # newest chunk only; then reservoir too short -> timeout
+    src._sample_queue.put(chunk(4)); script.append(("put", 4))
+    read(512)
+    out["consume_script"] = np.array([[0 if a == "put" else 1, b] for a, b in script])
+    out["consume_heads"] = np.array(heads)
     np.savez_compressed(os.path.join(OUT, "hackrf_chain.npz"), **out)
 
 

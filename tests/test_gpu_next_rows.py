@@ -109,3 +109,38 @@ def test_top_peaks_matches_reference(dev, golden):
             sel.append(int(i))
     assert [int(f) for f, _ in got] == sel
     plan.close()
+
+
+def test_frame_pipeline_matches_reference_sequence(dev, golden):
+    """source -> cal -> tare -> holds -> peaks on the device vs the same chain of reference primitives."""
+    from topdogspectrumanalyser_b200 import synth
+    from topdogspectrumanalyser_b200.datasources import B200SampleDataSource, ReplayFeed
+    from topdogspectrumanalyser_b200.frame_pipeline import B200FramePipeline
+    n, frames, fs, fc, cal = 1024, 40, 2.048e6, 98e6, -3.5
+    iq = synth.cfg2_frames(b=frames, n=n, seed=91)
+    src = B200SampleDataSource(int(fs), int(fc), feed=ReplayFeed(iq, fs, fc))
+    src.set_fft_size(n)
+    src.start()
+    pipe = B200FramePipeline(src, cal_offset_db=cal, peak_list=True)
+    pipe.max_peak_search_enabled = pipe.min_hold_enabled = True
+    w = O.make_window("hanning", n)
+    tare, mx, mn = O.Tare(), None, None
+    for i, f in enumerate(iq):
+        if i == 3:
+            pipe.start_tare()
+            tare.start()
+        assert pipe.update_data()
+        db = O.power_db_frame(f, w, O.MODE_POWER).astype(np.float32).astype(np.float64) + cal   # float32 row from the kernel
+        db = tare.apply(db)
+        mx = O.max_hold_update(mx, db.copy())
+        mn = O.min_hold_update(mn, db.copy())
+        assert np.abs(pipe.live_power_levels - db).max() <= 2e-4
+        assert np.abs(pipe.max_power_levels - mx).max() <= 2e-4
+        assert np.abs(pipe.min_power_levels - mn).max() <= 2e-4
+        assert pipe.tare_active == tare.active
+    assert tare.active and np.abs(pipe.baseline_power_levels - tare.baseline).max() <= 2e-4
+    assert 1 <= len(pipe.peaks) <= 5 and all(pipe.frequency_bins[0] <= f <= pipe.frequency_bins[-1] for f, _ in pipe.peaks)
+    # size change drops the holds like the reference's shape-mismatch rule (display_data_processor.py:375-377)
+    src.sdr = ReplayFeed(synth.cfg2_frames(b=2, n=2048, seed=92), fs, fc)
+    src.sample_count = 2048
+    assert pipe.update_data() and pipe.live_power_levels.shape == (2048,) and not pipe.tare_active

@@ -16,24 +16,7 @@ def dev():
     return torch.device("cuda:0")
 
 
-class ReplayFeed:
-    """pyrtlsdr-shaped feed that hands out pre-computed frames (complex128, like RtlSdr.read_samples)."""
-
-    def __init__(self, frames, fs, fc, dtype=np.complex128):
-        self.frames, self.i, self.fs, self.fc, self.dtype = frames, 0, fs, fc, dtype
-        self.sample_rate, self.center_freq, self.gain = fs, fc, "auto"
-
-    def get_sample_rate(self):
-        return self.fs
-
-    def get_center_freq(self):
-        return self.fc
-
-    def read_samples(self, n):
-        f = self.frames[self.i]
-        self.i += 1
-        assert len(f) == n
-        return f.astype(self.dtype)
+from topdogspectrumanalyser_b200.datasources import ReplayFeed  # noqa: E402
 
 
 def make_source(frames, n, fs, fc, **kw):

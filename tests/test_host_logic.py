@@ -119,3 +119,27 @@ def test_sweep_csv_and_binary_parsers(golden):
     # rows wider than max_bins are dropped, never truncated silently
     lo5, _, _, _, _ = sweep_io.parse_csv(text, max_rows=64, max_bins=10)
     assert len(lo5) == 0
+
+
+def test_hackrf_chunk_feed_consume_policy(golden):
+    """Freshest-tail consume policy vs the executed HackrfSamplesDataSource._consume_samples (hackrf_samples.py:254-305)."""
+    from topdogspectrumanalyser_b200.datasources import HackrfChunkFeed
+    g = golden("hackrf_chain.npz")
+    feed = HackrfChunkFeed(20e6, 2450e6, timeout=0.05)
+    heads = iter(g["consume_heads"])
+    for kind, arg in g["consume_script"]:
+        if kind == 0:
+            feed.put((np.arange(65536, dtype=np.float32) + 100000.0 * arg).astype(np.complex64))
+        else:
+            r = feed.read_samples(int(arg))
+            first, last, n = next(heads)
+            if n == 0:
+                assert r is None
+            else:
+                assert len(r) == n and r[0].real == first and r[-1].real == last
+    # drop-oldest on overflow (hackrf_samples.py:221-237)
+    feed = HackrfChunkFeed(20e6, 2450e6)
+    for k in range(6):
+        feed.put(np.full(8, k, dtype=np.complex64))
+    assert feed.stats["queue_overflows"] == 2 and feed.stats["samples_dropped"] == 16
+    assert feed.read_samples(4)[0].real == 5.0

@@ -53,6 +53,109 @@ class SyntheticIQFeed:
         pass
 
 
+class ReplayFeed:
+    """Feed that hands out pre-recorded frames one per ``read_samples`` call (file replay, tests).
+
+    ``dtype`` is what the device library would return: complex128 for pyrtlsdr, complex64 for pyhackrf."""
+
+    def __init__(self, frames, sample_rate: float, centre_freq: float, dtype=np.complex128):
+        self.frames, self.i, self.dtype = frames, 0, dtype
+        self.fs, self.fc = float(sample_rate), float(centre_freq)
+        self.sample_rate, self.center_freq, self.gain = self.fs, self.fc, "auto"
+
+    def get_sample_rate(self):
+        return self.fs
+
+    def get_center_freq(self):
+        return self.fc
+
+    def read_samples(self, n: int):
+        f = self.frames[self.i]
+        self.i += 1
+        if len(f) != n:
+            raise ValueError(f"replay frame has {len(f)} samples, {n} requested")
+        return np.asarray(f).astype(self.dtype)
+
+    def close(self):
+        pass
+
+
+class HackrfChunkFeed:
+    """Feed with the reference HackRF source's consume policy (datasources/hackrf_samples.py:28-29,254-305).
+
+    A reader thread ``put``s 65 536-sample chunks into a depth-4 queue (oldest dropped when full, :221-237);
+    ``read_samples(n)`` drains the queue keeping only the newest chunk as reservoir and hands out the LAST n
+    samples of it, shrinking the reservoir from the end; returns ``None`` after ``timeout`` seconds without data.
+    """
+    READ_CHUNK, MAX_QUEUE_SIZE, CONSUME_TIMEOUT = 65536, 4, 0.5
+
+    def __init__(self, sample_rate: float, centre_freq: float, timeout: Optional[float] = None):
+        import queue
+        self._queue_mod = queue
+        self.sample_rate, self.center_freq = float(sample_rate), float(centre_freq)
+        self._q = queue.Queue(maxsize=self.MAX_QUEUE_SIZE)
+        self._reservoir = np.array([], dtype=np.complex64)
+        self.timeout = self.CONSUME_TIMEOUT if timeout is None else timeout
+        self.stats = {"samples_dropped": 0, "queue_overflows": 0}
+        self.gain = None
+
+    def get_sample_rate(self):
+        return self.sample_rate
+
+    def get_center_freq(self):
+        return self.center_freq
+
+    def put(self, chunk: np.ndarray) -> None:
+        """Producer side: non-blocking put, drop the OLDEST chunk on overflow (:221-237)."""
+        try:
+            self._q.put(chunk, block=False)
+        except self._queue_mod.Full:
+            try:
+                old = self._q.get_nowait()
+                self.stats["samples_dropped"] += len(old)
+                self.stats["queue_overflows"] += 1
+            except self._queue_mod.Empty:
+                pass
+            self._q.put(chunk, block=False)
+
+    def read_samples(self, count: int):
+        import time
+        if count <= 0:
+            return np.array([], dtype=np.complex64)
+        fresh = None
+        while True:                                               # :269-276
+            try:
+                fresh = self._q.get_nowait()
+            except self._queue_mod.Empty:
+                break
+        if fresh is not None:
+            self._reservoir = fresh
+        if len(self._reservoir) >= count:                         # :281-284
+            result = self._reservoir[-count:]
+            self._reservoir = self._reservoir[:-count]
+            return result
+        start = time.time()
+        while len(self._reservoir) < count:                       # :287-301
+            if time.time() - start > self.timeout:
+                return None
+            try:
+                chunk = self._q.get(timeout=0.01)
+                while True:
+                    try:
+                        chunk = self._q.get_nowait()
+                    except self._queue_mod.Empty:
+                        break
+                self._reservoir = chunk
+            except self._queue_mod.Empty:
+                continue
+        result = self._reservoir[-count:]
+        self._reservoir = self._reservoir[:-count]
+        return result
+
+    def close(self):
+        pass
+
+
 class B200SampleDataSource(SampleDataSource):
     """Sample-mode source with the window -> FFT -> |.|^2 -> avg -> dB chain on the GPU."""
 
@@ -298,43 +401,64 @@ class B200SampleDataSource(SampleDataSource):
         if not self.running:
             return self._zeros()
         try:
-            fs = self.sdr.get_sample_rate()
-            fc = self.sdr.get_center_freq()
-            if self._flush_reads_remaining > 0:
-                for _ in range(self._flush_reads_remaining):
-                    self.sdr.read_samples(self.fft_size)
-                self._flush_reads_remaining = 0
-            samples = np.asarray(self.sdr.read_samples(self.fft_size))
-            self._store_raw(samples.copy())
-            plan = self._ensure_plan()
-            mode, floor = self._mode_and_floor()
-            if (plan.mode, plan.log_floor, plan.fs) != (mode, floor, float(fs)):
-                plan.set_mode(mode, floor, float(fs))
-            self._pin_in.numpy()[:] = samples                      # complex128 feeds narrow to complex64 here
-            self._x_dev.copy_(self._pin_in, non_blocking=True)
-            x = self._x_dev.view(1, self.fft_size)
-            st = self._state
-            st.avg_mode, st.avg_n = self._avg_settings.mode, self._avg_settings.n
+            row, bins, held = self._device_row()
+            if held is not None:
+                return held, bins
+            power_db = row[0].cpu().numpy().astype(self.out_dtype)
             if self.style == "hackrf":
-                if st.averaging or self.use_psd:
-                    # |X|^2 [/(fs*N)] -> averager -> 10*log10 (hackrf_samples.py:374-381)
-                    db, silent = plan.psd_db_avg_hold_dc(x, st, self._dc_state, self._DC_ALPHA, last_only=True)
-                else:
-                    db, silent = plan.psd_db_dc(x, self._dc_state, self._DC_ALPHA)       # :383
-                if int(silent.item()):
-                    if self._last_good_power is not None:                                # :351-355
-                        return self._last_good_power, self._bins(fs, fc)
-                    return np.zeros(self.fft_size), self._bins(fs, fc)
-                power_db = db[0].cpu().numpy().astype(self.out_dtype)
                 self._last_good_power = power_db
-            elif st.averaging:
-                power_db = plan.psd_db_avg_hold(x, st, last_only=True)[0].cpu().numpy().astype(self.out_dtype)
-            else:
-                power_db = plan.psd_db(x)[0].cpu().numpy().astype(self.out_dtype)
-            return power_db, self._bins(fs, fc)
+            return power_db, bins
         except Exception as e:
             logger.error("Error computing power levels: %s", e)
             return self._zeros()
+
+    def get_power_levels_device(self):
+        """Same frame as :meth:`get_power_levels` but left on the GPU: ``(float32 CUDA row [1, N], freq_bins)``.
+
+        Used by ``frame_pipeline.B200FramePipeline`` so cal/tare/holds/peaks run without a host round trip.
+        Returns ``(None, bins)`` when the HackRF-style silence hold applies (caller keeps its last row)."""
+        row, bins, held = self._device_row()
+        return (None if held is not None else row), bins
+
+    def _device_row(self):
+        """Read one frame from the feed and run the fused kernel. Returns (device row, bins, held_host_row)."""
+        fs = self.sdr.get_sample_rate()
+        fc = self.sdr.get_center_freq()
+        if self._flush_reads_remaining > 0:
+            for _ in range(self._flush_reads_remaining):
+                self.sdr.read_samples(self.fft_size)
+            self._flush_reads_remaining = 0
+        samples = self.sdr.read_samples(self.fft_size)
+        if samples is None:                                    # feed timed out (hackrf_samples.py:351)
+            if self._last_good_power is not None:
+                return None, self._bins(fs, fc), self._last_good_power
+            return None, self._bins(fs, fc), np.zeros(self.fft_size)
+        samples = np.asarray(samples)
+        self._store_raw(samples.copy())
+        plan = self._ensure_plan()
+        mode, floor = self._mode_and_floor()
+        if (plan.mode, plan.log_floor, plan.fs) != (mode, floor, float(fs)):
+            plan.set_mode(mode, floor, float(fs))
+        self._pin_in.numpy()[:] = samples                      # complex128 feeds narrow to complex64 here
+        self._x_dev.copy_(self._pin_in, non_blocking=True)
+        x = self._x_dev.view(1, self.fft_size)
+        st = self._state
+        st.avg_mode, st.avg_n = self._avg_settings.mode, self._avg_settings.n
+        if self.style == "hackrf":
+            if st.averaging or self.use_psd:
+                # |X|^2 [/(fs*N)] -> averager -> 10*log10 (hackrf_samples.py:374-381)
+                db, silent = plan.psd_db_avg_hold_dc(x, st, self._dc_state, self._DC_ALPHA, last_only=True)
+            else:
+                db, silent = plan.psd_db_dc(x, self._dc_state, self._DC_ALPHA)       # :383
+            if int(silent.item()):
+                if self._last_good_power is not None:                                # :351-355
+                    return None, self._bins(fs, fc), self._last_good_power
+                return None, self._bins(fs, fc), np.zeros(self.fft_size)
+        elif st.averaging:
+            db = plan.psd_db_avg_hold(x, st, last_only=True)
+        else:
+            db = plan.psd_db(x)
+        return db, self._bins(fs, fc), None
 
     def get_power_levels_batch(self, n_frames: int):
         """Extension for streaming use: ``n_frames`` consecutive frames in one launch -> ``[B, N]`` float32."""

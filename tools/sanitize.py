@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Small workload for compute-sanitizer: every kernel family once, few frames."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from topdogspectrumanalyser_b200 import synth
+from topdogspectrumanalyser_b200.engine import SpectrumPlan, TraceState, trace_update, stitch, WaterfallRing
+from topdogspectrumanalyser_b200 import analytics as A
+dev = torch.device("cuda:0")
+for n in (512, 1024, 4096, 8192, 65536):
+    for prec in ("f64", "f32"):
+        b = 700 if n == 4096 else (3 if n > 8192 else 40)       # 4096: more frames than resident CTAs -> ring refills
+        x = torch.from_numpy(synth.cfg2_frames(b=b, n=n, seed=n)).to(dev)
+        plan = SpectrumPlan(n, precision=prec, device=dev)
+        y = plan.psd_db(x)
+        st = TraceState(n, dev); st.set_averaging("exp", 4); st.max_hold_enabled = st.min_hold_enabled = True
+        if n <= 8192:
+            plan.psd_db_avg_hold(x[:8], st)
+            plan.psd_db_dc(x[:4], torch.zeros(2, dtype=torch.float64, device=dev))
+        torch.cuda.synchronize(); plan.close()
+        print("ok", n, prec, float(y[0, 0]))
+plan = SpectrumPlan(65536, device=dev)
+plan.welch(torch.from_numpy(synth.cfg3_stream(1 << 18)).to(dev), 32768)
+rows = torch.randn(6, 4096, device=dev)
+st = TraceState(4096, dev); st.start_tare(); st.max_hold_enabled = True
+trace_update(rows, st, -1.0)
+A.top_peaks(np.arange(4096.0), rows[0]); A.DensityHistogram(4096, dev).update(rows[0])
+ring = WaterfallRing(8, 4096, -100.0, dev); ring.push(rows)
+stitch(rows[:, :50].contiguous(), torch.arange(6, dtype=torch.float64, device=dev) * 5e6, 5e6, 0.0, 30e6, 300)
+torch.cuda.synchronize(); print("all ok")

@@ -790,7 +790,7 @@ int tdsa_psd_db_batch_host(tdsa_handle_t p, const void* iq_host, int64_t n_frame
   if (n_frames == 0) return TDSA_OK;
   if (!iq_host || !db_out_host) return fail(TDSA_ERR_INVALID, "null buffer");
   const int64_t n = p->n;
-  if (chunk_frames < 1) chunk_frames = std::max<int64_t>(1, ((int64_t)32 << 20) / (n * 8));   // ~32 MiB of IQ per chunk
+  if (chunk_frames < 1) chunk_frames = std::max<int64_t>(1, ((int64_t)16 << 20) / (n * 8));   // ~16 MiB of IQ per chunk (measured best of 4..64 MiB)
   chunk_frames = std::min(chunk_frames, n_frames);
   const size_t in_bytes = (size_t)((chunk_frames - 1) * stride + n) * sizeof(float2);
   const size_t out_bytes = (size_t)chunk_frames * n * sizeof(float);

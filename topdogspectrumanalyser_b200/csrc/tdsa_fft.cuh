@@ -27,6 +27,10 @@ namespace tdsa {
 #ifndef TDSA_L2_AHEAD
 #define TDSA_L2_AHEAD 0   // measured: 0, 2 and 4 frames ahead are within noise of each other at N=4096
 #endif
+// programmatic dependent launch (griddepcontrol) on the fused kernel
+#ifndef TDSA_PDL
+#define TDSA_PDL 0   // measured: no gain at 80-150 us per launch (81.9 vs 82.0 us); kept as an option
+#endif
 #ifndef TDSA_PADS_R8
 #define TDSA_PADS_R8(LOG2N, WIDE) pads_r8(LOG2N, WIDE)
 #endif
@@ -87,6 +91,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
+// programmatic dependent launch: let the next launch on the stream start its prologue early, and make this
+// grid wait for the previous one (completion + memory flush) before it touches any frame data
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -479,25 +487,14 @@ fft_fused_kernel(const FftArgs<T> a) {
   auto acquire = [&]() { if constexpr (GROUPS > 1) bar_sync(3 + g, 2 * TH); };
   auto release = [&]() { if constexpr (GROUPS > 1) bar_arrive(3 + (1 - g), 2 * TH); };
 
+#if TDSA_PDL
+  pdl_launch_dependents();
+#endif
   if constexpr (NSTAGE > 0) {
     if (t == 0) {
 #pragma unroll
       for (int s = 0; s < NSTAGE; ++s) mbar_init(bar_u32 + 8 * s, 1);
       fence_mbar_init();
-#pragma unroll
-      for (int s = 0; s < NSTAGE; ++s) {
-        const int64_t fs = unit + (int64_t)s * unit_stride;
-        if (fs < a.n_frames) {
-          mbar_arrive_expect_tx(bar_u32 + 8 * s, (uint32_t)P::STAGE_BYTES);
-          bulk_g2s(stage_u32 + (uint32_t)(s * P::STAGE_BYTES), a.iq + fs * a.frame_stride, (uint32_t)P::STAGE_BYTES,
-                   bar_u32 + 8 * s);
-        }
-      }
-#pragma unroll
-      for (int s = NSTAGE; s < NSTAGE + kL2Ahead; ++s) {
-        const int64_t fs = unit + (int64_t)s * unit_stride;
-        if (fs < a.n_frames) bulk_prefetch_l2(a.iq + fs * a.frame_stride, (uint32_t)P::STAGE_BYTES);
-      }
     }
   }
 
@@ -535,6 +532,27 @@ fft_fused_kernel(const FftArgs<T> a) {
 #pragma unroll
     for (int j = 1; j < 16; ++j) {
       if (j < 4 || (j & 3) == 0) { const CT w = tw_last[j * (DIT ? KLAST : TH) + t]; twlr[j] = w.x; twli[j] = w.y; }
+    }
+  }
+#if TDSA_PDL
+  pdl_wait_prior_grid();            // everything above only touched plan tables; frame data may come from the prior grid
+#endif
+  if constexpr (NSTAGE > 0) {
+    if (t == 0) {
+#pragma unroll
+      for (int s = 0; s < NSTAGE; ++s) {
+        const int64_t fs = unit + (int64_t)s * unit_stride;
+        if (fs < a.n_frames) {
+          mbar_arrive_expect_tx(bar_u32 + 8 * s, (uint32_t)P::STAGE_BYTES);
+          bulk_g2s(stage_u32 + (uint32_t)(s * P::STAGE_BYTES), a.iq + fs * a.frame_stride, (uint32_t)P::STAGE_BYTES,
+                   bar_u32 + 8 * s);
+        }
+      }
+#pragma unroll
+      for (int s = NSTAGE; s < NSTAGE + kL2Ahead; ++s) {
+        const int64_t fs = unit + (int64_t)s * unit_stride;
+        if (fs < a.n_frames) bulk_prefetch_l2(a.iq + fs * a.frame_stride, (uint32_t)P::STAGE_BYTES);
+      }
     }
   }
   if constexpr (P::TW_SMEM > 0 || NSTAGE > 0) __syncthreads();   // tables staged, mbarriers initialised

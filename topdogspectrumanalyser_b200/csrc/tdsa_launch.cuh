@@ -107,9 +107,21 @@ cudaError_t launch_final(const FftArgs<T>& a, int sm_count, cudaStream_t stream,
     info->stages = NSTAGE; info->logr = LOGR;
   }
   if (dry || a.n_frames <= 0) return cudaSuccess;
+#if TDSA_PDL
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return le != cudaSuccess ? le : cudaGetLastError();
+#else
   kern<<<grid, kThreads, kSmem, stream>>>(a);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return cudaGetLastError();
+#endif
 }
 
 // DC removal (hackrf front end) and bulk-copy staging are only compiled for whole transforms (TAIL == 0).

@@ -125,6 +125,36 @@ def test_empty_and_strided(dev):
     plan.close()
 
 
+def test_unaligned_frames_take_the_direct_load_path(dev):
+    """Odd frame_stride / 8-byte-aligned base: the bulk-copy staging needs 16-byte frames, so the launcher must fall
+    back to direct loads and still match (both precisions)."""
+    import torch
+    from topdogspectrumanalyser_b200.engine import SpectrumPlan
+    stream = synth.cfg3_stream(n_samples=40000, seed=9)
+    x = torch.from_numpy(stream).to(dev)
+    for prec, tol in (("f64", TOL_DB), ("f32", 5e-2)):
+        plan = SpectrumPlan(4096, precision=prec, device=dev)
+        got = plan.psd_db(x[1:], n_frames=9, frame_stride=3001).cpu().numpy().astype(np.float64)   # base + 8 B, odd stride
+        frames = np.stack([stream[1 + i * 3001:1 + i * 3001 + 4096] for i in range(9)])
+        want = O.power_db_batch(frames, O.make_window("hanning", 4096))
+        assert np.abs(got - want).max() <= tol, prec
+        plan.close()
+
+
+def test_many_more_frames_than_resident_ctas(dev):
+    """Ring refills and the persistent frame loop: 3001 frames of 1024 points (odd count, > one wave), f64 and f32."""
+    import torch
+    from topdogspectrumanalyser_b200.engine import SpectrumPlan
+    iq = synth.cfg2_frames(b=3001, n=1024, seed=12)
+    want = O.power_db_batch(iq, O.make_window("hanning", 1024), workers=-1)
+    x = torch.from_numpy(iq).to(dev)
+    plan = SpectrumPlan(1024, device=dev)
+    assert np.abs(plan.psd_db(x).cpu().numpy() - want).max() <= TOL_DB
+    plan.set_precision("f32")
+    f32_tail_ok(plan.psd_db(x).cpu().numpy().astype(np.float64), want)
+    plan.close()
+
+
 def test_unsupported_size_fails_loudly(dev):
     from topdogspectrumanalyser_b200 import _lib
     from topdogspectrumanalyser_b200.engine import SpectrumPlan

@@ -75,6 +75,10 @@ static bool is_big(const tdsa_plan* p) {
   return p->log2n > (p->precision == TDSA_PREC_F32 ? MaxLog2<float>::value : MaxLog2<double>::value);
 }
 
+// Large transforms: one radix-16 head pass when the remaining M = N/16 fits the single-CTA kernels best tuned
+// range (M <= 4096), otherwise two head passes (N = 256*M).
+static int big_head_passes(const tdsa_plan* p) { return (p->log2n - 4 <= 12) ? 1 : 2; }
+
 static int ensure_scratch(void** ptr, size_t* have, size_t need) {
   if (*have >= need) return TDSA_OK;
   if (*ptr) cudaFree(*ptr);
@@ -291,7 +295,7 @@ int tdsa_create(int n_fft, int window_id, int window_norm, int mode, double log_
     if (rc) break;
     if (p->log2n > MaxLog2<float>::value || p->log2n > MaxLog2<double>::value) {
       // tables for the inner (N/256)-point transform of the two-kernel path
-      rc = upload_twiddles(p->log2n - 8, 4, 4, &p->d_twin64, &p->d_twin32);
+      rc = upload_twiddles(p->log2n - 4 * big_head_passes(p), 4, 4, &p->d_twin64, &p->d_twin32);
       if (rc) break;
       std::vector<double2> th;
       build_twiddles_head(p->log2n, th);
@@ -542,8 +546,9 @@ int tdsa_welch(tdsa_handle_t p, const void* iq_stream, int64_t n_samples, int64_
     count_launch();
     CK(cudaGetLastError());
   }
-  welch_finish_kernel<<<(int)((n + 255) / 256), 256, 0, p->stream>>>(sum, peak, n, nseg, big ? p->log2n - 8 : 0, p->floor,
-                                                                   p->mode, avg_db, peak_db);
+  welch_finish_kernel<<<(int)((n + 255) / 256), 256, 0, p->stream>>>(sum, peak, n, nseg,
+                                                                   big ? p->log2n - 4 * big_head_passes(p) : 0,
+                                                                   big ? big_head_passes(p) : 0, p->floor, p->mode, avg_db, peak_db);
   count_launch();
   CK(cudaGetLastError());
   return TDSA_OK;

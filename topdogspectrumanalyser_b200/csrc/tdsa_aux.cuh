@@ -496,19 +496,19 @@ __global__ void __launch_bounds__(256) group_mean_db_kernel(const double* __rest
   db_out[i] = to_db<double>(buf, ep);
 }
 
-// final: avg_db[k] = dB(sum/nseg); optional un-permute for the two-kernel large-FFT path:
-// permuted index i = s*M + klow with s = 16*k0 + k1  ->  k = k0 + 16*k1 + 256*klow.
+// final: avg_db[k] = dB(sum/nseg); optional un-permute for the two-kernel large-FFT path: permuted index
+// i = s*M + klow;  two head passes: s = 16*k0 + k1 -> k = k0 + 16*k1 + 256*klow;  one head pass: k = s + 16*klow.
 __global__ void __launch_bounds__(256) welch_finish_kernel(const double* __restrict__ sum_state,
                                                           const float* __restrict__ peak_state, int64_t width,
-                                                          int64_t n_seg, int log2_m_perm, double floor, int mode,
-                                                          float* __restrict__ avg_db, float* __restrict__ peak_db) {
+                                                          int64_t n_seg, int log2_m_perm, int head_passes, double floor,
+                                                          int mode, float* __restrict__ avg_db, float* __restrict__ peak_db) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= width) return;
   int64_t k = i;
   if (log2_m_perm > 0) {
     const int64_t m = (int64_t)1 << log2_m_perm;
     const int64_t s = i >> log2_m_perm, kl = i & (m - 1);
-    k = (s >> 4) + 16 * (s & 15) + 256 * kl;
+    k = (head_passes == 1) ? s + 16 * kl : (s >> 4) + 16 * (s & 15) + 256 * kl;
   }
   EpiParams ep;
   ep.db_out = nullptr; ep.lin_out = nullptr; ep.scale = 1.0; ep.floor = floor; ep.mode = mode;

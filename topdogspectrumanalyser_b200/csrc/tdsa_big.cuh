@@ -71,4 +71,40 @@ __global__ void __launch_bounds__(256, 2) big_head_kernel(const BigArgs<T> a) {
   }
 }
 
+// One-pass head for N = 16*M (M <= 4096, e.g. 65536 = 16 x 4096): every thread owns one column c of the
+// N-point frame, reads x[c + j*N/16] (coalesced across threads), applies the window, runs one radix-16 and the
+// post-twiddle W_N^(c*q), and writes sub-transform q to Y[q*N/16 + c] (coalesced). No shared memory at all;
+// the M-point sub-transforms are finished by fft_fused_kernel<TAIL = 3>, which for M = 4096 is the tuned kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) big_head1_kernel(const BigArgs<T> a) {
+  using CT = typename CplxOf<T>::type;
+  const int64_t n = (int64_t)1 << a.log2n;
+  const int64_t s0 = n >> 4;                               // columns per frame = M
+  const int64_t total = a.n_frames * s0;
+  for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < total; w += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = w / s0, c = w - f * s0;
+    T re[16], im[16];
+    {
+      const float2* src = a.iq + f * a.frame_stride + c;
+      float2 v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = ldg_stream(src + j * s0);
+      T dcr = T(0), dci = T(0);
+      if (a.dc != nullptr) { double2 d = a.dc[f]; dcr = (T)d.x; dci = (T)d.y; }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const T wv = a.window[c + j * s0];
+        re[j] = ((T)v[j].x - dcr) * wv;
+        im[j] = ((T)v[j].y - dci) * wv;
+      }
+    }
+    dft16<T>(re, im);
+#pragma unroll
+    for (int q = 1; q < 16; ++q) { const CT wq = a.tw[q * s0 + c]; cmul<T>(re[q], im[q], wq.x, wq.y); }
+    CT* dst = a.y + f * n + c;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) dst[q * s0] = mk<T>(re[q], im[q]);
+  }
+}
+
 }  // namespace tdsa

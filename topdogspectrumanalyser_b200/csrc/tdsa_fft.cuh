@@ -442,6 +442,8 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
 //           s2 = g & 255 of big frame g >> 8 (input complex T from big_head_kernel's scratch);
 //           bin klow of it is bin (s2 >> 4) + 16*(s2 & 15) + 256*klow of the 256*N-point frame.
 // TAIL = 2: same input, rows left in the permuted [g][klow] order (coalesced stores).
+// TAIL = 3: second kernel after the ONE-pass head (N_big = 16*N): "frame" g is sub-transform s = g & 15 of big
+//           frame g >> 4; bin klow of it is bin s + 16*klow.
 // TWMODE: where the per-thread pass-0 constants (15 twiddles W_N^(t*q), 16 window values) live.
 //   0 = read from the tables every frame (L1/L2);
 //   1 = all of them in registers for the whole kernel (float32: 46 registers);
@@ -729,6 +731,8 @@ fft_fused_kernel(const FftArgs<T> a) {
           if constexpr (TAIL == 1) {
             const int s2 = (int)(f & 255);
             Epi::template store<T, MAG>(a.ep, f >> 8, N * 256, (s2 >> 4) + 16 * (s2 & 15) + 256 * k, pw);
+          } else if constexpr (TAIL == 3) {
+            Epi::template store<T, MAG>(a.ep, f >> 4, N * 16, (int)(f & 15) + 16 * k, pw);
           } else {
             Epi::template store<T, MAG>(a.ep, f, N, k, pw);
           }

@@ -9,7 +9,14 @@ int effective_logr_f64(int log2n) { return effective_logr<double>(log2n); }
 
 #include "tdsa_big.cuh"
 namespace tdsa {
-cudaError_t launch_big_head_f64(const BigArgs<double>& a, int sm, cudaStream_t s) {
+cudaError_t launch_big_head_f64(const BigArgs<double>& a, int sm, cudaStream_t s, int passes) {
+  if (passes == 1) {
+    const int64_t work = a.n_frames * (((int64_t)1 << a.log2n) >> 4);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)sm * 8));
+    big_head1_kernel<double><<<grid, 256, 0, s>>>(a);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+  }
   constexpr int kSmem = 4096 * 2 * sizeof(double);
   static bool once = false;
   if (!once) {

@@ -9,7 +9,8 @@
 
 namespace tdsa {
 
-enum : int { kEpiDb = 0, kEpiLinear = 1, kEpiDbTail = 2, kEpiLinearTail = 3, kEpiLinearPermuted = 4 };
+enum : int { kEpiDb = 0, kEpiLinear = 1, kEpiDbTail = 2, kEpiLinearTail = 3, kEpiLinearPermuted = 4,
+             kEpiDbTail16 = 5, kEpiLinearTail16 = 6 };   // Tail16: after the one-pass head (N_big = 16*M)
 
 struct LaunchInfo {
   int threads = 0;
@@ -174,6 +175,8 @@ cudaError_t launch_epi(int epi, const FftArgs<T>& a, int sm_count, cudaStream_t 
       case kEpiDbTail: return launch_one<T, LOG2N, EpiDb, 1, 4>(a, sm_count, stream, info, dry);
       case kEpiLinearTail: return launch_one<T, LOG2N, EpiLinear, 1, 4>(a, sm_count, stream, info, dry);
       case kEpiLinearPermuted: return launch_one<T, LOG2N, EpiLinear, 2, 4>(a, sm_count, stream, info, dry);
+      case kEpiDbTail16: return launch_one<T, LOG2N, EpiDb, 3, 4>(a, sm_count, stream, info, dry);
+      case kEpiLinearTail16: return launch_one<T, LOG2N, EpiLinear, 3, 4>(a, sm_count, stream, info, dry);
       default: break;
     }
   }
@@ -206,7 +209,8 @@ int effective_logr_f32(int log2n);
 int effective_logr_f64(int log2n);
 // head kernel of the two-kernel path (tdsa_big.cuh), defined next to the matching precision
 template <typename T> struct BigArgs;
-cudaError_t launch_big_head_f32(const BigArgs<float>& a, int sm, cudaStream_t s);
-cudaError_t launch_big_head_f64(const BigArgs<double>& a, int sm, cudaStream_t s);
+// passes = 2: big_head_kernel (N = 256*M); passes = 1: big_head1_kernel (N = 16*M)
+cudaError_t launch_big_head_f32(const BigArgs<float>& a, int sm, cudaStream_t s, int passes);
+cudaError_t launch_big_head_f64(const BigArgs<double>& a, int sm, cudaStream_t s, int passes);
 
 }  // namespace tdsa

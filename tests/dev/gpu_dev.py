@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Developer diagnostics on a GPU box: per-size error statistics and quick kernel timings."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from oracle import oracle as O

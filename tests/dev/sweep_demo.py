@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """Config 4 end to end on N GPUs (torchrun): shard sub-bands, kernel 1 + group average, NCCL all-gather, stitch.
 
-  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/sweep_demo.py [--check]
+  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tests/dev/sweep_demo.py [--check]
 """
 import argparse, os, sys, time, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 import torch.distributed as dist

@@ -64,9 +64,6 @@ extern "C" {
 #define TDSA_AVG_EXP 1
 #define TDSA_AVG_LIN 2
 
-/* flags for tdsa_trace_update */
-#define TDSA_HOLD_MAX 1
-#define TDSA_HOLD_MIN 2
 
 typedef struct tdsa_plan* tdsa_handle_t;
 

@@ -263,3 +263,43 @@ def test_streaming_waterfall(dev):
         for f in synth.cfg5_chunk(c).reshape(16, n):
             ring.add_row(O.power_db_frame(f, w, O.MODE_POWER, averager=a).astype(np.float32))
     assert np.abs(st.history().cpu().numpy() - ring.view()).max() <= TOL_DB
+
+
+def test_cabi_error_codes_and_messages(dev):
+    """Every entry point answers bad arguments with a negative TDSA_ERR_* and a message (include/tdsa.h conventions)."""
+    import ctypes as C
+    import torch
+    from topdogspectrumanalyser_b200 import _lib as L
+    from topdogspectrumanalyser_b200.engine import SpectrumPlan, TraceState
+    lib = L.load()
+    h = C.c_void_p()
+    assert lib.tdsa_create(1000, 0, 0, 0, 1e-10, 1.0, 0, C.byref(h)) == -2 and b"powers of two" in lib.tdsa_last_error()
+    assert lib.tdsa_create(1024, 9, 0, 0, 1e-10, 1.0, 0, C.byref(h)) == -1
+    assert lib.tdsa_create(1024, 0, 0, 7, 1e-10, 1.0, 0, C.byref(h)) == -1
+    assert lib.tdsa_create(1024, 0, 0, 0, 1e-10, 1.0, 5, C.byref(h)) == -1
+    assert lib.tdsa_create(1 << 21, 0, 0, 0, 1e-10, 1.0, 0, C.byref(h)) == -2
+    assert lib.tdsa_psd_db_batch(None, None, 1, 1024, None) == -1
+    plan = SpectrumPlan(1024, device=dev)
+    x = torch.zeros((2, 1024), dtype=torch.complex64, device=dev)
+    y = torch.zeros((2, 1024), dtype=torch.float32, device=dev)
+    assert lib.tdsa_psd_db_batch(plan._h, x.data_ptr(), -1, 1024, y.data_ptr()) == -1
+    assert lib.tdsa_psd_db_batch(plan._h, x.data_ptr(), 2, 0, y.data_ptr()) == -1
+    assert lib.tdsa_psd_db_batch(plan._h, None, 2, 1024, y.data_ptr()) == -1
+    assert lib.tdsa_psd_db_batch(plan._h, x.data_ptr() + 4, 1, 1024, y.data_ptr()) == -1 and b"aligned" in lib.tdsa_last_error()
+    assert lib.tdsa_psd_db_batch(plan._h, x.data_ptr(), 0, 1024, y.data_ptr()) == 0          # empty batch is fine
+    assert lib.tdsa_welch(plan._h, x.data_ptr(), 100, 512, y.data_ptr(), y.data_ptr()) == -1
+    assert lib.tdsa_set_mode(plan._h, 9, 1e-10, 1.0) == -1
+    # the mag20 branch is never averaged in the reference (hackrf_samples.py:378-383)
+    plan.set_mode("mag20")
+    st = TraceState(1024, dev)
+    st.set_averaging("exp", 4)
+    with pytest.raises(L.TdsaError):
+        plan.psd_db_avg_hold(x, st)
+    # averaging without state / holds without flags
+    plan.set_mode("power")
+    assert lib.tdsa_psd_db_avg_hold(plan._h, x.data_ptr(), 2, 1024, 1, 4, None, None, None, None, None, 0, y.data_ptr()) == -1
+    assert lib.tdsa_top_peaks(y.data_ptr(), 1 << 20, 5, 10, C.c_float(10.0), None, None, None, None) == -1
+    idx = torch.zeros(16, dtype=torch.int32, device=dev)
+    assert lib.tdsa_top_peaks(y.data_ptr(), 1 << 20, 5, 10, C.c_float(10.0), idx.data_ptr(), y.data_ptr(), idx.data_ptr(), None) == -2
+    plan.close()
+    plan.close()                                                  # idempotent

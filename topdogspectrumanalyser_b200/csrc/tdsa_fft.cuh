@@ -169,6 +169,23 @@ __device__ __forceinline__ void r4_tw(T* re, T* im, const T* wr, const T* wi) {
   re[I3] = t1r - t3i; im[I3] = t1i + t3r;   // t1 + i*t3
 }
 
+// Radix-4 butterfly on windowed samples a[Ik] = x[Ik]*w[Ik] with REAL weights (pass 0): the window multiply is
+// folded into the first radix-2 level (p0 = x0*w0; t0 = p0 + x2*w2; t1 = p0 - x2*w2: 3 operations per component
+// instead of 4). xr/xi hold the raw (converted) samples, w the window values.
+template <typename T, int I0, int I1, int I2, int I3>
+__device__ __forceinline__ void r4_win(T* re, T* im, const T* w) {
+  const T p0r = re[I0] * w[I0], p0i = im[I0] * w[I0];
+  const T t0r = fm<T>(re[I2], w[I2], p0r), t0i = fm<T>(im[I2], w[I2], p0i);
+  const T t1r = fm<T>(-re[I2], w[I2], p0r), t1i = fm<T>(-im[I2], w[I2], p0i);
+  const T p1r = re[I1] * w[I1], p1i = im[I1] * w[I1];
+  const T t2r = fm<T>(re[I3], w[I3], p1r), t2i = fm<T>(im[I3], w[I3], p1i);
+  const T t3r = fm<T>(-re[I3], w[I3], p1r), t3i = fm<T>(-im[I3], w[I3], p1i);
+  re[I0] = t0r + t2r; im[I0] = t0i + t2i;
+  re[I2] = t0r - t2r; im[I2] = t0i - t2i;
+  re[I1] = t1r + t3i; im[I1] = t1i - t3r;
+  re[I3] = t1r - t3i; im[I3] = t1i + t3r;
+}
+
 // Second half of the 16-point DFT: four radix-4 butterflies over j0 whose inputs B[j0][q0] = a[4*q0 + j0]
 // carry the constant twiddles W16^(j0*q0), folded in the same way; then the 4x4 transpose to natural order.
 template <typename T> __device__ __forceinline__ void dft16_stage_b(T* re, T* im) {
@@ -206,6 +223,15 @@ template <typename T> __device__ __forceinline__ void dft16(T* re, T* im) {
   r4<T, 1, 5, 9, 13>(re, im);
   r4<T, 2, 6, 10, 14>(re, im);
   r4<T, 3, 7, 11, 15>(re, im);
+  dft16_stage_b<T>(re, im);
+}
+
+// 16-point DFT of x[j]*w[j] with real window weights w, the multiply folded into stage A (pass 0).
+template <typename T> __device__ __forceinline__ void dft16_win(T* re, T* im, const T* w) {
+  r4_win<T, 0, 4, 8, 12>(re, im, w);
+  r4_win<T, 1, 5, 9, 13>(re, im, w);
+  r4_win<T, 2, 6, 10, 14>(re, im, w);
+  r4_win<T, 3, 7, 11, 15>(re, im, w);
   dft16_stage_b<T>(re, im);
 }
 
@@ -606,18 +632,27 @@ fft_fused_kernel(const FftArgs<T> a) {
         for (int j = 0; j < PP; ++j) v[j] = ldg_stream(src + j * TH);
       }
       acquire();
+      if constexpr (PP == 16) {            // window folded into the first butterfly level
 #pragma unroll
-      for (int j = 0; j < PP; ++j) {
-        if constexpr (HAS_DC) {
-          re[j] = ((T)v[j].x - dcr) * win[j];
-          im[j] = ((T)v[j].y - dci) * win[j];
-        } else {
-          re[j] = (T)v[j].x * win[j];
-          im[j] = (T)v[j].y * win[j];
+        for (int j = 0; j < PP; ++j) {
+          if constexpr (HAS_DC) { re[j] = (T)v[j].x - dcr; im[j] = (T)v[j].y - dci; }
+          else { re[j] = (T)v[j].x; im[j] = (T)v[j].y; }
+        }
+        dft16_win<T>(re, im, win);
+      } else {
+#pragma unroll
+        for (int j = 0; j < PP; ++j) {
+          if constexpr (HAS_DC) {
+            re[j] = ((T)v[j].x - dcr) * win[j];
+            im[j] = ((T)v[j].y - dci) * win[j];
+          } else {
+            re[j] = (T)v[j].x * win[j];
+            im[j] = (T)v[j].y * win[j];
+          }
         }
       }
     }
-    dft_full<T, PP>(re, im);
+    if constexpr (TAIL != 0 || PP != 16) dft_full<T, PP>(re, im);
     if constexpr (!DIT) {                    // DIF: post-twiddle W_N^(t*q)
 #pragma unroll
       for (int q = 1; q < PP; ++q) {

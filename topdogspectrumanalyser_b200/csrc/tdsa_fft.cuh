@@ -418,9 +418,9 @@ template <typename T, bool MAG20> __device__ __forceinline__ float to_db_m(T p, 
     const float m = sqrtf((float)p) + (float)ep.floor;
     return 2.0f * kDbPerLog2 * lg2_approx(m);
   } else {
-    // scale in T, then narrow once; the floor (1e-10 / 1e-12) is added in float32: it only matters when the
-    // scaled power is itself that small, where float32 still resolves it to 6e-8 relative.
-    const float v = (float)(p * (T)ep.scale) + (float)ep.floor;
+    // narrow once, then scale and add the floor (1e-10 / 1e-12) with one float32 FMA: 6e-8 relative on the
+    // argument of the log is 2.6e-7 dB, and it keeps 16 multiplies per thread off the FP64 pipe
+    const float v = __fmaf_rn((float)p, (float)ep.scale, (float)ep.floor);
     return kDbPerLog2 * lg2_approx(v);
   }
 }

@@ -58,6 +58,11 @@ struct tdsa_plan {
   double* d_win64 = nullptr; float* d_win32 = nullptr;        // with (-1)^n folded in
   double2* d_tw64 = nullptr; float2* d_tw32 = nullptr;
   bool win_dirty = true;
+  // warp-local 4096-point kernel (tdsa_fft_wl.cuh): window permuted to its thread order, frame scheduler
+  // words {next, done}, and the tensor map of the last input batch
+  double* d_wperm64 = nullptr; float* d_wperm32 = nullptr;
+  int* d_sched = nullptr;
+  CUtensorMap tmap; const void* tmap_ptr = nullptr; int64_t tmap_frames = -1, tmap_stride = -1;
   // large-FFT (two-kernel) tables: inner plan size M = N/256
   double2* d_twin64 = nullptr; float2* d_twin32 = nullptr;    // twiddles of the M-point inner transform
   double2* d_twh64 = nullptr; float2* d_twh32 = nullptr;      // DIF tables of big_head_kernel (passes 0, 1)
@@ -125,8 +130,62 @@ static int upload_window(tdsa_plan* p) {
   }
   CK(cudaMemcpy(p->d_win64, w64.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(p->d_win32, w32.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+  if (p->d_wperm64) {   // thread tid of fft_wl_kernel owns samples r + 16 c + 256 j
+    std::vector<double> p64(n);
+    std::vector<float> p32(n);
+    for (int tid = 0; tid < 256; ++tid) {
+      int r, c;
+      wl_thread_identity(tid, &r, &c);
+      for (int j = 0; j < 16; ++j) {
+        p64[j * 256 + tid] = w64[r + 16 * c + 256 * j];
+        p32[j * 256 + tid] = w32[r + 16 * c + 256 * j];
+      }
+    }
+    CK(cudaMemcpy(p->d_wperm64, p64.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->d_wperm32, p32.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+  }
   p->win_dirty = false;
   return TDSA_OK;
+}
+
+// ---- tensor map of a batch of 4096-sample frames: [frame][256 rows][32 floats], 128-byte swizzle -------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      ptr = nullptr;
+    return (EncodeTiledFn)ptr;
+  }();
+  return fn;
+}
+
+static bool wl_enabled() {
+  static const bool on = [] { const char* e = getenv("TDSA_WL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+// true when this batch can take the warp-local kernel; fills p->tmap
+static bool wl_prepare(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t stride, int epi) {
+  if (!wl_enabled() || p->log2n != 12 || !p->d_sched || (epi != kEpiDb && epi != kEpiLinear)) return false;
+  if (((uintptr_t)iq & 15) != 0 || (stride & 1) != 0 || stride <= 0 || n_frames <= 0 || n_frames >= (1 << 30)) return false;
+  if (p->tmap_ptr == iq && p->tmap_frames == n_frames && p->tmap_stride == stride) return true;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {32, 256, (cuuint64_t)n_frames};
+  const cuuint64_t strides[2] = {128, (cuuint64_t)stride * 8};
+  const cuuint32_t box[3] = {32, 256, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(&p->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(iq), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { p->tmap_ptr = nullptr; return false; }
+  p->tmap_ptr = iq; p->tmap_frames = n_frames; p->tmap_stride = stride;
+  return true;
 }
 
 // exp(-2*pi*i*m/L), folded to the first octant with exact integer arithmetic so that
@@ -243,16 +302,22 @@ static int run_fused(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t str
   if (p->win_dirty && !dry) { int rc = upload_window(p); if (rc) return rc; }
   if (is_big(p)) return run_big(p, iq, n_frames, stride, dc, epi, db, lin, info, dry);
   cudaError_t e;
+  // dry runs (launch geometry queries) describe the warp-local kernel whenever the size has one
+  const bool wl = dry ? (wl_enabled() && p->log2n == 12 && p->d_sched && (epi == kEpiDb || epi == kEpiLinear) && encode_tiled_fn())
+                      : wl_prepare(p, iq, n_frames, stride, epi);
+  const WlSched sched{p->d_sched, p->d_sched ? p->d_sched + 1 : nullptr};
   if (p->precision == TDSA_PREC_F32) {
     FftArgs<float> a;
     a.iq = (const float2*)iq; a.n_frames = n_frames; a.frame_stride = stride;
     a.window = p->d_win32; a.tw = p->d_tw32; a.dc = dc; a.in_ct = nullptr; a.ep = make_epi(p, db, lin);
-    e = launch_fft_f32(p->log2n, epi, a, p->sm_count, p->stream, info, dry);
+    e = wl ? launch_wl_f32(epi, a, p->tmap, p->d_wperm32, sched, p->sm_count, p->stream, info, dry)
+           : launch_fft_f32(p->log2n, epi, a, p->sm_count, p->stream, info, dry);
   } else {
     FftArgs<double> a;
     a.iq = (const float2*)iq; a.n_frames = n_frames; a.frame_stride = stride;
     a.window = p->d_win64; a.tw = p->d_tw64; a.dc = dc; a.in_ct = nullptr; a.ep = make_epi(p, db, lin);
-    e = launch_fft_f64(p->log2n, epi, a, p->sm_count, p->stream, info, dry);
+    e = wl ? launch_wl_f64(epi, a, p->tmap, p->d_wperm64, sched, p->sm_count, p->stream, info, dry)
+           : launch_fft_f64(p->log2n, epi, a, p->sm_count, p->stream, info, dry);
   }
   if (e != cudaSuccess) return fail(TDSA_ERR_CUDA, "fused FFT launch failed (N=%d): %s", p->n, cudaGetErrorString(e));
   return TDSA_OK;
@@ -293,6 +358,12 @@ int tdsa_create(int n_fft, int window_id, int window_norm, int mode, double log_
         cudaMalloc(&p->d_win32, sizeof(float) * n_fft) != cudaSuccess) { rc = fail(TDSA_ERR_NOMEM, "window alloc failed"); break; }
     rc = upload_twiddles(p->log2n, effective_logr_f64(p->log2n), effective_logr_f32(p->log2n), &p->d_tw64, &p->d_tw32);
     if (rc) break;
+    if (p->log2n == 12 && effective_logr_f64(12) == 4 && effective_logr_f32(12) == 4) {   // warp-local kernel tables
+      if (cudaMalloc(&p->d_wperm64, sizeof(double) * n_fft) != cudaSuccess ||
+          cudaMalloc(&p->d_wperm32, sizeof(float) * n_fft) != cudaSuccess ||
+          cudaMalloc(&p->d_sched, 2 * sizeof(int)) != cudaSuccess ||
+          cudaMemset(p->d_sched, 0, 2 * sizeof(int)) != cudaSuccess) { rc = fail(TDSA_ERR_NOMEM, "warp-local tables alloc failed"); break; }
+    }
     if (p->log2n > MaxLog2<float>::value || p->log2n > MaxLog2<double>::value) {
       // tables for the inner (N/256)-point transform of the two-kernel path
       rc = upload_twiddles(p->log2n - 4 * big_head_passes(p), 4, 4, &p->d_twin64, &p->d_twin32);
@@ -311,6 +382,7 @@ int tdsa_create(int n_fft, int window_id, int window_norm, int mode, double log_
 int tdsa_destroy(tdsa_handle_t p) {
   if (!p) return TDSA_OK;
   cudaFree(p->d_win64); cudaFree(p->d_win32); cudaFree(p->d_tw64); cudaFree(p->d_tw32);
+  cudaFree(p->d_wperm64); cudaFree(p->d_wperm32); cudaFree(p->d_sched);
   cudaFree(p->d_twin64); cudaFree(p->d_twin32); cudaFree(p->d_twh64); cudaFree(p->d_twh32);
   cudaFree(p->scratch); cudaFree(p->scratch2);
   for (int i = 0; i < 2; ++i) {

@@ -453,7 +453,24 @@ template <typename T> struct FftArgs {
   const double2* dc;           // optional per-frame DC estimate to subtract (hackrf path) or nullptr
   const typename CplxOf<T>::type* in_ct;   // TAIL kernels: complex T input [n_frames][N] (no window)
   EpiParams ep;
+  int stagger = 0;             // diagnostic (TDSA_DEBUG_STAGGER): cycles the second half of the grid waits before its first frame
+  long long* dbg = nullptr;    // diagnostic (-DTDSA_DEBUG_TIMING): per-warp phase time stamps
 };
+
+// Phase time stamps of the first 32 frames of every warp: dbg[((block*8 + warp)*32 + it)*16 + i] = clock64,
+// and the SM id of each block behind them (tools/phase_timing.py reads the dump).
+#ifdef TDSA_DEBUG_TIMING
+#define TDSA_STAMP(i)                                                                                         \
+  do {                                                                                                        \
+    if ((threadIdx.x & 31) == 0 && a.dbg != nullptr && it < 32 && blockDim.x == 256) {                        \
+      long long c_;                                                                                           \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_)::"memory");                                            \
+      a.dbg[(((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32 + it) * 16 + (i)] = c_;                      \
+    }                                                                                                         \
+  } while (0)
+#else
+#define TDSA_STAMP(i) do {} while (0)
+#endif
 
 // ---- named barriers (ids 1..4; id 0 is __syncthreads) ---------------------------------------
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
@@ -588,6 +605,10 @@ fft_fused_kernel(const FftArgs<T> a) {
     if (g == 1) bar_arrive(3, 2 * TH);                           // group 0 owns the first compute phase
   }
   const bool mag20 = a.ep.mode == kModeMag20;
+  if (a.stagger > 0 && blockIdx.x >= gridDim.x / 2) {
+    const long long c0 = clock64();
+    while (clock64() - c0 < a.stagger) {}
+  }
 
   // Both groups run the same number of iterations so that the token hand-offs always pair up;
   // a group without a frame in the last iteration only passes the token on.
@@ -603,6 +624,13 @@ fft_fused_kernel(const FftArgs<T> a) {
       continue;
     }
     T re[PP], im[PP];
+#ifdef TDSA_DEBUG_TIMING
+    if (it == 0 && threadIdx.x == 0 && a.dbg != nullptr) {
+      unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      a.dbg[(int64_t)gridDim.x * 8 * 32 * 16 + blockIdx.x] = smid;
+    }
+#endif
+    TDSA_STAMP(0);
     // ---- pass 0: global/staged -> registers, window, full-radix DFT (no twiddles) -------------
     if constexpr (TAIL != 0) {
       const CT* src = a.in_ct + f * N + t;
@@ -623,6 +651,7 @@ fft_fused_kernel(const FftArgs<T> a) {
         if (it < NSTAGE)
 #endif
         mbar_wait(bar_u32 + 8 * stg, (uint32_t)((it / NSTAGE) & 1));
+        TDSA_STAMP(1);
         const float2* src = stage0 + (size_t)stg * N + t;
 #pragma unroll
         for (int j = 0; j < PP; ++j) v[j] = src[j * TH];
@@ -666,12 +695,15 @@ fft_fused_kernel(const FftArgs<T> a) {
       }
     }
     release();
+    TDSA_STAMP(2);
     {
       const int pb = P::phys(t);
 #pragma unroll
       for (int q = 0; q < PP; ++q) ex[pb + P::phys(q * TH)] = mk<T>(re[q], im[q]);
     }
+    TDSA_STAMP(3);
     group_sync();
+    TDSA_STAMP(4);
     if constexpr (NSTAGE > 0) {
       // every thread of the group has consumed this stage (its reads precede the barrier): refill it
 #if !defined(TDSA_DEBUG_SKIP_MEM) && !defined(TDSA_DEBUG_SKIP_LOAD)
@@ -716,9 +748,12 @@ fft_fused_kernel(const FftArgs<T> a) {
         for (int q = 1; q < PP; ++q) { const CT w = twi_[q * S + c]; cmul<T>(re[q], im[q], w.x, w.y); }
       }
       release();
+      TDSA_STAMP(5);
 #pragma unroll
       for (int q = 0; q < PP; ++q) ex[pb + P::phys(q * S)] = mk<T>(re[q], im[q]);
+      TDSA_STAMP(6);
       group_sync();
+      TDSA_STAMP(7);
     }
     // ---- last pass: radix R, NB butterflies per thread, digit-reversed reads, pre-twiddled ------
 #pragma unroll
@@ -774,9 +809,12 @@ fft_fused_kernel(const FftArgs<T> a) {
         }
       }
     };
+    TDSA_STAMP(8);
     if (mag20) emit(std::true_type{}); else emit(std::false_type{});
     release();
+    TDSA_STAMP(9);
     group_sync();   // exchange buffer is reused by the next frame's pass 0
+    TDSA_STAMP(10);
   }
 }
 

@@ -2,10 +2,14 @@
 #pragma once
 #include <stdlib.h>
 
+#include <stdio.h>
+
 #include <algorithm>
+#include <vector>
 #include <atomic>
 
 #include "tdsa_fft.cuh"
+#include "tdsa_fft_wl.cuh"
 
 namespace tdsa {
 
@@ -85,7 +89,9 @@ cudaError_t launch_final(const FftArgs<T>& a, int sm_count, cudaStream_t stream,
   using P = Plan<T, LOG2N, LOGR>;
   constexpr int kGroups = (LOGR == 4) ? pick_groups<T, LOG2N, TAIL>() : 1;
   constexpr size_t kSmemGroup = ((NSTAGE > 0 ? P::smem_staged(NSTAGE) : P::SMEM_BYTES) + 127) & ~(size_t)127;
-  constexpr size_t kSmem = kSmemGroup * kGroups;
+  // diagnostic: TDSA_DEBUG_EXTRA_SMEM=<bytes> pads the dynamic shared memory to force fewer CTAs per SM
+  static const size_t kExtraSmem = [] { const char* e = getenv("TDSA_DEBUG_EXTRA_SMEM"); return e ? (size_t)atol(e) : (size_t)0; }();
+  const size_t kSmem = std::min<size_t>(kSmemGroup * kGroups + kExtraSmem, 227 * 1024);
   constexpr int kThreads = P::THREADS * kGroups;
   // float32: window and pass-0 twiddles stay in registers across frames; float64 keeps base twiddles
   // and forms the rest; CTAs of more than 512 threads read the tables (64-register budget).
@@ -108,6 +114,19 @@ cudaError_t launch_final(const FftArgs<T>& a, int sm_count, cudaStream_t stream,
     info->stages = NSTAGE; info->logr = LOGR;
   }
   if (dry || a.n_frames <= 0) return cudaSuccess;
+  static const int kStagger = [] { const char* e = getenv("TDSA_DEBUG_STAGGER"); return e ? atoi(e) : 0; }();
+  FftArgs<T> b = a;
+  b.stagger = kStagger;
+#ifdef TDSA_DEBUG_TIMING
+  static long long* d_dbg = nullptr;
+  const size_t dbg_count = (size_t)grid * 8 * 32 * 16 + grid;
+  const char* dbg_path = getenv("TDSA_DEBUG_TIMING_OUT");
+  if (dbg_path && kThreads == 256 && LOG2N == 12 && TAIL == 0) {
+    if (!d_dbg) cudaMalloc(&d_dbg, sizeof(long long) * ((size_t)1024 * 8 * 32 * 16 + 1024));
+    cudaMemsetAsync(d_dbg, 0, sizeof(long long) * dbg_count, stream);
+    b.dbg = d_dbg;
+  }
+#endif
 #if TDSA_PDL
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmem; cfg.stream = stream;
@@ -115,12 +134,22 @@ cudaError_t launch_final(const FftArgs<T>& a, int sm_count, cudaStream_t stream,
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, b);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   return le != cudaSuccess ? le : cudaGetLastError();
 #else
-  kern<<<grid, kThreads, kSmem, stream>>>(a);
+  kern<<<grid, kThreads, kSmem, stream>>>(b);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
+#ifdef TDSA_DEBUG_TIMING
+  if (b.dbg) {
+    cudaStreamSynchronize(stream);
+    std::vector<long long> h(dbg_count);
+    cudaMemcpy(h.data(), d_dbg, sizeof(long long) * dbg_count, cudaMemcpyDeviceToHost);
+    char path[512];
+    snprintf(path, sizeof path, "%s_%s_g%d.bin", dbg_path, sizeof(T) == 4 ? "f32" : "f64", grid);
+    if (FILE* fp = fopen(path, "wb")) { fwrite(h.data(), sizeof(long long), dbg_count, fp); fclose(fp); }
+  }
+#endif
   return cudaGetLastError();
 #endif
 }
@@ -201,6 +230,89 @@ cudaError_t launch_fft_impl(int log2n, int epi, const FftArgs<T>& a, int sm, cud
 template <typename T> int effective_logr(int log2n) {
   return (log2n >= kMinLog2R8 && log2n <= kMaxLog2R8 && runtime_logr<T>() == 3) ? 3 : 4;
 }
+
+// ---- warp-local 4096-point kernel (tdsa_fft_wl.cuh) ----------------------------------------------------
+#ifndef TDSA_WL_STAGES_F32
+#define TDSA_WL_STAGES_F32 2
+#endif
+#ifndef TDSA_WL_STAGES_F64
+#define TDSA_WL_STAGES_F64 1
+#endif
+
+// lane -> (sub-transform r, team lane c) of fft_wl_kernel; the host permutes the window with the same map
+inline void wl_thread_identity(int tid, int* r, int* c) {
+  const int w = tid >> 5, l = tid & 31;
+  *r = 2 * w + ((l >> 3) & 1);
+  *c = (l & 7) + 8 * (l >> 4);
+}
+
+template <typename T, typename Epi, bool HAS_DC>
+cudaError_t launch_wl_final(const FftArgs<T>& a, const CUtensorMap& tmap, const T* wperm, WlSched sched, int sm_count,
+                            cudaStream_t stream, LaunchInfo* info, bool dry) {
+  constexpr int kStages = sizeof(T) == 4 ? TDSA_WL_STAGES_F32 : TDSA_WL_STAGES_F64;
+  constexpr int kTwMode = sizeof(T) == 4 ? TDSA_F32_TWMODE : TDSA_F64_TWMODE;
+  static const size_t kExtraSmem = [] { const char* e = getenv("TDSA_DEBUG_EXTRA_SMEM"); return e ? (size_t)atol(e) : (size_t)0; }();
+  const size_t kSmem = std::min<size_t>(WlPlan<T>::smem_bytes(kStages) + kExtraSmem, 227 * 1024);
+  auto kern = fft_wl_kernel<T, Epi, kTwMode, kStages, HAS_DC, 2>;
+  static int occ = -1;
+  if (occ < 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    if (e != cudaSuccess) return e;
+    int o = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, 256, kSmem);
+    if (e != cudaSuccess) return e;
+    occ = std::max(o, 1);
+  }
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.n_frames, (int64_t)sm_count * occ));
+  if (info) {
+    info->threads = 256; info->smem = (int)kSmem; info->ctas_per_sm = occ; info->grid = grid;
+    info->stages = kStages; info->logr = 4;
+  }
+  if (dry || a.n_frames <= 0) return cudaSuccess;
+  FftArgs<T> b = a;
+#ifdef TDSA_DEBUG_TIMING
+  static long long* d_dbg = nullptr;
+  const size_t dbg_count = (size_t)grid * 8 * 32 * 16 + grid;
+  const char* dbg_path = getenv("TDSA_DEBUG_TIMING_OUT");
+  if (dbg_path) {
+    if (!d_dbg) cudaMalloc(&d_dbg, sizeof(long long) * ((size_t)1024 * 8 * 32 * 16 + 1024));
+    cudaMemsetAsync(d_dbg, 0, sizeof(long long) * dbg_count, stream);
+    b.dbg = d_dbg;
+  }
+#endif
+  kern<<<grid, 256, kSmem, stream>>>(b, tmap, wperm, sched);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+#ifdef TDSA_DEBUG_TIMING
+  if (b.dbg) {
+    cudaStreamSynchronize(stream);
+    std::vector<long long> h(dbg_count);
+    cudaMemcpy(h.data(), d_dbg, sizeof(long long) * dbg_count, cudaMemcpyDeviceToHost);
+    char path[512];
+    snprintf(path, sizeof path, "%s_wl_%s_g%d.bin", dbg_path, sizeof(T) == 4 ? "f32" : "f64", grid);
+    if (FILE* fp = fopen(path, "wb")) { fwrite(h.data(), sizeof(long long), dbg_count, fp); fclose(fp); }
+  }
+#endif
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_wl_impl(int epi, const FftArgs<T>& a, const CUtensorMap& tmap, const T* wperm, WlSched sched, int sm,
+                           cudaStream_t s, LaunchInfo* info, bool dry) {
+  const bool dc = a.dc != nullptr;
+  if (epi == kEpiDb) {
+    return dc ? launch_wl_final<T, EpiDb, true>(a, tmap, wperm, sched, sm, s, info, dry)
+              : launch_wl_final<T, EpiDb, false>(a, tmap, wperm, sched, sm, s, info, dry);
+  }
+  if (epi == kEpiLinear) {
+    return dc ? launch_wl_final<T, EpiLinear, true>(a, tmap, wperm, sched, sm, s, info, dry)
+              : launch_wl_final<T, EpiLinear, false>(a, tmap, wperm, sched, sm, s, info, dry);
+  }
+  return cudaErrorInvalidValue;
+}
+cudaError_t launch_wl_f32(int epi, const FftArgs<float>& a, const CUtensorMap& tmap, const float* wperm, WlSched sched,
+                          int sm, cudaStream_t s, LaunchInfo* info, bool dry);
+cudaError_t launch_wl_f64(int epi, const FftArgs<double>& a, const CUtensorMap& tmap, const double* wperm, WlSched sched,
+                          int sm, cudaStream_t s, LaunchInfo* info, bool dry);
 
 // defined in tdsa_fft_f32.cu / tdsa_fft_f64.cu
 cudaError_t launch_fft_f32(int log2n, int epi, const FftArgs<float>& a, int sm, cudaStream_t s, LaunchInfo* info, bool dry);

@@ -3,6 +3,7 @@
 //      does it take to fill the FP64 / FP32 pipe?
 //   B: the shared-memory exchange alone (16 stores, barrier, 16 loads per thread) at 1 and 2 CTAs per SM.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I topdogspectrumanalyser_b200/csrc tools/ubench.cu -o tools/bin/ubench
+#include <algorithm>
 #include <cstdio>
 #include <vector>
 
@@ -76,6 +77,132 @@ __global__ void __launch_bounds__(256, 2) k_exch(T* out, long long* cyc) {
   if (t == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// C: do FP sections and shared-memory traffic of DIFFERENT warps overlap?  512 threads: warps 0-7 run the register-only
+// radix-16 loop, warps 8-15 run the warp-local exchange loop (mode 3), or only one half works (modes 1, 2).
+template <typename T, int ITER>
+__global__ void __launch_bounds__(512, 1) k_mix(T* out, long long* cyc, int mode) {
+  using CT = typename CplxOf<T>::type;
+  extern __shared__ __align__(128) unsigned char sm[];
+  CT* ex = reinterpret_cast<CT*>(sm);
+  const int t = threadIdx.x, half = t >> 8, tt = t & 255;
+  T re[16], im[16], wr[16], wi[16], br[4], bi[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { br[j] = T(0.05) + T(1e-4) * T((t + j) & 7); bi[j] = T(0.03) + T(1e-3) * T(j); }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { re[j] = T(t + j) * T(1e-3); im[j] = T(j) * T(2e-3); wr[j] = br[j & 3]; wi[j] = bi[j & 3]; }
+  __syncthreads();
+  const long long t0 = clock64();
+  if (half == 0) {
+    if (mode & 1) {
+#pragma unroll 1
+      for (int it = 0; it < ITER; ++it) dft16_pretw<T>(re, im, wr, wi);
+    }
+  } else {
+    if (mode & 2) {
+      const int c = tt & 15, s = tt >> 4;
+      CT* my = ex + s * (17 * 16);
+#pragma unroll 1
+      for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) my[c * 17 + q] = mk<T>(re[q], im[q]);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { CT x = my[j * 17 + c]; re[j] += x.x; im[j] += x.y; }
+        __syncwarp();
+      }
+    }
+  }
+  const long long t1 = clock64();
+  T sacc = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) sacc += re[j] + im[j];
+  out[blockIdx.x * blockDim.x + t] = sacc;
+  if ((t & 31) == 0) cyc[blockIdx.x * 16 + (t >> 5)] = t1 - t0;
+}
+
+template <typename T> void run_mix(const char* name) {
+  constexpr int ITER = 64;
+  T* out; long long* cyc;
+  cudaMalloc(&out, sizeof(T) * 148 * 512);
+  cudaMalloc(&cyc, sizeof(long long) * 148 * 16);
+  const size_t smem = (size_t)16 * 17 * 16 * 2 * sizeof(T) + 1024;
+  auto kern = k_mix<T, ITER>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  for (int mode = 1; mode <= 3; ++mode) {
+    kern<<<148, 512, smem>>>(out, cyc, mode);
+    cudaDeviceSynchronize();
+    kern<<<148, 512, smem>>>(out, cyc, mode);
+    cudaError_t e = cudaDeviceSynchronize();
+    std::vector<long long> h(148 * 16);
+    cudaMemcpy(h.data(), cyc, sizeof(long long) * 148 * 16, cudaMemcpyDeviceToHost);
+    double fp = 0, ex = 0;
+    for (int b = 0; b < 148; ++b) {
+      long long mf = 0, mx = 0;
+      for (int w = 0; w < 8; ++w) { mf = std::max(mf, h[b * 16 + w]); mx = std::max(mx, h[b * 16 + 8 + w]); }
+      fp += (double)mf; ex += (double)mx;
+    }
+    printf("C %s mode %d (%s): FP warps %.0f cycles per radix-16 (8 warps, slowest), exchange warps %.0f cycles per exchange (%s)\n", name, mode,
+           mode == 1 ? "FP only" : mode == 2 ? "exchange only" : "both", fp / 148 / ITER, ex / 148 / ITER, cudaGetErrorString(e));
+  }
+  cudaFree(out); cudaFree(cyc);
+}
+
+// D: what do float<->double conversions and MUFU cost next to FP64 work?  One radix-16 (192 FP64 ops) per iteration plus
+// 32 DADDs whose operands are (0) doubles, (1) converted floats (32 F2F.F64.F32), (2) as 0 plus 16 F2F.F32.F64 + 16 MUFU.LG2.
+template <int MODE, int ITER>
+__global__ void __launch_bounds__(512, 1) k_cvt(double* out, long long* cyc) {
+  double re[16], im[16], wr[16], wi[16], br[4], bi[4];
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { br[j] = 0.05 + 1e-4 * ((threadIdx.x + j) & 7); bi[j] = 0.03 + 1e-3 * j; }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { re[j] = (threadIdx.x + j) * 1e-3; im[j] = j * 2e-3; wr[j] = br[j & 3]; wi[j] = bi[j & 3]; }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = 1e-3f * (float)(threadIdx.x + j);
+  float facc = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (MODE == 1) { re[j] += (double)v[j]; im[j] += (double)v[16 + j]; }
+      else { re[j] += wr[(j + 1) & 15]; im[j] += wi[(j + 1) & 15]; }
+    }
+    dft16_pretw<double>(re, im, wr, wi);
+    if (MODE == 2) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) facc += lg2_approx((float)re[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += 1.0f;
+  }
+  const long long t1 = clock64();
+  double s = facc;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += re[j] + im[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int MODE> void run_cvt(const char* what) {
+  constexpr int ITER = 64;
+  double* out; long long* cyc;
+  cudaMalloc(&out, sizeof(double) * 148 * 512);
+  cudaMalloc(&cyc, sizeof(long long) * 148);
+  for (int wps = 1; wps <= 2; ++wps) {
+    k_cvt<MODE, ITER><<<148, 128 * wps>>>(out, cyc);
+    cudaDeviceSynchronize();
+    k_cvt<MODE, ITER><<<148, 128 * wps>>>(out, cyc);
+    cudaError_t e = cudaDeviceSynchronize();
+    std::vector<long long> h(148);
+    cudaMemcpy(h.data(), cyc, sizeof(long long) * 148, cudaMemcpyDeviceToHost);
+    double avg = 0; for (auto v : h) avg += (double)v; avg /= 148;
+    printf("D %s: %d warps/SMSP: %.0f cycles per iteration per warp (%s)\n", what, wps, avg / ITER, cudaGetErrorString(e));
+  }
+  cudaFree(out); cudaFree(cyc);
+}
+
 template <typename T> void run_dft(const char* name) {
   constexpr int ITER = 64;
   T* out; long long* cyc;
@@ -120,6 +247,11 @@ template <typename T, bool WL> void run_exch(const char* name) {
 }
 
 int main() {
+  run_cvt<0>("radix-16 + 32 DADD (224 FP64 ops)");
+  run_cvt<1>("same + 32 F2F.F64.F32");
+  run_cvt<2>("same as first + 16 F2F.F32.F64 + 16 MUFU.LG2");
+  run_mix<double>("f64");
+  run_mix<float>("f32");
   run_dft<double>("f64");
   run_dft<float>("f32");
   run_exch<double, false>("f64");

@@ -164,6 +164,14 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+// Dynamic frame scheduling inside fft_fused_kernel: measured (r01 experiments) 149.5 -> 139.3 us for float64 N=4096 but
+// 69.6 -> 75.8 us for float32 N=1024 (more, shorter iterations per CTA), so it is opt-in (TDSA_DYNAMIC=1); N=4096
+// takes the warp-local kernel, which always schedules dynamically.
+static bool dyn_enabled() {
+  static const bool on = [] { const char* e = getenv("TDSA_DYNAMIC"); return e && e[0] == '1'; }();
+  return on;
+}
+
 static bool wl_enabled() {
   static const bool on = [] { const char* e = getenv("TDSA_WL"); return !(e && e[0] == '0'); }();
   return on;
@@ -171,7 +179,7 @@ static bool wl_enabled() {
 
 // true when this batch can take the warp-local kernel; fills p->tmap
 static bool wl_prepare(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t stride, int epi) {
-  if (!wl_enabled() || p->log2n != 12 || !p->d_sched || (epi != kEpiDb && epi != kEpiLinear)) return false;
+  if (!wl_enabled() || p->log2n != 12 || !p->d_wperm64 || (epi != kEpiDb && epi != kEpiLinear)) return false;
   if (((uintptr_t)iq & 15) != 0 || (stride & 1) != 0 || stride <= 0 || n_frames <= 0 || n_frames >= (1 << 30)) return false;
   if (p->tmap_ptr == iq && p->tmap_frames == n_frames && p->tmap_stride == stride) return true;
   EncodeTiledFn enc = encode_tiled_fn();
@@ -303,19 +311,21 @@ static int run_fused(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t str
   if (is_big(p)) return run_big(p, iq, n_frames, stride, dc, epi, db, lin, info, dry);
   cudaError_t e;
   // dry runs (launch geometry queries) describe the warp-local kernel whenever the size has one
-  const bool wl = dry ? (wl_enabled() && p->log2n == 12 && p->d_sched && (epi == kEpiDb || epi == kEpiLinear) && encode_tiled_fn())
+  const bool wl = dry ? (wl_enabled() && p->log2n == 12 && p->d_wperm64 && (epi == kEpiDb || epi == kEpiLinear) && encode_tiled_fn())
                       : wl_prepare(p, iq, n_frames, stride, epi);
   const WlSched sched{p->d_sched, p->d_sched ? p->d_sched + 1 : nullptr};
   if (p->precision == TDSA_PREC_F32) {
     FftArgs<float> a;
     a.iq = (const float2*)iq; a.n_frames = n_frames; a.frame_stride = stride;
     a.window = p->d_win32; a.tw = p->d_tw32; a.dc = dc; a.in_ct = nullptr; a.ep = make_epi(p, db, lin);
+    a.sched = (dyn_enabled() && n_frames < (1 << 30)) ? p->d_sched : nullptr;
     e = wl ? launch_wl_f32(epi, a, p->tmap, p->d_wperm32, sched, p->sm_count, p->stream, info, dry)
            : launch_fft_f32(p->log2n, epi, a, p->sm_count, p->stream, info, dry);
   } else {
     FftArgs<double> a;
     a.iq = (const float2*)iq; a.n_frames = n_frames; a.frame_stride = stride;
     a.window = p->d_win64; a.tw = p->d_tw64; a.dc = dc; a.in_ct = nullptr; a.ep = make_epi(p, db, lin);
+    a.sched = (dyn_enabled() && n_frames < (1 << 30)) ? p->d_sched : nullptr;
     e = wl ? launch_wl_f64(epi, a, p->tmap, p->d_wperm64, sched, p->sm_count, p->stream, info, dry)
            : launch_fft_f64(p->log2n, epi, a, p->sm_count, p->stream, info, dry);
   }
@@ -358,11 +368,11 @@ int tdsa_create(int n_fft, int window_id, int window_norm, int mode, double log_
         cudaMalloc(&p->d_win32, sizeof(float) * n_fft) != cudaSuccess) { rc = fail(TDSA_ERR_NOMEM, "window alloc failed"); break; }
     rc = upload_twiddles(p->log2n, effective_logr_f64(p->log2n), effective_logr_f32(p->log2n), &p->d_tw64, &p->d_tw32);
     if (rc) break;
+    if (cudaMalloc(&p->d_sched, 2 * sizeof(int)) != cudaSuccess ||
+        cudaMemset(p->d_sched, 0, 2 * sizeof(int)) != cudaSuccess) { rc = fail(TDSA_ERR_NOMEM, "scheduler alloc failed"); break; }
     if (p->log2n == 12 && effective_logr_f64(12) == 4 && effective_logr_f32(12) == 4) {   // warp-local kernel tables
       if (cudaMalloc(&p->d_wperm64, sizeof(double) * n_fft) != cudaSuccess ||
-          cudaMalloc(&p->d_wperm32, sizeof(float) * n_fft) != cudaSuccess ||
-          cudaMalloc(&p->d_sched, 2 * sizeof(int)) != cudaSuccess ||
-          cudaMemset(p->d_sched, 0, 2 * sizeof(int)) != cudaSuccess) { rc = fail(TDSA_ERR_NOMEM, "warp-local tables alloc failed"); break; }
+          cudaMalloc(&p->d_wperm32, sizeof(float) * n_fft) != cudaSuccess) { rc = fail(TDSA_ERR_NOMEM, "warp-local tables alloc failed"); break; }
     }
     if (p->log2n > MaxLog2<float>::value || p->log2n > MaxLog2<double>::value) {
       // tables for the inner (N/256)-point transform of the two-kernel path

@@ -98,6 +98,26 @@ __device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcon
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// float -> T.  For T = double the hardware conversion (F2F.F64.F32) runs on the FP64 pipe at about four pipe cycles
+// per warp instruction (tools/ubench.cu, test D): 32 of them per thread and frame are ~9 % of the pipe's work.
+// widen_fast does the same job on the integer pipe: exact for every normal float; zero and denormals come out as
+// +-2^-127 * (1 + m) (absolute error < 1.2e-38, far below the log floor); Inf/NaN do NOT survive, so the caller
+// tracks them separately (see frame_special) and redoes the frame's conversion with the hardware path if any appear.
+#ifndef TDSA_INT_WIDEN
+#define TDSA_INT_WIDEN 0   // measured: 141.4 us with the integer path vs 135.7 us with F2F (extra instructions and spills cost more than the pipe time saved)
+#endif
+template <typename T> __device__ __forceinline__ T widen_fast(float x);
+template <> __device__ __forceinline__ float widen_fast<float>(float x) { return x; }
+template <> __device__ __forceinline__ double widen_fast<double>(float x) {
+#if TDSA_INT_WIDEN
+  const uint32_t u = __float_as_uint(x);
+  const uint32_t hi = ((u >> 3) & 0x0fffffffu) + 0x38000000u + (u & 0x80000000u);
+  return __hiloint2double((int)hi, (int)(u << 29));
+#else
+  return (double)x;
+#endif
+}
+
 template <typename T> __device__ __forceinline__ void cmul(T& xr, T& xi, T wr, T wi) {
   T r = xr * wr - xi * wi;
   T i = xr * wi + xi * wr;
@@ -453,6 +473,7 @@ template <typename T> struct FftArgs {
   const double2* dc;           // optional per-frame DC estimate to subtract (hackrf path) or nullptr
   const typename CplxOf<T>::type* in_ct;   // TAIL kernels: complex T input [n_frames][N] (no window)
   EpiParams ep;
+  int* sched = nullptr;        // dynamic frame scheduling: {next unclaimed frame, CTAs that have left}; nullptr = static
   int stagger = 0;             // diagnostic (TDSA_DEBUG_STAGGER): cycles the second half of the grid waits before its first frame
   long long* dbg = nullptr;    // diagnostic (-DTDSA_DEBUG_TIMING): per-warp phase time stamps
 };
@@ -582,11 +603,18 @@ fft_fused_kernel(const FftArgs<T> a) {
 #if TDSA_PDL
   pdl_wait_prior_grid();            // everything above only touched plan tables; frame data may come from the prior grid
 #endif
+  // Dynamic scheduling (staged single-group kernels with a scheduler): frame indices come from a global counter,
+  // so the faster of the CTAs sharing an SM takes more frames instead of idling at the end; slot[s] holds the
+  // frame that stage s carries.  The index for a refill is claimed one iteration ahead (no wait on the atomic).
+  const bool dyn = NSTAGE > 0 && GROUPS == 1 && a.sched != nullptr;
+  volatile int* slot = reinterpret_cast<volatile int*>(smem_raw + P::STAGE_OFFSET + (size_t)NSTAGE * P::STAGE_BYTES + 32);
+  (void)slot;
   if constexpr (NSTAGE > 0) {
     if (t == 0) {
 #pragma unroll
       for (int s = 0; s < NSTAGE; ++s) {
-        const int64_t fs = unit + (int64_t)s * unit_stride;
+        const int64_t fs = dyn ? (int64_t)atomicAdd(a.sched, 1) : unit + (int64_t)s * unit_stride;
+        if (dyn) slot[s] = (int)fs;
         if (fs < a.n_frames) {
           mbar_arrive_expect_tx(bar_u32 + 8 * s, (uint32_t)P::STAGE_BYTES);
           bulk_g2s(stage_u32 + (uint32_t)(s * P::STAGE_BYTES), a.iq + fs * a.frame_stride, (uint32_t)P::STAGE_BYTES,
@@ -613,11 +641,21 @@ fft_fused_kernel(const FftArgs<T> a) {
   // Both groups run the same number of iterations so that the token hand-offs always pair up;
   // a group without a frame in the last iteration only passes the token on.
   const int64_t first_unit = (int64_t)blockIdx.x * GROUPS;
-  const int64_t iters = first_unit < a.n_frames ? (a.n_frames - first_unit + unit_stride - 1) / unit_stride : 0;
+  const int64_t iters = dyn ? ((int64_t)1 << 40)
+                            : (first_unit < a.n_frames ? (a.n_frames - first_unit + unit_stride - 1) / unit_stride : 0);
 
   for (int64_t it64 = 0; it64 < iters; ++it64) {
     const int it = (int)it64;
-    const int64_t f = unit + it64 * unit_stride;
+    int64_t f = unit + it64 * unit_stride;
+    int fnext = 0;
+    if constexpr (NSTAGE > 0) {
+      if (dyn) {
+        f = slot[it % NSTAGE];
+        if (f >= a.n_frames) break;
+        if (t == 0) fnext = atomicAdd(a.sched, 1);           // consumed at the refill below
+      }
+    }
+    (void)fnext;
     if (GROUPS > 1 && f >= a.n_frames) {
 #pragma unroll
       for (int ph = 0; ph < NPASS; ++ph) { acquire(); release(); }
@@ -708,7 +746,8 @@ fft_fused_kernel(const FftArgs<T> a) {
       // every thread of the group has consumed this stage (its reads precede the barrier): refill it
 #if !defined(TDSA_DEBUG_SKIP_MEM) && !defined(TDSA_DEBUG_SKIP_LOAD)
       if (t == 0) {
-        const int64_t fn = f + (int64_t)NSTAGE * unit_stride;
+        const int64_t fn = dyn ? (int64_t)fnext : f + (int64_t)NSTAGE * unit_stride;
+        if (dyn) slot[it % NSTAGE] = fnext;
         if (fn < a.n_frames) {
           const int stg = it % NSTAGE;
           fence_proxy_async();
@@ -815,6 +854,12 @@ fft_fused_kernel(const FftArgs<T> a) {
     TDSA_STAMP(9);
     group_sync();   // exchange buffer is reused by the next frame's pass 0
     TDSA_STAMP(10);
+  }
+  if constexpr (NSTAGE > 0 && GROUPS == 1) {
+    if (dyn && t == 0) {                                     // the last CTA out re-arms the scheduler for the next launch
+      __threadfence();
+      if (atomicAdd(a.sched + 1, 1) == (int)gridDim.x - 1) { a.sched[0] = 0; a.sched[1] = 0; __threadfence(); }
+    }
   }
 }
 

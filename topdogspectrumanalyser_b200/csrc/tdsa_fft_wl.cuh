@@ -33,7 +33,7 @@ template <typename T> struct WlPlan {
   static constexpr size_t EX_BYTES = (size_t)(EX_ELEMS + TW_SMEM) * 2 * sizeof(T);
   static constexpr size_t STAGE_BYTES = (size_t)N * 8;
   static constexpr size_t CTRL_BYTES = 128;                           // mbarriers + frame slots
-  static constexpr size_t smem_bytes(int nstage) {
+  static __host__ __device__ constexpr size_t smem_bytes(int nstage) {
     return ((EX_BYTES + CTRL_BYTES + 1023) & ~(size_t)1023) + 1024 + (size_t)nstage * STAGE_BYTES;
   }
 };
@@ -45,12 +45,19 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap
       : "memory");
 }
 
+// L2 prefetch of one frame through the tensor map (no shared-memory destination, no completion)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1),
+               "r"(c2)
+               : "memory");
+}
+
 struct WlSched {
   int* next;       // next unclaimed frame
   int* done;       // CTAs that have left the frame loop
 };
 
-template <typename T, typename Epi, int TWMODE, int NSTAGE, bool HAS_DC, int MIN_CTAS>
+template <typename T, typename Epi, int TWMODE, int NSTAGE, bool HAS_DC, int MIN_CTAS, bool L2_AHEAD>
 __global__ void __launch_bounds__(256, MIN_CTAS)
 fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, const T* __restrict__ wperm, WlSched sched) {
   using W = WlPlan<T>;
@@ -97,6 +104,7 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
   }
 
   // claim the first NSTAGE frames and start their copies
+  int pend = 0;                                             // thread 0: frame claimed one refill ahead (L2_AHEAD)
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s) {
@@ -106,6 +114,10 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
         mbar_arrive_expect_tx(ctrl_u32 + 8 * s, (uint32_t)W::STAGE_BYTES);
         tma_load_3d(stage_u32 + (uint32_t)(s * W::STAGE_BYTES), &tmap, 0, 0, fs, ctrl_u32 + 8 * s);
       }
+    }
+    if constexpr (L2_AHEAD) {                               // the frame after those: claimed now, copied one iteration later
+      pend = atomicAdd(sched.next, 1);
+      if (pend < a.n_frames) tma_prefetch_3d(&tmap, 0, 0, pend);
     }
   }
   __syncthreads();
@@ -140,10 +152,28 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       float2 v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(src + j * 2048);
+      if constexpr (sizeof(T) == 8 && TDSA_INT_WIDEN) {
+        // integer-pipe widening; x * 0 is NaN exactly for Inf/NaN inputs, accumulated on the idle FP32 pipe
+        float special = 0.0f;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if constexpr (HAS_DC) { re[j] = (T)v[j].x - dcr; im[j] = (T)v[j].y - dci; }
-        else { re[j] = (T)v[j].x; im[j] = (T)v[j].y; }
+        for (int j = 0; j < 16; ++j) special = __fmaf_rn(v[j].x, 0.0f, __fmaf_rn(v[j].y, 0.0f, special));
+        if (special != special) {                            // rare: hardware conversion keeps Inf/NaN
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { re[j] = (T)v[j].x; im[j] = (T)v[j].y; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { re[j] = widen_fast<T>(v[j].x); im[j] = widen_fast<T>(v[j].y); }
+        }
+        if constexpr (HAS_DC) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { re[j] -= dcr; im[j] -= dci; }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if constexpr (HAS_DC) { re[j] = (T)v[j].x - dcr; im[j] = (T)v[j].y - dci; }
+          else { re[j] = (T)v[j].x; im[j] = (T)v[j].y; }
+        }
       }
       dft16_win<T>(re, im, win);
     }
@@ -174,11 +204,17 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     __syncthreads();                                         // all sixteen Y_r complete; every warp has left this stage
     TDSA_STAMP(6);
     if (tid == 0) {
-      slot[stg] = fnext;
-      if (fnext < a.n_frames) {
+      // L2_AHEAD: copy the frame claimed (and prefetched into L2) one iteration ago, prefetch the one claimed now
+      const int fcopy = L2_AHEAD ? pend : fnext;
+      slot[stg] = fcopy;
+      if (fcopy < a.n_frames) {
         fence_proxy_async();
         mbar_arrive_expect_tx(ctrl_u32 + 8 * stg, (uint32_t)W::STAGE_BYTES);
-        tma_load_3d(stage_u32 + (uint32_t)(stg * W::STAGE_BYTES), &tmap, 0, 0, fnext, ctrl_u32 + 8 * stg);
+        tma_load_3d(stage_u32 + (uint32_t)(stg * W::STAGE_BYTES), &tmap, 0, 0, fcopy, ctrl_u32 + 8 * stg);
+      }
+      if constexpr (L2_AHEAD) {
+        pend = fnext;
+        if (pend < a.n_frames) tma_prefetch_3d(&tmap, 0, 0, pend);
       }
     }
     // ---- last pass: thread kk = tid reads Y_j[kk], pre-twiddle W4096^(j kk), radix 16 over j ----------------
@@ -222,6 +258,200 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       *sched.done = 0;
       __threadfence();
     }
+  }
+}
+
+#ifdef TDSA_DEBUG_TIMING
+#define TDSA_STAMP_PP(i)                                                                                      \
+  do {                                                                                                        \
+    if (l == 0 && a.dbg != nullptr && it < 32) {                                                              \
+      long long c_;                                                                                           \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_)::"memory");                                            \
+      a.dbg[((((int64_t)blockIdx.x * 2 + g) * 8 + w) * 32 + it) * 16 + (i)] = c_;                             \
+    }                                                                                                         \
+  } while (0)
+#else
+#define TDSA_STAMP_PP(i) do {} while (0)
+#endif
+// ---------------------------------------------------------------------------------------------------------------
+// Ping-pong variant: ONE 512-thread CTA per SM holding two independent frame engines (groups) of 256 threads, each
+// with its own exchange buffer, staging ring and mbarriers, exactly as fft_wl_kernel.  The two groups hand a
+// "math token" back and forth (a pair of named barriers): a group holds it only for its pure FP sections (pass A,
+// pass B, last pass + |X|^2); staged loads, float->double conversions, shared-memory exchanges, the CTA-wide
+// barriers, log2 and the global stores all run WITHOUT the token, i.e. while the other group owns the FP pipe.
+// Phase time stamps showed two co-resident CTAs colliding (both in FP sections, then both outside them); the token
+// forces the alternation.  Frames are dealt statically in pairs (all CTAs are alike with one CTA per SM):
+// iteration it of CTA b handles frames 2 (b + it * gridDim.x) + g.
+template <typename T, typename Epi, int TWMODE, int NSTAGE, bool HAS_DC>
+__global__ void __launch_bounds__(512, 1)
+fft_wlpp_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, const T* __restrict__ wperm) {
+  using W = WlPlan<T>;
+  using CT = typename CplxOf<T>::type;
+  constexpr int N = W::N, TH = W::TH, REGION = W::REGION;
+  constexpr size_t GROUP_BYTES = W::smem_bytes(NSTAGE);     // multiple of 1024
+  extern __shared__ __align__(1024) unsigned char smem_all[];
+  const int g = (int)threadIdx.x >> 8;
+  const int tid = (int)threadIdx.x & 255;
+  unsigned char* smem_raw = smem_all + (size_t)g * GROUP_BYTES;
+  CT* ex = reinterpret_cast<CT*>(smem_raw);
+  CT* tws = ex + W::EX_ELEMS;
+  const uint32_t base_u32 = smem_u32(smem_raw);
+  const uint32_t ctrl_u32 = base_u32 + (uint32_t)W::EX_BYTES;
+  const uint32_t stage_u32 = (base_u32 + (uint32_t)(W::EX_BYTES + W::CTRL_BYTES) + 1023u) & ~1023u;
+  const unsigned char* stage_ptr = smem_raw + (stage_u32 - base_u32);
+
+  const int w = tid >> 5, l = tid & 31;
+  const int h = (l >> 3) & 1, c = (l & 7) + 8 * (l >> 4);
+  const int r = 2 * w + h;
+  CT* reg = ex + r * REGION;
+
+  auto group_sync = [&]() { bar_sync(1 + g, TH); };
+  auto acquire = [&]() { bar_sync(3 + g, 2 * TH); };         // wait until the other group has released the token
+  auto release = [&]() { bar_arrive(3 + (1 - g), 2 * TH); }; // hand the token to the other group
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) mbar_init(ctrl_u32 + 8 * s, 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < W::TW_SMEM; i += TH) tws[i] = a.tw[i];
+
+  const CT* tw_last = a.tw + 256;
+  T win[16];
+  T twlr[16], twli[16];
+  if constexpr (TWMODE == 1) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) win[j] = wperm[j * TH + tid];
+#pragma unroll
+    for (int j = 1; j < 16; ++j) { const CT x = tw_last[j * 256 + tid]; twlr[j] = x.x; twli[j] = x.y; }
+  } else {
+#pragma unroll
+    for (int j = 1; j < 16; ++j) {
+      if (j < 4 || (j & 3) == 0) { const CT x = tw_last[j * 256 + tid]; twlr[j] = x.x; twli[j] = x.y; }
+    }
+  }
+
+  // both groups run the same number of iterations so that the token hand-offs pair up
+  const int64_t pairs = (a.n_frames + 1) / 2;
+  const int iters = (int64_t)blockIdx.x < pairs ? (int)((pairs - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  auto frame_of = [&](int it) -> int64_t { return 2 * ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) + g; };
+
+  __syncthreads();                                           // barriers initialised, tables staged
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+      const int64_t fs = frame_of(s);
+      if (s < iters && fs < a.n_frames) {
+        mbar_arrive_expect_tx(ctrl_u32 + 8 * s, (uint32_t)W::STAGE_BYTES);
+        tma_load_3d(stage_u32 + (uint32_t)(s * W::STAGE_BYTES), &tmap, 0, 0, (int)fs, ctrl_u32 + 8 * s);
+      }
+    }
+  }
+  if (g == 1) bar_arrive(3, 2 * TH);                         // group 0 owns the token first
+  const bool mag20 = a.ep.mode == kModeMag20;
+  const int stage_off = c * 128 + (((w ^ c) & 7) << 4) + h * 8;
+
+  for (int it = 0; it < iters; ++it) {
+    const int64_t f = frame_of(it);
+    if (f >= a.n_frames) {                                   // odd tail: keep the hand-offs paired
+#pragma unroll
+      for (int ph = 0; ph < 3; ++ph) { acquire(); release(); }
+      continue;
+    }
+    const int stg = it % NSTAGE;
+    T re[16], im[16];
+    TDSA_STAMP_PP(0);
+    // ---- no token: staged samples -> registers, conversion -------------------------------------------------
+    {
+      if constexpr (TWMODE != 1) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) win[j] = wperm[j * TH + tid];
+      }
+      T dcr = T(0), dci = T(0);
+      if constexpr (HAS_DC) { const double2 d = a.dc[f]; dcr = (T)d.x; dci = (T)d.y; }
+      mbar_wait(ctrl_u32 + 8 * stg, (uint32_t)((it / NSTAGE) & 1));
+      const unsigned char* src = stage_ptr + (size_t)stg * W::STAGE_BYTES + stage_off;
+      float2 v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(src + j * 2048);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if constexpr (HAS_DC) { re[j] = (T)v[j].x - dcr; im[j] = (T)v[j].y - dci; }
+        else { re[j] = (T)v[j].x; im[j] = (T)v[j].y; }
+      }
+    }
+    TDSA_STAMP_PP(1);
+    acquire();
+    TDSA_STAMP_PP(2);
+    dft16_win<T>(re, im, win);                               // pass A
+    release();
+    TDSA_STAMP_PP(3);
+    // ---- no token: team-local 16x16 transpose, pass-B operands ----------------------------------------------
+#pragma unroll
+    for (int q = 0; q < 16; ++q) reg[c + 17 * q] = mk<T>(re[q], im[q]);
+    __syncwarp();
+    {
+      T wr[16], wi[16];
+      wr[0] = T(1); wi[0] = T(0);
+#pragma unroll
+      for (int j = 1; j < 16; ++j) { const CT x = tws[j * 16 + c]; wr[j] = x.x; wi[j] = x.y; }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { const CT x = reg[17 * c + j]; re[j] = x.x; im[j] = x.y; }
+      __syncwarp();
+      TDSA_STAMP_PP(4);
+      acquire();
+      TDSA_STAMP_PP(5);
+      dft16_pretw<T>(re, im, wr, wi);                        // pass B
+      release();
+      TDSA_STAMP_PP(6);
+    }
+    // ---- no token: CTA-wide (group-wide) exchange ------------------------------------------------------------
+#pragma unroll
+    for (int q = 0; q < 16; ++q) reg[c + 17 * q] = mk<T>(re[q], im[q]);
+    group_sync();
+    if (tid == 0) {
+      const int64_t fn = frame_of(it + NSTAGE);
+      if (it + NSTAGE < iters && fn < a.n_frames) {
+        fence_proxy_async();
+        mbar_arrive_expect_tx(ctrl_u32 + 8 * stg, (uint32_t)W::STAGE_BYTES);
+        tma_load_3d(stage_u32 + (uint32_t)(stg * W::STAGE_BYTES), &tmap, 0, 0, (int)fn, ctrl_u32 + 8 * stg);
+      }
+    }
+    {
+      const CT* col = ex + tid + (tid >> 4);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { const CT x = col[j * REGION]; re[j] = x.x; im[j] = x.y; }
+    }
+    group_sync();
+    T pw[16];
+    TDSA_STAMP_PP(7);
+    acquire();
+    TDSA_STAMP_PP(8);
+    {
+      T wr[16], wi[16];
+      wr[0] = T(1); wi[0] = T(0);
+#pragma unroll
+      for (int j = 1; j < 16; ++j) {
+        if constexpr (TWMODE == 1) { wr[j] = twlr[j]; wi[j] = twli[j]; }
+        else {
+          if (j < 4 || (j & 3) == 0) { wr[j] = twlr[j]; wi[j] = twli[j]; }
+          else { wr[j] = twlr[j & 3]; wi[j] = twli[j & 3]; cmul<T>(wr[j], wi[j], twlr[j & ~3], twli[j & ~3]); }
+        }
+      }
+      dft16_pretw<T>(re, im, wr, wi);                        // last pass
+#pragma unroll
+      for (int q = 0; q < 16; ++q) pw[q] = re[q] * re[q] + im[q] * im[q];
+    }
+    release();
+    TDSA_STAMP_PP(9);
+    // ---- no token: narrowing, log2, coalesced stores ----------------------------------------------------------
+    auto emit = [&](auto mag_tag) {
+      constexpr bool MAG = decltype(mag_tag)::value;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) Epi::template store<T, MAG>(a.ep, f, N, tid + 256 * q, pw[q]);
+    };
+    if (mag20) emit(std::true_type{}); else emit(std::false_type{});
+    TDSA_STAMP_PP(10);
   }
 }
 

@@ -334,11 +334,15 @@ def main():
                        "kernel": main_run["info"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": f"fft_fused_kernel<{'double' if args.precision == 'f64' else 'float'},12,EpiDb>",
+                         "kernel": (f"fft_wl_kernel<{'double' if args.precision == 'f64' else 'float'},EpiDb> "
+                                    "(warp-local 16x256 plan, swizzled TMA tensor staging, dynamic frame scheduling)"
+                                    if os.environ.get("TDSA_WL", "1") != "0" else
+                                    f"fft_fused_kernel<{'double' if args.precision == 'f64' else 'float'},12,EpiDb>"),
                          "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * samples_per_step,
                          "kernel_ms_avg": main_run["kernel_ms"], "kernel_ms_best": main_run["kernel_ms_best"],
-                         "note": ("HBM is the bound the metric names; ncu shows the float64 kernel limited by the FP64 pipe "
-                                  "and the shared-memory pipe (see sm_side), not by HBM" if args.precision == "f64" else
+                         "note": ("HBM is the bound the metric names; the float64 kernel is limited by the FP64 pipe (DFMA-class "
+                                  "work plus the float<->double conversions that run on it: ~3000 of ~4400 cycles per frame "
+                                  "and SM) and by how well FP sections overlap shared-memory phases, not by HBM" if args.precision == "f64" else
                                   "ncu: issue slots and the L1/shared data pipe co-limit with HBM (see DESIGN.md 3.1)"),
                          "sm_side": sm_side(args.precision, main_run["kernel_ms"])},
             "e2e": {"value": world * samples_per_step / e2e_s, "unit": UNIT,

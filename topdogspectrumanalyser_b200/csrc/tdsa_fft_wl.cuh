@@ -1,7 +1,7 @@
 // tdsa_fft_wl.cuh — "warp-local" variant of the fused window + FFT + |.|^2 + dB kernel for N = 4096.
 //
 // Same arithmetic as fft_fused_kernel (tdsa_fft.cuh; reference datasources/rtl_samples.py:169-184), different
-// schedule.  Phase time stamps of fft_fused_kernel (profiles/r02_phase_timing.md) showed that its three CTA-wide
+// schedule.  Phase time stamps of fft_fused_kernel (profiles/r01_phase_timing.md) showed that its three CTA-wide
 // barriers per frame keep all eight warps of a CTA in the same phase, so the arithmetic pipe and the
 // shared-memory pipe are used one after the other instead of together, and that the two CTAs of an SM run at
 // very different speeds, which a static frame assignment turns into an idle tail.  Here:

@@ -203,6 +203,57 @@ template <int MODE> void run_cvt(const char* what) {
   cudaFree(out); cudaFree(cyc);
 }
 
+// E: packed float32 (FFMA2 / FADD2, sm_100) against scalar FFMA: 16 independent accumulator chains per thread
+template <int MODE, int ITER>
+__global__ void __launch_bounds__(512, 1) k_pack(float* out, long long* cyc) {
+  float2 acc[16], x[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { acc[j] = make_float2(threadIdx.x * 1e-3f + j, j * 1e-2f); x[j] = make_float2(1.0f + 1e-6f * j, 1.0f - 1e-6f * j); }
+  const float2 y = make_float2(1e-3f * (threadIdx.x & 3), 2e-3f);
+  __syncthreads();
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+    for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (MODE == 0) { acc[j].x = __fmaf_rn(acc[j].x, x[j].x, y.x); acc[j].y = __fmaf_rn(acc[j].y, x[j].y, y.y); }   // 2 scalar FFMA
+        else if (MODE == 1) acc[j] = __ffma2_rn(acc[j], x[j], y);                                                       // 1 FFMA2
+        else acc[j] = __fadd2_rn(acc[j], x[j]);                                                                         // 1 FADD2
+      }
+    }
+  }
+  const long long t1 = clock64();
+  float s = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += acc[j].x + acc[j].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if ((threadIdx.x & 31) == 0) cyc[blockIdx.x * 16 + (threadIdx.x >> 5)] = t1 - t0;
+}
+
+template <int MODE> void run_pack(const char* what) {
+  constexpr int ITER = 32;
+  float* out; long long* cyc;
+  cudaMalloc(&out, sizeof(float) * 148 * 512);
+  cudaMalloc(&cyc, sizeof(long long) * 148 * 16);
+  for (int wps = 1; wps <= 4; wps *= 2) {
+    k_pack<MODE, ITER><<<148, 128 * wps>>>(out, cyc);
+    cudaDeviceSynchronize();
+    k_pack<MODE, ITER><<<148, 128 * wps>>>(out, cyc);
+    cudaError_t e = cudaDeviceSynchronize();
+    std::vector<long long> h(148 * 16);
+    cudaMemcpy(h.data(), cyc, sizeof(long long) * 148 * 16, cudaMemcpyDeviceToHost);
+    double mx = 0;
+    for (int b = 0; b < 148; ++b) { long long m = 0; for (int w = 0; w < 4 * wps; ++w) m = std::max(m, h[b * 16 + w]); mx += (double)m; }
+    mx /= 148;
+    // 128 complex (= 256 scalar) multiply-adds per thread and iteration
+    printf("E %s: %d warps/SMSP: %.2f cycles per 32 lanes x 2 floats (slowest warp; %.0f cycles per iteration) (%s)\n", what, wps,
+           mx / ITER / 128.0 / wps, mx / ITER, cudaGetErrorString(e));
+  }
+  cudaFree(out); cudaFree(cyc);
+}
+
 template <typename T> void run_dft(const char* name) {
   constexpr int ITER = 64;
   T* out; long long* cyc;
@@ -247,6 +298,9 @@ template <typename T, bool WL> void run_exch(const char* name) {
 }
 
 int main() {
+  run_pack<0>("2 x scalar FFMA");
+  run_pack<1>("FFMA2");
+  run_pack<2>("FADD2");
   run_cvt<0>("radix-16 + 32 DADD (224 FP64 ops)");
   run_cvt<1>("same + 32 F2F.F64.F32");
   run_cvt<2>("same as first + 16 F2F.F32.F64 + 16 MUFU.LG2");

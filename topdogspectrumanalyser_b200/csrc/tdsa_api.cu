@@ -149,6 +149,9 @@ static int upload_window(tdsa_plan* p) {
 }
 
 // ---- tensor map of a batch of 4096-sample frames: [frame][256 rows][32 floats], 128-byte swizzle -------------
+#ifndef TDSA_TMAP_L2_PROMOTION
+#define TDSA_TMAP_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+#endif
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -189,7 +192,7 @@ static bool wl_prepare(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t s
   const cuuint32_t box[3] = {32, 256, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = enc(&p->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(iq), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, TDSA_TMAP_L2_PROMOTION,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { p->tmap_ptr = nullptr; return false; }
   p->tmap_ptr = iq; p->tmap_frames = n_frames; p->tmap_stride = stride;

@@ -31,6 +31,9 @@ namespace tdsa {
 #ifndef TDSA_PDL
 #define TDSA_PDL 0   // measured: no gain at 80-150 us per launch (81.9 vs 82.0 us); kept as an option
 #endif
+#ifndef TDSA_STREAM_STORES
+#define TDSA_STREAM_STORES 0
+#endif
 #ifndef TDSA_PADS_R8
 #define TDSA_PADS_R8(LOG2N, WIDE) pads_r8(LOG2N, WIDE)
 #endif
@@ -451,7 +454,11 @@ template <typename T> __device__ __forceinline__ float to_db(T p, const EpiParam
 struct EpiDb {
   template <typename T, bool MAG20>
   static __device__ __forceinline__ void store(const EpiParams& ep, int64_t f, int n, int k, T p) {
+#if TDSA_STREAM_STORES
+    __stcs(ep.db_out + f * n + k, to_db_m<T, MAG20>(p, ep));     // written once, never re-read by this kernel
+#else
     ep.db_out[f * n + k] = to_db_m<T, MAG20>(p, ep);
+#endif
   }
 };
 struct EpiLinear {

@@ -175,6 +175,11 @@ static bool dyn_enabled() {
   return on;
 }
 
+static bool welch_cluster_enabled() {
+  static const bool on = [] { const char* e = getenv("TDSA_WELCH_CLUSTER"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 static bool wl_enabled() {
   static const bool on = [] { const char* e = getenv("TDSA_WL"); return !(e && e[0] == '0'); }();
   return on;
@@ -612,6 +617,40 @@ int tdsa_welch(tdsa_handle_t p, const void* iq_stream, int64_t n_samples, int64_
   if (p->mode == TDSA_MODE_MAG20) return fail(TDSA_ERR_INVALID, "welch averages power; use power or psd mode");
   const int64_t nseg = (n_samples - p->n) / hop + 1;
   const int64_t n = p->n;
+  // 65536-point segments: one cluster kernel keeps everything but the IQ samples on the SMs (tdsa_welch_cluster.cuh)
+  if (p->log2n == kWcLog2N && welch_cluster_enabled()) {
+    int max_clusters = 0;
+    const bool f32 = p->precision == TDSA_PREC_F32;
+    if (f32) launch_welch_cluster_f32(WelchClusterArgs<float>(), 0, p->stream, &max_clusters);
+    else launch_welch_cluster_f64(WelchClusterArgs<double>(), 0, p->stream, &max_clusters);
+    if (max_clusters > 0) {
+      if (p->win_dirty) { int rcw = upload_window(p); if (rcw) return rcw; }
+      const int clusters = (int)std::min<int64_t>(max_clusters, nseg);
+      int rcs = ensure_scratch(&p->scratch, &p->scratch_bytes, (size_t)clusters * n * (sizeof(double) + sizeof(float)));
+      if (rcs) return rcs;
+      double* part_sum = (double*)p->scratch;
+      float* part_peak = (float*)(part_sum + (size_t)clusters * n);
+      cudaError_t e;
+      if (f32) {
+        WelchClusterArgs<float> a;
+        a.iq = (const float2*)iq_stream; a.n_seg = nseg; a.hop = hop; a.window = p->d_win32; a.tw_head = p->d_twh32;
+        a.tw_inner = p->d_twin32; a.part_sum = part_sum; a.part_peak = part_peak;
+        e = launch_welch_cluster_f32(a, clusters, p->stream, nullptr);
+      } else {
+        WelchClusterArgs<double> a;
+        a.iq = (const float2*)iq_stream; a.n_seg = nseg; a.hop = hop; a.window = p->d_win64; a.tw_head = p->d_twh64;
+        a.tw_inner = p->d_twin64; a.part_sum = part_sum; a.part_peak = part_peak;
+        e = launch_welch_cluster_f64(a, clusters, p->stream, nullptr);
+      }
+      if (e != cudaSuccess) return fail(TDSA_ERR_CUDA, "welch cluster launch failed: %s", cudaGetErrorString(e));
+      const double scale = (p->mode == TDSA_MODE_PSD) ? 1.0 / (p->fs * (double)n) : 1.0;
+      welch_cluster_finish_kernel<<<(int)(n / 256), 256, 0, p->stream>>>(part_sum, part_peak, clusters, nseg, scale, p->floor,
+                                                                       avg_db, peak_db);
+      count_launch();
+      CK(cudaGetLastError());
+      return TDSA_OK;
+    }
+  }
   // state: sum[N] double | peak[N] float, kept behind the linear scratch
   const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(nseg, ((int64_t)128 << 20) / (n * 8)));
   const size_t lin_bytes = (size_t)chunk * n * sizeof(double);

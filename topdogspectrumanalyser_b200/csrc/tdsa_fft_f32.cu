@@ -5,6 +5,9 @@ cudaError_t launch_fft_f32(int log2n, int epi, const FftArgs<float>& a, int sm, 
   return launch_fft_impl<float>(log2n, epi, a, sm, s, info, dry);
 }
 int effective_logr_f32(int log2n) { return effective_logr<float>(log2n); }
+cudaError_t launch_welch_cluster_f32(const WelchClusterArgs<float>& a, int clusters, cudaStream_t s, int* max_clusters) {
+  return launch_welch_cluster_impl<float>(a, clusters, s, max_clusters);
+}
 cudaError_t launch_wl_f32(int epi, const FftArgs<float>& a, const CUtensorMap& tmap, const float* wperm, WlSched sched,
                           int sm, cudaStream_t s, LaunchInfo* info, bool dry) {
   return launch_wl_impl<float>(epi, a, tmap, wperm, sched, sm, s, info, dry);

@@ -5,6 +5,9 @@ cudaError_t launch_fft_f64(int log2n, int epi, const FftArgs<double>& a, int sm,
   return launch_fft_impl<double>(log2n, epi, a, sm, s, info, dry);
 }
 int effective_logr_f64(int log2n) { return effective_logr<double>(log2n); }
+cudaError_t launch_welch_cluster_f64(const WelchClusterArgs<double>& a, int clusters, cudaStream_t s, int* max_clusters) {
+  return launch_welch_cluster_impl<double>(a, clusters, s, max_clusters);
+}
 cudaError_t launch_wl_f64(int epi, const FftArgs<double>& a, const CUtensorMap& tmap, const double* wperm, WlSched sched,
                           int sm, cudaStream_t s, LaunchInfo* info, bool dry) {
   return launch_wl_impl<double>(epi, a, tmap, wperm, sched, sm, s, info, dry);

@@ -10,6 +10,7 @@
 
 #include "tdsa_fft.cuh"
 #include "tdsa_fft_wl.cuh"
+#include "tdsa_welch_cluster.cuh"
 
 namespace tdsa {
 
@@ -367,6 +368,40 @@ cudaError_t launch_wl_f32(int epi, const FftArgs<float>& a, const CUtensorMap& t
                           int sm, cudaStream_t s, LaunchInfo* info, bool dry);
 cudaError_t launch_wl_f64(int epi, const FftArgs<double>& a, const CUtensorMap& tmap, const double* wperm, WlSched sched,
                           int sm, cudaStream_t s, LaunchInfo* info, bool dry);
+
+// ---- cluster Welch kernel (tdsa_welch_cluster.cuh): clusters of 16 CTAs, one CTA per SM -------------------------
+// max_clusters != nullptr: only report how many clusters can be co-resident (0 = this device cannot run it)
+template <typename T>
+cudaError_t launch_welch_cluster_impl(const WelchClusterArgs<T>& a, int clusters, cudaStream_t stream, int* max_clusters) {
+  auto kern = welch_cluster_kernel<T>;
+  constexpr size_t kSmem = WelchClusterPlan<T>::SMEM_BYTES;
+  static int max_active = -1;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kWcCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = kSmem; cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
+  if (max_active < 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    int n = 0;
+    if (e == cudaSuccess) {
+      cfg.gridDim = dim3(kWcCluster * 8);
+      e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    max_active = n;
+    if (getenv("TDSA_DEBUG_PRINT")) fprintf(stderr, "welch_cluster_kernel: %d clusters of %d CTAs can be co-resident\n", n, kWcCluster);
+  }
+  if (max_clusters) { *max_clusters = max_active; return cudaSuccess; }
+  if (max_active <= 0) return cudaErrorNotSupported;
+  cfg.gridDim = dim3(kWcCluster * clusters);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  return le != cudaSuccess ? le : cudaGetLastError();
+}
+cudaError_t launch_welch_cluster_f32(const WelchClusterArgs<float>& a, int clusters, cudaStream_t s, int* max_clusters);
+cudaError_t launch_welch_cluster_f64(const WelchClusterArgs<double>& a, int clusters, cudaStream_t s, int* max_clusters);
 
 // defined in tdsa_fft_f32.cu / tdsa_fft_f64.cu
 cudaError_t launch_fft_f32(int log2n, int epi, const FftArgs<float>& a, int sm, cudaStream_t s, LaunchInfo* info, bool dry);

@@ -24,6 +24,9 @@
 
 namespace tdsa {
 
+#ifndef TDSA_WC_DIAG
+#define TDSA_WC_DIAG 0
+#endif
 constexpr int kWcCluster = 16;                 // CTAs per cluster = sub-transforms per segment
 constexpr int kWcLog2N = 16;
 
@@ -58,7 +61,9 @@ __device__ __forceinline__ void st_cluster(uint32_t addr, double2 v) {
 template <typename T> struct WelchClusterPlan {
   using P = Plan<T, 12, 4>;
   static constexpr size_t BUF_BYTES = (((size_t)P::PHYS_SIZE * 2 * sizeof(T)) + 127) & ~(size_t)127;
-  static constexpr size_t SMEM_BYTES = 2 * BUF_BYTES + (size_t)256 * 2 * sizeof(T);
+  static constexpr size_t TW_BYTES = (size_t)256 * 2 * sizeof(T);
+  static constexpr size_t WIN_BYTES = (size_t)16 * 256 * sizeof(T);   // this CTA's window columns, [j][t]
+  static constexpr size_t SMEM_BYTES = 2 * BUF_BYTES + TW_BYTES + WIN_BYTES;
 };
 
 // base twiddles W^(x*{1,2,3,4,8,12}) -> all fifteen W^(x*q) (one complex multiply each for the other nine)
@@ -77,14 +82,18 @@ __global__ void __launch_bounds__(256, 1) welch_cluster_kernel(const WelchCluste
   using CT = typename CplxOf<T>::type;
   using W = WelchClusterPlan<T>;
   constexpr int M = 4096;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char wc_smem[];
+  unsigned char* smem_raw = wc_smem;
   CT* tws = reinterpret_cast<CT*>(smem_raw + 2 * W::BUF_BYTES);
+  T* wins = reinterpret_cast<T*>(smem_raw + 2 * W::BUF_BYTES + W::TW_BYTES);
   const uint32_t buf_u32 = smem_u32(smem_raw);
   const int t = (int)threadIdx.x;
   const uint32_t rho = cluster_ctarank();
   const int c = 256 * (int)rho + t;                        // this thread's column of the head pass
 
   for (int i = t; i < 256; i += 256) tws[i] = a.tw_inner[i];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) wins[j * 256 + t] = a.window[c + j * M];     // constant across segments
   // base twiddles of the head post-multiply W_N^(c q) and of the last inner pass W_4096^(j t)
   T hbr[16], hbi[16], lbr[16], lbi[16];
   const CT* tw_last = a.tw_inner + 256;
@@ -115,39 +124,58 @@ __global__ void __launch_bounds__(256, 1) welch_cluster_kernel(const WelchCluste
   }
   cluster_arrive();                                        // every CTA of the cluster is resident before remote stores
   cluster_wait();
+  __syncthreads();                                         // window columns and table staged
 
-  int it = 0;
-  for (int64_t seg = cid; seg < a.n_seg; seg += ncl, ++it) {
-    const uint32_t boff = (uint32_t)((it & 1) * W::BUF_BYTES);
-    CT* ex = reinterpret_cast<CT*>(smem_raw + boff);
+  // head of segment `seg` (samples already in v[]) into receive buffer `buf` of every CTA; then prefetch seg + ncl
+  auto head = [&](int64_t seg, int buf) {
+    const uint32_t boff = (uint32_t)(buf * W::BUF_BYTES);
     T re[16], im[16];
-    // ---- head: window, radix 16 over j, post-twiddle, scatter output q to CTA q --------------------------------
     {
       T win[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) win[j] = a.window[c + j * M];
+      for (int j = 0; j < 16; ++j) win[j] = wins[j * 256 + t];
 #pragma unroll
       for (int j = 0; j < 16; ++j) { re[j] = (T)v[j].x; im[j] = (T)v[j].y; }
       dft16_win<T>(re, im, win);
+    }
+    {
       T wr[16], wi[16];
       expand_base<T>(hbr, hbi, wr, wi);
 #pragma unroll
       for (int q = 1; q < 16; ++q) cmul<T>(re[q], im[q], wr[q], wi[q]);
-#pragma unroll
-      for (int q = 0; q < 16; ++q) st_cluster(remote[q] + boff, mk<T>(re[q], im[q]));
     }
-    // prefetch the next segment's samples while the cluster synchronises and the tail runs
-    {
-      const int64_t nseg = seg + ncl;
-      if (nseg < a.n_seg) {
-        const float2* src = a.iq + nseg * a.hop + c;
+#if TDSA_WC_DIAG == 1      // diagnostic (wrong results): keep the scatter local, to price the SM-to-SM traffic
+    CT* exl = reinterpret_cast<CT*>(smem_raw + boff);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = ldg_stream(src + j * M);
-      }
+    for (int q = 0; q < 16; ++q) exl[P::phys(t) + P::phys(q * 256)] = mk<T>(re[q], im[q]);
+#else
+#pragma unroll
+    for (int q = 0; q < 16; ++q) st_cluster(remote[q] + boff, mk<T>(re[q], im[q]));
+#endif
+    const int64_t nseg = seg + ncl;
+    if (nseg < a.n_seg) {
+      const float2* src = a.iq + nseg * a.hop + c;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = ldg_stream(src + j * M);
     }
-    cluster_arrive();
-    cluster_wait();                                        // sub-sequence q of this segment is complete in CTA q
+  };
+
+  // Order per CTA: H(0) | barrier | { H(i+1) ; T(i) ; barrier }.  The head of the NEXT segment is issued before the
+  // tail of the current one, so its SM-to-SM stores drain while the tail computes; the barrier after the tail both
+  // publishes H(i+1) and tells everyone that buffer (i & 1) has been consumed (H(i+2) may overwrite it).
+  if (cid < a.n_seg) head(cid, 0);
+  cluster_arrive();
+  cluster_wait();
+  int it = 0;
+  for (int64_t seg = cid; seg < a.n_seg; seg += ncl, ++it) {
+    if (seg + ncl < a.n_seg) head(seg + ncl, (it + 1) & 1);
+    CT* ex = reinterpret_cast<CT*>(smem_raw + (size_t)(it & 1) * W::BUF_BYTES);
+    T re[16], im[16];
     // ---- tail: 4096-point transform in place (DIT plan of Plan<T,12>: passes 16 x 16 x 16) --------------------
+#if TDSA_WC_DIAG == 2      // diagnostic (wrong results): no tail passes, to price head + exchange + barrier alone
+    if (a.n_seg < 0)
+#endif
+    {
     {                                                      // pass 0: x[t + 256 j], no twiddles
       const int pb = P::phys(t);
 #pragma unroll
@@ -179,6 +207,7 @@ __global__ void __launch_bounds__(256, 1) welch_cluster_kernel(const WelchCluste
       expand_base<T>(lbr, lbi, wr, wi);
       dft16_pretw<T>(re, im, wr, wi);
     }
+    }
     // bins kl = t + 256 q2 of sub-transform rho  ->  bin rho + 16 kl of the segment
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
@@ -186,6 +215,8 @@ __global__ void __launch_bounds__(256, 1) welch_cluster_kernel(const WelchCluste
       sum[q] += (double)pw;
       peak[q] = fmaxf(peak[q], (float)pw);                 // NaN-ignoring, like np.fmax
     }
+    cluster_arrive();
+    cluster_wait();
   }
   // partial rows of this cluster
   {
@@ -203,7 +234,7 @@ __global__ void __launch_bounds__(256, 1) welch_cluster_kernel(const WelchCluste
 }
 
 // avg_db[k] = dB(sum over clusters / n_seg), peak_db[k] = dB(max over clusters); rows are already fftshift-ed
-__global__ void __launch_bounds__(256) welch_cluster_finish_kernel(const double* __restrict__ part_sum,
+static __global__ void __launch_bounds__(256) welch_cluster_finish_kernel(const double* __restrict__ part_sum,
                                                                   const float* __restrict__ part_peak, int clusters,
                                                                   int64_t n_seg, double scale, double floor,
                                                                   float* __restrict__ avg_db, float* __restrict__ peak_db) {

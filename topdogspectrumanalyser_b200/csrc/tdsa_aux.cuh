@@ -423,13 +423,32 @@ __global__ void __launch_bounds__(256) stitch_interp_kernel(const StitchArgs a) 
   const double x_first = stitch_x(a, 0, bw), x_last = stitch_x(a, total - 1, bw);
   if (xv < x_first) { a.out[g] = stitch_y(a, 0); return; }        // default left = fp[0]
   if (xv > x_last) { a.out[g] = stitch_y(a, total - 1); return; } // default right = fp[-1]
-  int64_t lo_i = 0, hi_i = total - 1;     // invariant: x[lo_i] <= xv, and (hi_i == total-1 or x[hi_i] > xv)
-  while (hi_i - lo_i > 1) {
-    const int64_t mid = (lo_i + hi_i) >> 1;
-    if (stitch_x(a, mid, bw) <= xv) lo_i = mid; else hi_i = mid;
+  // j = largest index with x[j] <= xv.  Two levels: the row whose first sample is the last one <= xv (binary search
+  // over rows), then the sample inside it from the spacing, corrected with the exact comparisons np.interp makes.
+  int64_t j;
+  {
+    int64_t rlo = 0, rhi = a.n_rows - 1;             // x_first(rlo) <= xv (checked above)
+    while (rlo < rhi) {
+      const int64_t mid = (rlo + rhi + 1) >> 1;
+      if (stitch_x(a, mid * a.k, bw) <= xv) rlo = mid; else rhi = mid - 1;
+    }
+    const double x0 = stitch_x(a, rlo * a.k, bw);
+    int64_t i = (int64_t)floor((xv - x0) / bw);
+    i = i < 0 ? 0 : (i > a.k - 1 ? a.k - 1 : i);
+    while (i < a.k - 1 && stitch_x(a, rlo * a.k + i + 1, bw) <= xv) ++i;
+    while (i > 0 && stitch_x(a, rlo * a.k + i, bw) > xv) --i;
+    j = rlo * a.k + i;
   }
-  int64_t j = lo_i;
-  if (stitch_x(a, hi_i, bw) <= xv) j = hi_i;
+  // overlapping rows break the ordering the shortcut relies on: verify, and fall back to the search over all samples
+  if (!(stitch_x(a, j, bw) <= xv) || (j < total - 1 && stitch_x(a, j + 1, bw) <= xv)) {
+    int64_t lo_i = 0, hi_i = total - 1;     // invariant: x[lo_i] <= xv, and (hi_i == total-1 or x[hi_i] > xv)
+    while (hi_i - lo_i > 1) {
+      const int64_t mid = (lo_i + hi_i) >> 1;
+      if (stitch_x(a, mid, bw) <= xv) lo_i = mid; else hi_i = mid;
+    }
+    j = lo_i;
+    if (stitch_x(a, hi_i, bw) <= xv) j = hi_i;
+  }
   const double xj = stitch_x(a, j, bw), yj = stitch_y(a, j);
   if (j == total - 1 || xj == xv) { a.out[g] = yj; return; }
   const double xj1 = stitch_x(a, j + 1, bw), yj1 = stitch_y(a, j + 1);

@@ -121,6 +121,15 @@ template <> __device__ __forceinline__ double widen_fast<double>(float x) {
 #endif
 }
 
+// widen_fast that also keeps the running maximum of the magnitude bits (>= 0x7f800000 <=> an Inf or NaN was seen)
+__device__ __forceinline__ double widen_track(float x, uint32_t& top) {
+  const uint32_t u = __float_as_uint(x);
+  const uint32_t a = u & 0x7fffffffu;
+  top = max(top, a);
+  const uint32_t hi = (a >> 3) + 0x38000000u + (u & 0x80000000u);
+  return __hiloint2double((int)hi, (int)(u << 29));
+}
+
 template <typename T> __device__ __forceinline__ void cmul(T& xr, T& xi, T wr, T wi) {
   T r = xr * wr - xi * wi;
   T i = xr * wi + xi * wr;

@@ -153,16 +153,19 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(src + j * 2048);
       if constexpr (sizeof(T) == 8 && TDSA_INT_WIDEN) {
-        // integer-pipe widening; x * 0 is NaN exactly for Inf/NaN inputs, accumulated on the idle FP32 pipe
-        float special = 0.0f;
+        // integer-pipe widening; the largest |bits| seen tells whether an Inf/NaN went through (exponent 0xFF)
+        uint32_t top = 0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) special = __fmaf_rn(v[j].x, 0.0f, __fmaf_rn(v[j].y, 0.0f, special));
-        if (special != special) {                            // rare: hardware conversion keeps Inf/NaN
+        for (int j = 0; j < 16; ++j) {
+          re[j] = widen_track(v[j].x, top);
+          im[j] = widen_track(v[j].y, top);
+        }
+        if (top >= 0x7f800000u) {                            // rare: redo from the staged frame with the hardware conversion
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { re[j] = (T)v[j].x; im[j] = (T)v[j].y; }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { re[j] = widen_fast<T>(v[j].x); im[j] = widen_fast<T>(v[j].y); }
+          for (int j = 0; j < 16; ++j) {
+            const float2 x = *reinterpret_cast<const float2*>(src + j * 2048);
+            re[j] = (T)x.x; im[j] = (T)x.y;
+          }
         }
         if constexpr (HAS_DC) {
 #pragma unroll

@@ -593,7 +593,10 @@ int tdsa_group_avg_db(tdsa_handle_t p, const void* iq, int64_t n_groups, int64_t
   if (!iq || !db_rows) return fail(TDSA_ERR_INVALID, "null buffer");
   const int64_t n = p->n;
   const int64_t per_group = frames_per_group * n * (int64_t)sizeof(double);
-  const int64_t chunk = std::max<int64_t>(1, ((int64_t)256 << 20) / per_group);
+  // groups per launch: the float64 rows of a chunk are written by the FFT kernel and read straight back by the
+  // group-mean kernel, so a chunk that fits the 126 MB L2 keeps that traffic off HBM (TDSA_GROUP_CHUNK_MB to tune)
+  static const int64_t chunk_mb = [] { const char* e = getenv("TDSA_GROUP_CHUNK_MB"); return (int64_t)(e ? atoi(e) : 256); }();
+  const int64_t chunk = std::max<int64_t>(1, (std::max<int64_t>(chunk_mb, 1) << 20) / per_group);
   for (int64_t g0 = 0; g0 < n_groups; g0 += chunk) {
     const int64_t ng = std::min(chunk, n_groups - g0);
     int rc = ensure_scratch(&p->scratch, &p->scratch_bytes, (size_t)(ng * per_group));

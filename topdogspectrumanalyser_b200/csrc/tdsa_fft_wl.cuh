@@ -264,412 +264,4 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
   }
 }
 
-#ifdef TDSA_DEBUG_TIMING
-#define TDSA_STAMP_PP(i)                                                                                      \
-  do {                                                                                                        \
-    if (l == 0 && a.dbg != nullptr && it < 32) {                                                              \
-      long long c_;                                                                                           \
-      asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_)::"memory");                                            \
-      a.dbg[((((int64_t)blockIdx.x * 2 + g) * 8 + w) * 32 + it) * 16 + (i)] = c_;                             \
-    }                                                                                                         \
-  } while (0)
-#else
-#define TDSA_STAMP_PP(i) do {} while (0)
-#endif
-// ---------------------------------------------------------------------------------------------------------------
-// Ping-pong variant: ONE 512-thread CTA per SM holding two independent frame engines (groups) of 256 threads, each
-// with its own exchange buffer, staging ring and mbarriers, exactly as fft_wl_kernel.  The two groups hand a
-// "math token" back and forth (a pair of named barriers): a group holds it only for its pure FP sections (pass A,
-// pass B, last pass + |X|^2); staged loads, float->double conversions, shared-memory exchanges, the CTA-wide
-// barriers, log2 and the global stores all run WITHOUT the token, i.e. while the other group owns the FP pipe.
-// Phase time stamps showed two co-resident CTAs colliding (both in FP sections, then both outside them); the token
-// forces the alternation.  Frames are dealt statically in pairs (all CTAs are alike with one CTA per SM):
-// iteration it of CTA b handles frames 2 (b + it * gridDim.x) + g.
-template <typename T, typename Epi, int TWMODE, int NSTAGE, bool HAS_DC>
-__global__ void __launch_bounds__(512, 1)
-fft_wlpp_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, const T* __restrict__ wperm) {
-  using W = WlPlan<T>;
-  using CT = typename CplxOf<T>::type;
-  constexpr int N = W::N, TH = W::TH, REGION = W::REGION;
-  constexpr size_t GROUP_BYTES = W::smem_bytes(NSTAGE);     // multiple of 1024
-  extern __shared__ __align__(1024) unsigned char smem_all[];
-  const int g = (int)threadIdx.x >> 8;
-  const int tid = (int)threadIdx.x & 255;
-  unsigned char* smem_raw = smem_all + (size_t)g * GROUP_BYTES;
-  CT* ex = reinterpret_cast<CT*>(smem_raw);
-  CT* tws = ex + W::EX_ELEMS;
-  const uint32_t base_u32 = smem_u32(smem_raw);
-  const uint32_t ctrl_u32 = base_u32 + (uint32_t)W::EX_BYTES;
-  const uint32_t stage_u32 = (base_u32 + (uint32_t)(W::EX_BYTES + W::CTRL_BYTES) + 1023u) & ~1023u;
-  const unsigned char* stage_ptr = smem_raw + (stage_u32 - base_u32);
-
-  const int w = tid >> 5, l = tid & 31;
-  const int h = (l >> 3) & 1, c = (l & 7) + 8 * (l >> 4);
-  const int r = 2 * w + h;
-  CT* reg = ex + r * REGION;
-
-  auto group_sync = [&]() { bar_sync(1 + g, TH); };
-  auto acquire = [&]() { bar_sync(3 + g, 2 * TH); };         // wait until the other group has released the token
-  auto release = [&]() { bar_arrive(3 + (1 - g), 2 * TH); }; // hand the token to the other group
-
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) mbar_init(ctrl_u32 + 8 * s, 1);
-    fence_mbar_init();
-  }
-  for (int i = tid; i < W::TW_SMEM; i += TH) tws[i] = a.tw[i];
-
-  const CT* tw_last = a.tw + 256;
-  T win[16];
-  T twlr[16], twli[16];
-  if constexpr (TWMODE == 1) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) win[j] = wperm[j * TH + tid];
-#pragma unroll
-    for (int j = 1; j < 16; ++j) { const CT x = tw_last[j * 256 + tid]; twlr[j] = x.x; twli[j] = x.y; }
-  } else {
-#pragma unroll
-    for (int j = 1; j < 16; ++j) {
-      if (j < 4 || (j & 3) == 0) { const CT x = tw_last[j * 256 + tid]; twlr[j] = x.x; twli[j] = x.y; }
-    }
-  }
-
-  // both groups run the same number of iterations so that the token hand-offs pair up
-  const int64_t pairs = (a.n_frames + 1) / 2;
-  const int iters = (int64_t)blockIdx.x < pairs ? (int)((pairs - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-  auto frame_of = [&](int it) -> int64_t { return 2 * ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) + g; };
-
-  __syncthreads();                                           // barriers initialised, tables staged
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) {
-      const int64_t fs = frame_of(s);
-      if (s < iters && fs < a.n_frames) {
-        mbar_arrive_expect_tx(ctrl_u32 + 8 * s, (uint32_t)W::STAGE_BYTES);
-        tma_load_3d(stage_u32 + (uint32_t)(s * W::STAGE_BYTES), &tmap, 0, 0, (int)fs, ctrl_u32 + 8 * s);
-      }
-    }
-  }
-  if (g == 1) bar_arrive(3, 2 * TH);                         // group 0 owns the token first
-  const bool mag20 = a.ep.mode == kModeMag20;
-  const int stage_off = c * 128 + (((w ^ c) & 7) << 4) + h * 8;
-
-  for (int it = 0; it < iters; ++it) {
-    const int64_t f = frame_of(it);
-    if (f >= a.n_frames) {                                   // odd tail: keep the hand-offs paired
-#pragma unroll
-      for (int ph = 0; ph < 3; ++ph) { acquire(); release(); }
-      continue;
-    }
-    const int stg = it % NSTAGE;
-    T re[16], im[16];
-    TDSA_STAMP_PP(0);
-    // ---- no token: staged samples -> registers, conversion -------------------------------------------------
-    {
-      if constexpr (TWMODE != 1) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) win[j] = wperm[j * TH + tid];
-      }
-      T dcr = T(0), dci = T(0);
-      if constexpr (HAS_DC) { const double2 d = a.dc[f]; dcr = (T)d.x; dci = (T)d.y; }
-      mbar_wait(ctrl_u32 + 8 * stg, (uint32_t)((it / NSTAGE) & 1));
-      const unsigned char* src = stage_ptr + (size_t)stg * W::STAGE_BYTES + stage_off;
-      float2 v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(src + j * 2048);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if constexpr (HAS_DC) { re[j] = (T)v[j].x - dcr; im[j] = (T)v[j].y - dci; }
-        else { re[j] = (T)v[j].x; im[j] = (T)v[j].y; }
-      }
-    }
-    TDSA_STAMP_PP(1);
-    acquire();
-    TDSA_STAMP_PP(2);
-    dft16_win<T>(re, im, win);                               // pass A
-    release();
-    TDSA_STAMP_PP(3);
-    // ---- no token: team-local 16x16 transpose, pass-B operands ----------------------------------------------
-#pragma unroll
-    for (int q = 0; q < 16; ++q) reg[c + 17 * q] = mk<T>(re[q], im[q]);
-    __syncwarp();
-    {
-      T wr[16], wi[16];
-      wr[0] = T(1); wi[0] = T(0);
-#pragma unroll
-      for (int j = 1; j < 16; ++j) { const CT x = tws[j * 16 + c]; wr[j] = x.x; wi[j] = x.y; }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { const CT x = reg[17 * c + j]; re[j] = x.x; im[j] = x.y; }
-      __syncwarp();
-      TDSA_STAMP_PP(4);
-      acquire();
-      TDSA_STAMP_PP(5);
-      dft16_pretw<T>(re, im, wr, wi);                        // pass B
-      release();
-      TDSA_STAMP_PP(6);
-    }
-    // ---- no token: CTA-wide (group-wide) exchange ------------------------------------------------------------
-#pragma unroll
-    for (int q = 0; q < 16; ++q) reg[c + 17 * q] = mk<T>(re[q], im[q]);
-    group_sync();
-    if (tid == 0) {
-      const int64_t fn = frame_of(it + NSTAGE);
-      if (it + NSTAGE < iters && fn < a.n_frames) {
-        fence_proxy_async();
-        mbar_arrive_expect_tx(ctrl_u32 + 8 * stg, (uint32_t)W::STAGE_BYTES);
-        tma_load_3d(stage_u32 + (uint32_t)(stg * W::STAGE_BYTES), &tmap, 0, 0, (int)fn, ctrl_u32 + 8 * stg);
-      }
-    }
-    {
-      const CT* col = ex + tid + (tid >> 4);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) { const CT x = col[j * REGION]; re[j] = x.x; im[j] = x.y; }
-    }
-    group_sync();
-    T pw[16];
-    TDSA_STAMP_PP(7);
-    acquire();
-    TDSA_STAMP_PP(8);
-    {
-      T wr[16], wi[16];
-      wr[0] = T(1); wi[0] = T(0);
-#pragma unroll
-      for (int j = 1; j < 16; ++j) {
-        if constexpr (TWMODE == 1) { wr[j] = twlr[j]; wi[j] = twli[j]; }
-        else {
-          if (j < 4 || (j & 3) == 0) { wr[j] = twlr[j]; wi[j] = twli[j]; }
-          else { wr[j] = twlr[j & 3]; wi[j] = twli[j & 3]; cmul<T>(wr[j], wi[j], twlr[j & ~3], twli[j & ~3]); }
-        }
-      }
-      dft16_pretw<T>(re, im, wr, wi);                        // last pass
-#pragma unroll
-      for (int q = 0; q < 16; ++q) pw[q] = re[q] * re[q] + im[q] * im[q];
-    }
-    release();
-    TDSA_STAMP_PP(9);
-    // ---- no token: narrowing, log2, coalesced stores ----------------------------------------------------------
-    auto emit = [&](auto mag_tag) {
-      constexpr bool MAG = decltype(mag_tag)::value;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) Epi::template store<T, MAG>(a.ep, f, N, tid + 256 * q, pw[q]);
-    };
-    if (mag20) emit(std::true_type{}); else emit(std::false_type{});
-    TDSA_STAMP_PP(10);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Warp-specialised variant: ONE 512-thread CTA per SM.  Warps 0-7 ("sub-transform warps") only ever run pass A, the
-// team-local transpose and pass B of successive frames; warps 8-15 ("last-pass warps") only ever run the last
-// radix-16 pass, |X|^2, dB and the stores.  The two halves are a producer/consumer pipeline over a DOUBLE-BUFFERED
-// exchange (mbarriers yfull[2] / yfree[2], eight arrivals each, no CTA-wide barrier anywhere in the frame loop), so
-// every SM sub-partition holds four warps that are in different phases by construction: while the sub-transform
-// warps of frame k+1 are in an FP section, the last-pass warps of frame k are loading, narrowing, taking logs or
-// storing, and vice versa.  Each role keeps only its own constants in registers (128 per thread suffice).
-// Staging: NSTAGE swizzled TMA stages, full[] (expect_tx) / empty[] (eight arrivals) mbarriers; the first last-pass
-// warp re-arms a stage as soon as it sees it empty (polling, never blocking on it).  Frames are dealt statically
-// (one CTA per SM, all alike): frame k of CTA b is b + k * gridDim.x.
-template <typename T> struct WsPlan {
-  using W = WlPlan<T>;
-  static constexpr size_t EX_BYTES = (size_t)(2 * W::EX_ELEMS + W::TW_SMEM) * 2 * sizeof(T);
-  static constexpr size_t CTRL_BYTES = 128;     // full[4] @0, empty[4] @32, yfull[2] @64, yfree[2] @80
-  static __host__ __device__ constexpr size_t smem_bytes(int nstage) {
-    return ((EX_BYTES + CTRL_BYTES + 1023) & ~(size_t)1023) + 1024 + (size_t)nstage * W::STAGE_BYTES;
-  }
-};
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// bounded wait: a protocol error traps instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity) {
-  unsigned spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
-  }
-}
-
-template <typename T, typename Epi, int TWMODE, int NSTAGE, bool HAS_DC>
-__global__ void __launch_bounds__(512, 1)
-fft_ws_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, const T* __restrict__ wperm) {
-  using W = WlPlan<T>;
-  using S = WsPlan<T>;
-  using CT = typename CplxOf<T>::type;
-  constexpr int N = W::N, REGION = W::REGION;
-  static_assert(NSTAGE >= 1 && NSTAGE <= 4, "stage ring");
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  CT* ex = reinterpret_cast<CT*>(smem_raw);
-  CT* tws = ex + 2 * W::EX_ELEMS;
-  const uint32_t base_u32 = smem_u32(smem_raw);
-  const uint32_t full_u32 = base_u32 + (uint32_t)S::EX_BYTES;
-  const uint32_t empty_u32 = full_u32 + 32, yfull_u32 = full_u32 + 64, yfree_u32 = full_u32 + 80;
-  const uint32_t stage_u32 = (base_u32 + (uint32_t)(S::EX_BYTES + S::CTRL_BYTES) + 1023u) & ~1023u;
-  const unsigned char* stage_ptr = smem_raw + (stage_u32 - base_u32);
-
-  const int tid_all = (int)threadIdx.x;
-  const bool producer = tid_all < 256;                       // warps 0-7: sub-transforms; warps 8-15: last pass
-  const int tid = tid_all & 255;
-  const int w = tid >> 5, l = tid & 31;
-
-  // frames of this CTA
-  const int64_t first = blockIdx.x;
-  const int K = first < a.n_frames ? (int)((a.n_frames - first + gridDim.x - 1) / gridDim.x) : 0;
-  auto frame_of = [&](int k) -> int64_t { return first + (int64_t)k * gridDim.x; };
-
-  if (tid_all == 0) {
-#pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_u32 + 8 * s, 1); mbar_init(empty_u32 + 8 * s, 8); }
-    mbar_init(yfull_u32, 8); mbar_init(yfull_u32 + 8, 8);
-    mbar_init(yfree_u32, 8); mbar_init(yfree_u32 + 8, 8);
-    fence_mbar_init();
-  }
-  for (int i = tid_all; i < W::TW_SMEM; i += 512) tws[i] = a.tw[i];
-  __syncthreads();                                           // the only CTA-wide barrier
-  if (tid_all == 0) {
-#pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) {
-      if (s < K) {
-        mbar_arrive_expect_tx(full_u32 + 8 * s, (uint32_t)W::STAGE_BYTES);
-        tma_load_3d(stage_u32 + (uint32_t)(s * W::STAGE_BYTES), &tmap, 0, 0, (int)frame_of(s), full_u32 + 8 * s);
-      }
-    }
-  }
-
-  if (producer) {
-    // ===== sub-transform warps: frame k -> exchange buffer k & 1 ================================================
-    const int h = (l >> 3) & 1, c = (l & 7) + 8 * (l >> 4);
-    const int r = 2 * w + h;
-    const int stage_off = c * 128 + (((w ^ c) & 7) << 4) + h * 8;
-    T win[16];
-    if constexpr (TWMODE == 1) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) win[j] = wperm[j * 256 + tid];
-    }
-    for (int k = 0; k < K; ++k) {
-      const int stg = k % NSTAGE;
-      CT* reg = ex + (k & 1) * W::EX_ELEMS + r * REGION;
-      T re[16], im[16];
-      if constexpr (TWMODE != 1) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) win[j] = wperm[j * 256 + tid];
-      }
-      T dcr = T(0), dci = T(0);
-      if constexpr (HAS_DC) { const double2 d = a.dc[frame_of(k)]; dcr = (T)d.x; dci = (T)d.y; }
-      mbar_wait_b(full_u32 + 8 * stg, (uint32_t)((k / NSTAGE) & 1));
-      {
-        const unsigned char* src = stage_ptr + (size_t)stg * W::STAGE_BYTES + stage_off;
-        float2 v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(src + j * 2048);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if constexpr (HAS_DC) { re[j] = (T)v[j].x - dcr; im[j] = (T)v[j].y - dci; }
-          else { re[j] = (T)v[j].x; im[j] = (T)v[j].y; }
-        }
-      }
-      __syncwarp();
-      if (l == 0) mbar_arrive(empty_u32 + 8 * stg);          // this warp has the stage's samples in registers
-      dft16_win<T>(re, im, win);                             // pass A
-      // the last-pass warps must be done with frame k - 2 before its buffer is overwritten
-      if (k >= 2) mbar_wait_b(yfree_u32 + 8 * (k & 1), (uint32_t)(((k >> 1) - 1) & 1));
-#pragma unroll
-      for (int q = 0; q < 16; ++q) reg[c + 17 * q] = mk<T>(re[q], im[q]);
-      __syncwarp();
-      {                                                      // pass B
-        T wr[16], wi[16];
-        wr[0] = T(1); wi[0] = T(0);
-#pragma unroll
-        for (int j = 1; j < 16; ++j) { const CT x = tws[j * 16 + c]; wr[j] = x.x; wi[j] = x.y; }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { const CT x = reg[17 * c + j]; re[j] = x.x; im[j] = x.y; }
-        __syncwarp();
-        dft16_pretw<T>(re, im, wr, wi);
-      }
-#pragma unroll
-      for (int q = 0; q < 16; ++q) reg[c + 17 * q] = mk<T>(re[q], im[q]);
-      __syncwarp();
-      if (l == 0) mbar_arrive(yfull_u32 + 8 * (k & 1));
-    }
-  } else {
-    // ===== last-pass warps: exchange buffer k & 1 -> dB row of frame k ==========================================
-    const CT* tw_last = a.tw + 256;
-    T twlr[16], twli[16];
-#pragma unroll
-    for (int j = 1; j < 16; ++j) {
-      if (TWMODE == 1 || j < 4 || (j & 3) == 0) { const CT x = tw_last[j * 256 + tid]; twlr[j] = x.x; twli[j] = x.y; }
-    }
-    const bool mag20 = a.ep.mode == kModeMag20;
-    int next_issue = NSTAGE;                                 // thread 256 only: next frame whose copy is to be started
-    auto poll_issue = [&]() {                                // re-arm every stage that has been emptied; never blocks
-      if (tid == 0) {
-        while (next_issue < K) {
-          const int s = next_issue % NSTAGE;
-          if (!mbar_try_wait(empty_u32 + 8 * s, (uint32_t)(((next_issue / NSTAGE) - 1) & 1))) break;
-          fence_proxy_async();
-          mbar_arrive_expect_tx(full_u32 + 8 * s, (uint32_t)W::STAGE_BYTES);
-          tma_load_3d(stage_u32 + (uint32_t)(s * W::STAGE_BYTES), &tmap, 0, 0, (int)frame_of(next_issue), full_u32 + 8 * s);
-          ++next_issue;
-        }
-      }
-    };
-    for (int k = 0; k < K; ++k) {
-      const int64_t f = frame_of(k);
-      T re[16], im[16];
-      poll_issue();
-      // wait for the eight sub-transform warps; warp 8 keeps polling the stage ring while it waits
-      if (w == 0) {
-        unsigned spins = 0;
-        while (!mbar_try_wait(yfull_u32 + 8 * (k & 1), (uint32_t)((k >> 1) & 1))) {
-          poll_issue();
-          if (++spins > (1u << 26)) __trap();
-        }
-        __syncwarp();
-      } else {
-        mbar_wait_b(yfull_u32 + 8 * (k & 1), (uint32_t)((k >> 1) & 1));
-      }
-      {
-        const CT* col = ex + (k & 1) * W::EX_ELEMS + tid + (tid >> 4);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { const CT x = col[j * REGION]; re[j] = x.x; im[j] = x.y; }
-      }
-      {
-        T wr[16], wi[16];
-        wr[0] = T(1); wi[0] = T(0);
-#pragma unroll
-        for (int j = 1; j < 16; ++j) {
-          if constexpr (TWMODE == 1) { wr[j] = twlr[j]; wi[j] = twli[j]; }
-          else {
-            if (j < 4 || (j & 3) == 0) { wr[j] = twlr[j]; wi[j] = twli[j]; }
-            else { wr[j] = twlr[j & 3]; wi[j] = twli[j & 3]; cmul<T>(wr[j], wi[j], twlr[j & ~3], twli[j & ~3]); }
-          }
-        }
-        dft16_pretw<T>(re, im, wr, wi);                      // last pass: radix 16 over r, pre-twiddle W4096^(r kk)
-      }
-      __syncwarp();
-      if (l == 0) mbar_arrive(yfree_u32 + 8 * (k & 1));      // buffer consumed
-      poll_issue();
-      auto emit = [&](auto mag_tag) {
-        constexpr bool MAG = decltype(mag_tag)::value;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const T pw = re[q] * re[q] + im[q] * im[q];
-          Epi::template store<T, MAG>(a.ep, f, N, tid + 256 * q, pw);
-        }
-      };
-      if (mag20) emit(std::true_type{}); else emit(std::false_type{});
-    }
-    // stages emptied after the last poll of the loop still have to be re-armed for the sub-transform warps
-    if (tid == 0) {
-      while (next_issue < K) {
-        const int s = next_issue % NSTAGE;
-        mbar_wait_b(empty_u32 + 8 * s, (uint32_t)(((next_issue / NSTAGE) - 1) & 1));
-        fence_proxy_async();
-        mbar_arrive_expect_tx(full_u32 + 8 * s, (uint32_t)W::STAGE_BYTES);
-        tma_load_3d(stage_u32 + (uint32_t)(s * W::STAGE_BYTES), &tmap, 0, 0, (int)frame_of(next_issue), full_u32 + 8 * s);
-        ++next_issue;
-      }
-    }
-  }
-}
-
 }  // namespace tdsa

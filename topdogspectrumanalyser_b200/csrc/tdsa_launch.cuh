@@ -242,18 +242,6 @@ template <typename T> int effective_logr(int log2n) {
 #ifndef TDSA_WL_L2AHEAD_F64
 #define TDSA_WL_L2AHEAD_F64 0
 #endif
-#ifndef TDSA_WL_WS_F32          // 1: fft_ws_kernel (512 threads: eight sub-transform warps + eight last-pass warps)
-#define TDSA_WL_WS_F32 0
-#endif
-#ifndef TDSA_WL_WS_F64
-#define TDSA_WL_WS_F64 0
-#endif
-#ifndef TDSA_WL_PINGPONG_F32    // 1: fft_wlpp_kernel (two frame engines per CTA trading a math token)
-#define TDSA_WL_PINGPONG_F32 0   // measured: 94 us vs 80 us (the exchange phases, not the FP sections, dominate float32)
-#endif
-#ifndef TDSA_WL_PINGPONG_F64
-#define TDSA_WL_PINGPONG_F64 0   // measured: 209 us vs 135 us (FP64 sections run 2.5-4x slower than the pipe allows while the other group's LDS/STS/F2F traffic shares the MIO queue)
-#endif
 #ifndef TDSA_WL_STAGES_F64
 #define TDSA_WL_STAGES_F64 1
 #endif
@@ -272,70 +260,6 @@ cudaError_t launch_wl_final(const FftArgs<T>& a, const CUtensorMap& tmap, const 
   constexpr int kTwMode = sizeof(T) == 4 ? TDSA_F32_TWMODE : TDSA_F64_TWMODE;
   static const size_t kExtraSmem = [] { const char* e = getenv("TDSA_DEBUG_EXTRA_SMEM"); return e ? (size_t)atol(e) : (size_t)0; }();
   const size_t kSmem = std::min<size_t>(WlPlan<T>::smem_bytes(kStages) + kExtraSmem, 227 * 1024);
-  // warp-specialised build: one 512-thread CTA per SM, producer / consumer warps (see fft_ws_kernel)
-  constexpr bool kWarpSpec = (sizeof(T) == 4 ? TDSA_WL_WS_F32 : TDSA_WL_WS_F64) != 0;
-  if constexpr (kWarpSpec) {
-    constexpr int kWsStages = 2;
-    const size_t smemw = WsPlan<T>::smem_bytes(kWsStages);
-    auto kws = fft_ws_kernel<T, Epi, kTwMode, kWsStages, HAS_DC>;
-    static bool once_ws = false;
-    if (!once_ws) {
-      cudaError_t e = cudaFuncSetAttribute(kws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw);
-      if (e != cudaSuccess) return e;
-      once_ws = true;
-    }
-    const int gridw = (int)std::max<int64_t>(1, std::min<int64_t>(a.n_frames, (int64_t)sm_count));
-    if (info) {
-      info->threads = 512; info->smem = (int)smemw; info->ctas_per_sm = 1; info->grid = gridw;
-      info->stages = kWsStages; info->logr = 4;
-    }
-    if (dry || a.n_frames <= 0) return cudaSuccess;
-    kws<<<gridw, 512, smemw, stream>>>(a, tmap, wperm);
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
-    return cudaGetLastError();
-  }
-  // ping-pong build: one 512-thread CTA per SM, two frame engines, static pairs (see fft_wlpp_kernel)
-  constexpr bool kPingPong = (sizeof(T) == 4 ? TDSA_WL_PINGPONG_F32 : TDSA_WL_PINGPONG_F64) != 0;
-  if constexpr (kPingPong) {
-    const size_t smem2 = 2 * WlPlan<T>::smem_bytes(kStages);
-    auto kpp = fft_wlpp_kernel<T, Epi, kTwMode, kStages, HAS_DC>;
-    static bool once = false;
-    if (!once) {
-      cudaError_t e = cudaFuncSetAttribute(kpp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-      if (e != cudaSuccess) return e;
-      once = true;
-    }
-    const int gridp = (int)std::max<int64_t>(1, std::min<int64_t>((a.n_frames + 1) / 2, (int64_t)sm_count));
-    if (info) {
-      info->threads = 512; info->smem = (int)smem2; info->ctas_per_sm = 1; info->grid = gridp;
-      info->stages = kStages; info->logr = 4;
-    }
-    if (dry || a.n_frames <= 0) return cudaSuccess;
-    FftArgs<T> bp = a;
-#ifdef TDSA_DEBUG_TIMING
-    static long long* d_dbgp = nullptr;
-    const size_t dbgp_count = (size_t)gridp * 2 * 8 * 32 * 16;
-    const char* dbgp_path = getenv("TDSA_DEBUG_TIMING_OUT");
-    if (dbgp_path) {
-      if (!d_dbgp) cudaMalloc(&d_dbgp, sizeof(long long) * ((size_t)2048 * 8 * 32 * 16));
-      cudaMemsetAsync(d_dbgp, 0, sizeof(long long) * dbgp_count, stream);
-      bp.dbg = d_dbgp;
-    }
-#endif
-    kpp<<<gridp, 512, smem2, stream>>>(bp, tmap, wperm);
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
-#ifdef TDSA_DEBUG_TIMING
-    if (bp.dbg) {
-      cudaStreamSynchronize(stream);
-      std::vector<long long> hh(dbgp_count);
-      cudaMemcpy(hh.data(), d_dbgp, sizeof(long long) * dbgp_count, cudaMemcpyDeviceToHost);
-      char path[512];
-      snprintf(path, sizeof path, "%s_pp_%s_g%d.bin", dbgp_path, sizeof(T) == 4 ? "f32" : "f64", gridp);
-      if (FILE* fp = fopen(path, "wb")) { fwrite(hh.data(), sizeof(long long), dbgp_count, fp); fclose(fp); }
-    }
-#endif
-    return cudaGetLastError();
-  }
   auto kern = fft_wl_kernel<T, Epi, kTwMode, kStages, HAS_DC, 2, (sizeof(T) == 4 ? TDSA_WL_L2AHEAD_F32 : TDSA_WL_L2AHEAD_F64) != 0>;
   static int occ = -1;
   if (occ < 0) {

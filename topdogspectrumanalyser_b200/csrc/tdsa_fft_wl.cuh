@@ -57,7 +57,7 @@ struct WlSched {
   int* done;       // CTAs that have left the frame loop
 };
 
-template <typename T, typename Epi, int TWMODE, int NSTAGE, bool HAS_DC, int MIN_CTAS, bool L2_AHEAD>
+template <typename T, typename Epi, int TWMODE, int NSTAGE, bool HAS_DC, int MIN_CTAS, bool L2_AHEAD, bool TWB_BASE>
 __global__ void __launch_bounds__(256, MIN_CTAS)
 fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, const T* __restrict__ wperm, WlSched sched) {
   using W = WlPlan<T>;
@@ -103,6 +103,14 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     }
   }
 
+  // pass-B twiddles W256^(j c) depend on the thread's team lane only: optionally six of them stay in registers
+  T twbr[TWB_BASE ? 16 : 1], twbi[TWB_BASE ? 16 : 1];
+  if constexpr (TWB_BASE) {
+#pragma unroll
+    for (int j = 1; j < 16; ++j) {
+      if (j < 4 || (j & 3) == 0) { const CT x = a.tw[j * 16 + c]; twbr[j] = x.x; twbi[j] = x.y; }
+    }
+  }
   // claim the first NSTAGE frames and start their copies
   int pend = 0;                                             // thread 0: frame claimed one refill ahead (L2_AHEAD)
   if (tid == 0) {
@@ -192,8 +200,16 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     {
       T wr[16], wi[16];
       wr[0] = T(1); wi[0] = T(0);
+      if constexpr (TWB_BASE) {                              // W256^(j c) from six base twiddles held in registers
 #pragma unroll
-      for (int j = 1; j < 16; ++j) { const CT x = tws[j * 16 + c]; wr[j] = x.x; wi[j] = x.y; }
+        for (int j = 1; j < 16; ++j) {
+          if (j < 4 || (j & 3) == 0) { wr[j] = twbr[j]; wi[j] = twbi[j]; }
+          else { wr[j] = twbr[j & 3]; wi[j] = twbi[j & 3]; cmul<T>(wr[j], wi[j], twbr[j & ~3], twbi[j & ~3]); }
+        }
+      } else {
+#pragma unroll
+        for (int j = 1; j < 16; ++j) { const CT x = tws[j * 16 + c]; wr[j] = x.x; wi[j] = x.y; }
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) { const CT x = reg[17 * c + j]; re[j] = x.x; im[j] = x.y; }
       __syncwarp();                                          // every lane of the team has read before anyone overwrites

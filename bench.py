@@ -142,52 +142,81 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------
-# clocks sampler (NVML in-process so that millisecond-long timed regions still get samples)
+# clocks sampler (NVML polled by a child process so that millisecond-long timed regions still get samples)
 # ------------------------------------------------------------------------------------------
-class ClockSampler:
-    def __init__(self, index: int):
-        self.samples, self.reasons = [], set()
-        self.max_mhz = None
-        self._stop = threading.Event()
-        self._thr = None
+def _clock_worker(index, conn):
+    """Child process: poll NVML as fast as it answers; send (monotonic time, SM MHz, reason bits) tuples on request."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        conn.send(("ready", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+    except Exception as e:                       # no NVML: the parent records that there are no samples
+        conn.send(("error", repr(e)))
+        return
+    out = []
+    while not conn.poll(0):
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-        except Exception:
-            self.nv = None
-
-    def _loop(self):
-        nv = self.nv
-        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
-                 0x80: "hw_power_brake_slowdown"}
-        while not self._stop.is_set():
+            mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
             except Exception:
-                break
-            time.sleep(0.0005)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            out.append((time.monotonic(), mhz, int(r)))
+        except Exception:
+            break
+    conn.send(out)
+
+
+class ClockSampler:
+    """SM clock and throttle reasons during the timed region, sampled by a separate PROCESS (the launching thread holds
+    the GIL for the whole region, which starves an in-process sampler); only samples inside [t0, t1] are kept."""
+
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+             0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int):
+        import multiprocessing as mp
+        self.max_mhz, self.proc = None, None
+        try:
+            ctx = mp.get_context("spawn")
+            self.conn, child = ctx.Pipe()
+            self.proc = ctx.Process(target=_clock_worker, args=(index, child), daemon=True)
+            self.proc.start()
+            if self.conn.poll(30):
+                tag, val = self.conn.recv()
+                if tag == "ready":
+                    self.max_mhz = val
+                else:
+                    self.proc = None
+            else:
+                self.proc = None
+        except Exception:
+            self.proc = None
 
     def start(self):
-        if self.nv is not None:
-            self._thr = threading.Thread(target=self._loop, daemon=True)
-            self._thr.start()
+        self.t0 = time.monotonic()
 
     def stop(self):
-        self._stop.set()
-        if self._thr is not None:
-            self._thr.join(timeout=2)
-        med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        t1 = time.monotonic()
+        samples = []
+        if self.proc is not None:
+            try:
+                self.conn.send("stop")
+                if self.conn.poll(10):
+                    samples = self.conn.recv()
+                self.proc.join(timeout=5)
+            except Exception:
+                samples = []
+        inside = [s for s in samples if self.t0 <= s[0] <= t1]
+        reasons = set()
+        for _, _, r in inside:
+            for bit, name in self.NAMES.items():
+                if r & bit:
+                    reasons.add(name)
+        med = float(np.median([s[1] for s in inside])) if inside else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons), "samples": len(inside),
+                "window_ms": (t1 - self.t0) * 1e3}
 
 
 # ------------------------------------------------------------------------------------------
@@ -248,12 +277,12 @@ def main():
 
     def measure(precision, steps, warmup, sample_clocks):
         plan = SpectrumPlan(N_FFT, "hanning", mode="power", precision=precision, device=dev)
+        sampler = ClockSampler(local_rank) if sample_clocks else None     # child process is polling from here on
         for _ in range(warmup):
             plan.psd_db(x, out=out)
         barrier()
-        sampler = ClockSampler(local_rank) if sample_clocks else None
         if sampler:
-            sampler.start()
+            sampler.start()                                               # only samples from now on are kept
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         n0 = _lib.launch_count()
         ev[0].record()

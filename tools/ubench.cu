@@ -254,6 +254,68 @@ template <int MODE> void run_pack(const char* what) {
   cudaFree(out); cudaFree(cyc);
 }
 
+// F: the ping-pong skeleton alone.  512 threads = two groups of 8 warps; a group holds the math token (a pair of named
+// barriers, as fft_wlpp_kernel did) only for its FP section (2 x radix-16) and runs its exchange without it.
+template <int ITER, bool TOKEN>
+__global__ void __launch_bounds__(512, 1) k_pingpong(double* out, long long* cyc) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  double2* ex = reinterpret_cast<double2*>(sm);
+  const int tall = threadIdx.x, g = tall >> 8, t = tall & 255;
+  double re[16], im[16], wr[16], wi[16], br[4], bi[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { br[j] = 0.05 + 1e-4 * ((t + j) & 7); bi[j] = 0.03 + 1e-3 * j; }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { re[j] = (t + j) * 1e-3; im[j] = j * 2e-3; wr[j] = br[j & 3]; wi[j] = bi[j & 3]; }
+  const int c = t & 15, s = t >> 4;
+  double2* my = ex + (g * 16 + s) * (17 * 16);
+  long long fp_cycles = 0;
+  __syncthreads();
+  if (TOKEN && g == 1) bar_arrive(3, 512);
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (int it = 0; it < ITER; ++it) {
+    if (TOKEN) bar_sync(3 + g, 512);
+    const long long f0 = clock64();
+    dft16_pretw<double>(re, im, wr, wi);
+    dft16_pretw<double>(re, im, wr, wi);
+    fp_cycles += clock64() - f0;
+    if (TOKEN) bar_arrive(3 + (1 - g), 512);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) my[c * 17 + q] = make_double2(re[q], im[q]);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { double2 x = my[j * 17 + c]; re[j] = x.x * 1e-3; im[j] = x.y * 1e-3; }
+    __syncwarp();
+  }
+  const long long t1 = clock64();
+  double sacc = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) sacc += re[j] + im[j];
+  out[blockIdx.x * 512 + tall] = sacc;
+  if ((tall & 31) == 0) { cyc[(blockIdx.x * 16 + (tall >> 5)) * 2] = t1 - t0; cyc[(blockIdx.x * 16 + (tall >> 5)) * 2 + 1] = fp_cycles; }
+}
+
+template <bool TOKEN> void run_pingpong() {
+  constexpr int ITER = 64;
+  double* out; long long* cyc;
+  cudaMalloc(&out, sizeof(double) * 148 * 512);
+  cudaMalloc(&cyc, sizeof(long long) * 148 * 32);
+  const size_t smem = (size_t)32 * 17 * 16 * 16 + 1024;
+  auto kern = k_pingpong<ITER, TOKEN>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<148, 512, smem>>>(out, cyc);
+  cudaDeviceSynchronize();
+  kern<<<148, 512, smem>>>(out, cyc);
+  cudaError_t e = cudaDeviceSynchronize();
+  std::vector<long long> h(148 * 32);
+  cudaMemcpy(h.data(), cyc, sizeof(long long) * 148 * 32, cudaMemcpyDeviceToHost);
+  double tot = 0, fp = 0;
+  for (int i = 0; i < 148 * 16; ++i) { tot += (double)h[2 * i]; fp += (double)h[2 * i + 1]; }
+  printf("F ping-pong skeleton (%s): %.0f cycles per iteration per warp, of which %.0f in the FP section (2 x radix-16; 1600 = pipe-bound for a group alone) (%s)\n",
+         TOKEN ? "math token" : "no token", tot / (148 * 16) / ITER, fp / (148 * 16) / ITER, cudaGetErrorString(e));
+  cudaFree(out); cudaFree(cyc);
+}
+
 template <typename T> void run_dft(const char* name) {
   constexpr int ITER = 64;
   T* out; long long* cyc;
@@ -298,6 +360,8 @@ template <typename T, bool WL> void run_exch(const char* name) {
 }
 
 int main() {
+  run_pingpong<false>();
+  run_pingpong<true>();
   run_pack<0>("2 x scalar FFMA");
   run_pack<1>("FFMA2");
   run_pack<2>("FADD2");

@@ -253,10 +253,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # keep stdout to the ONE JSON line: with NCCL_DEBUG set (VERSION, WARN, ...) NCCL prints its version banner
-        # and any diagnostics to stdout unless told otherwise
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # keep stdout to the ONE JSON line: with NCCL_DEBUG set (the GPU boxes export it) NCCL prints its version banner
+        # to stdout when the first communicator comes up, so file descriptor 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     def barrier():
         if world > 1:

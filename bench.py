@@ -154,7 +154,7 @@ def _clock_worker(index, conn):
     except Exception as e:                       # no NVML: the parent records that there are no samples
         conn.send(("error", repr(e)))
         return
-    out = []
+    out, errors = [], 0
     while not conn.poll(0):
         try:
             mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
@@ -163,9 +163,11 @@ def _clock_worker(index, conn):
             except Exception:
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
             out.append((time.monotonic(), mhz, int(r)))
-        except Exception:
-            break
-    conn.send(out)
+            time.sleep(0.00005)                  # ~10 kHz is plenty; do not hammer the driver next to the launches
+        except Exception:                        # a transient NVML error must not end the sampling
+            errors += 1
+            time.sleep(0.0002)
+    conn.send((out, errors))
 
 
 class ClockSampler:
@@ -194,21 +196,29 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark_warmup(self):
+        self.tw = time.monotonic()
+
     def start(self):
         self.t0 = time.monotonic()
 
     def stop(self):
         t1 = time.monotonic()
-        samples = []
+        samples, errors = [], None
         if self.proc is not None:
             try:
                 self.conn.send("stop")
                 if self.conn.poll(10):
-                    samples = self.conn.recv()
+                    samples, errors = self.conn.recv()
                 self.proc.join(timeout=5)
             except Exception:
                 samples = []
-        inside = [s for s in samples if self.t0 <= s[0] <= t1]
+        timed = [s for s in samples if self.t0 <= s[0] <= t1]
+        # the warm-up steps run the same launches back to back with the timed ones: same load, longer window
+        inside = [s for s in samples if getattr(self, "tw", self.t0) <= s[0] <= t1]
+        if not inside and samples:               # NVML stalled across the whole window: take the closest sample
+            mid = 0.5 * (self.t0 + t1)
+            inside = [min(samples, key=lambda s: abs(s[0] - mid))]
         reasons = set()
         for _, _, r in inside:
             for bit, name in self.NAMES.items():
@@ -216,7 +226,8 @@ class ClockSampler:
                     reasons.add(name)
         med = float(np.median([s[1] for s in inside])) if inside else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons), "samples": len(inside),
-                "window_ms": (t1 - self.t0) * 1e3}
+                "samples_in_timed_region": len(timed), "timed_region_ms": (t1 - self.t0) * 1e3,
+                "window": "warm-up + timed steps (identical launches, back to back)", "nvml_errors": errors}
 
 
 # ------------------------------------------------------------------------------------------
@@ -287,6 +298,10 @@ def main():
     def measure(precision, steps, warmup, sample_clocks):
         plan = SpectrumPlan(N_FFT, "hanning", mode="power", precision=precision, device=dev)
         sampler = ClockSampler(local_rank) if sample_clocks else None     # child process is polling from here on
+        if sampler:
+            plan.psd_db(x, out=out)                                       # module load / first launch before the window opens
+            torch.cuda.synchronize()
+            sampler.mark_warmup()
         for _ in range(warmup):
             plan.psd_db(x, out=out)
         barrier()

@@ -359,7 +359,76 @@ template <typename T, bool WL> void run_exch(const char* name) {
   cudaFree(out); cudaFree(cyc);
 }
 
+// G: does SHFL share the shared-memory data path?  mode 0: all 16 warps shuffle (64 SHFL.BFLY per iteration);
+// mode 1: all 16 warps do conflict-free LDS.128 + STS.128 (16 each); mode 2: warps 0-7 shuffle, warps 8-15 LDS/STS.
+template <int ITER>
+__global__ void __launch_bounds__(512, 1) k_shfl(float* out, long long* cyc, int mode) {
+  extern __shared__ __align__(128) unsigned char sm[];
+  float4* ex = reinterpret_cast<float4*>(sm);
+  const int t = threadIdx.x, w = t >> 5;
+  float v[16];
+  float4 q[4];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = (float)(t + j);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) q[j] = make_float4(t, j, 1, 2);
+  const bool do_shfl = mode == 0 || (mode == 2 && w < 8);
+  __syncthreads();
+  const long long t0 = clock64();
+  if (do_shfl) {
+#pragma unroll 1
+    for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 1 << k);
+    }
+  } else {
+#pragma unroll 1
+    for (int it = 0; it < ITER; ++it) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ex[t + 512 * j] = q[j];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float4 x = ex[(t ^ 1) + 512 * j]; q[j].x += x.x; q[j].y += x.w; }
+        __syncwarp();
+      }
+    }
+  }
+  const long long t1 = clock64();
+  float s = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += v[j];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) s += q[j].x + q[j].y;
+  out[blockIdx.x * blockDim.x + t] = s;
+  if ((t & 255) == 0) cyc[blockIdx.x * 2 + (t >> 8)] = t1 - t0;
+}
+
+static void run_shfl() {
+  constexpr int ITER = 64;
+  float* out; long long* cyc;
+  cudaMalloc(&out, 148 * 512 * sizeof(float)); cudaMalloc(&cyc, 148 * 2 * sizeof(long long));
+  cudaFuncSetAttribute(k_shfl<ITER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  for (int mode = 0; mode < 3; ++mode) {
+    for (int rep = 0; rep < 2; ++rep) k_shfl<ITER><<<148, 512, 64 * 1024>>>(out, cyc, mode);
+    cudaError_t e = cudaDeviceSynchronize();
+    std::vector<long long> h(148 * 2);
+    cudaMemcpy(h.data(), cyc, sizeof(long long) * 148 * 2, cudaMemcpyDeviceToHost);
+    double a0 = 0, a1 = 0; for (int i = 0; i < 148; ++i) { a0 += h[2 * i]; a1 += h[2 * i + 1]; } a0 /= 148; a1 /= 148;
+    // per iteration: shuffling warps issue 64 SHFL each; LDS/STS warps 16 STS.128 + 16 LDS.128 each (= 128 wavefronts per warp)
+    printf("G mode %d (%s): warps 0-7 %.0f cycles/iter, warps 8-15 %.0f cycles/iter (%s)\n", mode,
+           mode == 0 ? "16 warps SHFL: 1024 SHFL per iter and SM" : mode == 1 ? "16 warps LDS/STS.128: 2048 wavefronts per iter and SM"
+                                                                         : "8 warps SHFL (512) + 8 warps LDS/STS (1024 wavefronts)",
+           a0 / ITER, a1 / ITER, cudaGetErrorString(e));
+  }
+  cudaFree(out); cudaFree(cyc);
+}
+
 int main() {
+  run_shfl();
   run_pingpong<false>();
   run_pingpong<true>();
   run_pack<0>("2 x scalar FFMA");

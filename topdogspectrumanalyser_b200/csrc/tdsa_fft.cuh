@@ -121,6 +121,40 @@ template <> __device__ __forceinline__ double widen_fast<double>(float x) {
 #endif
 }
 
+// Lean integer widening (TDSA_INT_WIDEN == 2): arithmetic shift keeps the sign in bit 31, the mask clears the three
+// sign copies below it, the add re-biases the exponent (127 -> 1023): SHF.R.S32 + LOP3 + IADD3 + SHL per value.
+// Inf/NaN inputs are caught separately by the caller (nonfinite_probe on the idle FP32 pipe).
+__device__ __forceinline__ double widen_lean(float x) {
+  const int u = __float_as_int(x);
+  const uint32_t hi = ((uint32_t)(u >> 3) & 0x8fffffffu) + 0x38000000u;
+  return __hiloint2double((int)hi, (int)((uint32_t)u << 29));
+}
+// acc stays 0 while every x seen is finite; 0 * Inf = 0 * NaN = NaN poisons it otherwise (one FFMA on the FP32 pipe)
+__device__ __forceinline__ void nonfinite_probe(float x, float& acc) { acc = __fmaf_rn(x, 0.0f, acc); }
+
+// float64 power -> float32 on the integer pipe (TDSA_INT_NARROW): clamp the high word to [2^-126, NaN pattern]
+// (unsigned, so a NaN with the sign bit set stays NaN), re-bias the exponent, funnel-shift the top 23 mantissa bits
+// in. Truncation instead of rounding: relative error < 2^-23, i.e. < 5.2e-7 dB after the log.
+// Values >= 2^128 (|X| > 1.8e19) and NaN both come out as NaN.
+#ifndef TDSA_INT_NARROW
+#define TDSA_INT_NARROW 0
+#endif
+__device__ __forceinline__ float narrow_trunc(double p) {
+  uint32_t hi = (uint32_t)__double2hiint(p);
+  const uint32_t lo = (uint32_t)__double2loint(p);
+  hi = min(max(hi, 0x38100000u), 0x47f80000u) - 0x38000000u;
+  return __uint_as_float(__funnelshift_l(lo, hi, 3));
+}
+template <typename T> __device__ __forceinline__ float narrow_power(T p);
+template <> __device__ __forceinline__ float narrow_power<float>(float p) { return p; }
+template <> __device__ __forceinline__ float narrow_power<double>(double p) {
+#if TDSA_INT_NARROW
+  return narrow_trunc(p);
+#else
+  return (float)p;
+#endif
+}
+
 // widen_fast that also keeps the running maximum of the magnitude bits (>= 0x7f800000 <=> an Inf or NaN was seen)
 __device__ __forceinline__ double widen_track(float x, uint32_t& top) {
   const uint32_t u = __float_as_uint(x);
@@ -452,7 +486,7 @@ template <typename T, bool MAG20> __device__ __forceinline__ float to_db_m(T p, 
   } else {
     // narrow once, then scale and add the floor (1e-10 / 1e-12) with one float32 FMA: 6e-8 relative on the
     // argument of the log is 2.6e-7 dB, and it keeps 16 multiplies per thread off the FP64 pipe
-    const float v = __fmaf_rn((float)p, (float)ep.scale, (float)ep.floor);
+    const float v = __fmaf_rn(narrow_power<T>(p), (float)ep.scale, (float)ep.floor);
     return kDbPerLog2 * lg2_approx(v);
   }
 }

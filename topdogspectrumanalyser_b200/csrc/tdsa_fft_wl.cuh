@@ -160,7 +160,19 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       float2 v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(src + j * 2048);
-      if constexpr (sizeof(T) == 8 && TDSA_INT_WIDEN) {
+      if constexpr (sizeof(T) == 8 && TDSA_INT_WIDEN == 2) {
+        float probe = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          nonfinite_probe(v[j].x, probe); nonfinite_probe(v[j].y, probe);
+          re[j] = widen_lean(v[j].x); im[j] = widen_lean(v[j].y);
+        }
+        if (probe != probe) re[0] = (T)probe;                // an Inf/NaN sample: the whole frame becomes NaN, as in the reference
+        if constexpr (HAS_DC) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { re[j] -= dcr; im[j] -= dci; }
+        }
+      } else if constexpr (sizeof(T) == 8 && TDSA_INT_WIDEN == 1) {
         // integer-pipe widening; the largest |bits| seen tells whether an Inf/NaN went through (exponent 0xFF)
         uint32_t top = 0;
 #pragma unroll

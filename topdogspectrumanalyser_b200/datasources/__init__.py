@@ -1,5 +1,8 @@
 from .base import SampleDataSource, AveragerSettings, IN_REFERENCE_APP
-from .b200_samples import B200SampleDataSource, HackrfChunkFeed, ReplayFeed, SyntheticIQFeed, register_with_source_manager
+from .feeds import ChunkRingFeed, HackrfDeviceFeed, ReplayFeed, SyntheticIQFeed, open_rtlsdr
+from .b200_samples import (B200HackrfSamples, B200RtlSamples, B200SampleDataSource, HackrfChunkFeed, install_backend,
+                           uninstall_backend)
 
-__all__ = ["SampleDataSource", "AveragerSettings", "IN_REFERENCE_APP", "B200SampleDataSource",
-           "SyntheticIQFeed", "HackrfChunkFeed", "ReplayFeed", "register_with_source_manager"]
+__all__ = ["SampleDataSource", "AveragerSettings", "IN_REFERENCE_APP", "B200SampleDataSource", "B200RtlSamples",
+           "B200HackrfSamples", "SyntheticIQFeed", "ChunkRingFeed", "HackrfChunkFeed", "HackrfDeviceFeed", "ReplayFeed",
+           "open_rtlsdr", "install_backend", "uninstall_backend"]

@@ -18,142 +18,11 @@ import torch
 from .. import _lib as L
 from ..engine import LOG_FLOOR, POWER_LOG_FLOOR, SpectrumPlan, TraceState
 from .base import IN_REFERENCE_APP, AveragerSettings, SampleDataSource
+from .feeds import ChunkRingFeed, HackrfDeviceFeed, ReplayFeed, SyntheticIQFeed, open_rtlsdr  # noqa: F401
+
+HackrfChunkFeed = ChunkRingFeed          # round-1 name of the streaming feed
 
 logger = logging.getLogger(__name__)
-
-
-class SyntheticIQFeed:
-    """Seeded complex64 IQ with pyrtlsdr's surface: AWGN plus one tone (for tests and demos)."""
-
-    def __init__(self, sample_rate: float = 2.048e6, centre_freq: float = 98e6, tone_hz: float = 250e3,
-                 tone_amp: float = 0.5, seed: int = 0):
-        self.sample_rate, self.center_freq = float(sample_rate), float(centre_freq)
-        self.tone_hz, self.tone_amp = tone_hz, tone_amp
-        self.rng = np.random.default_rng(seed)
-        self.t0 = 0
-        self.gain = "auto"
-
-    def get_sample_rate(self):
-        return self.sample_rate
-
-    def get_center_freq(self):
-        return self.center_freq
-
-    def read_samples(self, n: int) -> np.ndarray:
-        s = np.float32(np.sqrt(0.5))
-        x = np.empty(n, dtype=np.complex64)
-        x.real = self.rng.standard_normal(n, dtype=np.float32) * s
-        x.imag = self.rng.standard_normal(n, dtype=np.float32) * s
-        t = np.arange(self.t0, self.t0 + n, dtype=np.float64)
-        x += (self.tone_amp * np.exp(2j * np.pi * self.tone_hz * t / self.sample_rate)).astype(np.complex64)
-        self.t0 += n
-        return x
-
-    def close(self):
-        pass
-
-
-class ReplayFeed:
-    """Feed that hands out pre-recorded frames one per ``read_samples`` call (file replay, tests).
-
-    ``dtype`` is what the device library would return: complex128 for pyrtlsdr, complex64 for pyhackrf."""
-
-    def __init__(self, frames, sample_rate: float, centre_freq: float, dtype=np.complex128):
-        self.frames, self.i, self.dtype = frames, 0, dtype
-        self.fs, self.fc = float(sample_rate), float(centre_freq)
-        self.sample_rate, self.center_freq, self.gain = self.fs, self.fc, "auto"
-
-    def get_sample_rate(self):
-        return self.fs
-
-    def get_center_freq(self):
-        return self.fc
-
-    def read_samples(self, n: int):
-        f = self.frames[self.i]
-        self.i += 1
-        if len(f) != n:
-            raise ValueError(f"replay frame has {len(f)} samples, {n} requested")
-        return np.asarray(f).astype(self.dtype)
-
-    def close(self):
-        pass
-
-
-class HackrfChunkFeed:
-    """Feed with the reference HackRF source's consume policy (datasources/hackrf_samples.py:28-29,254-305).
-
-    A reader thread ``put``s 65 536-sample chunks into a depth-4 queue (oldest dropped when full, :221-237);
-    ``read_samples(n)`` drains the queue keeping only the newest chunk as reservoir and hands out the LAST n
-    samples of it, shrinking the reservoir from the end; returns ``None`` after ``timeout`` seconds without data.
-    """
-    READ_CHUNK, MAX_QUEUE_SIZE, CONSUME_TIMEOUT = 65536, 4, 0.5
-
-    def __init__(self, sample_rate: float, centre_freq: float, timeout: Optional[float] = None):
-        import queue
-        self._queue_mod = queue
-        self.sample_rate, self.center_freq = float(sample_rate), float(centre_freq)
-        self._q = queue.Queue(maxsize=self.MAX_QUEUE_SIZE)
-        self._reservoir = np.array([], dtype=np.complex64)
-        self.timeout = self.CONSUME_TIMEOUT if timeout is None else timeout
-        self.stats = {"samples_dropped": 0, "queue_overflows": 0}
-        self.gain = None
-
-    def get_sample_rate(self):
-        return self.sample_rate
-
-    def get_center_freq(self):
-        return self.center_freq
-
-    def put(self, chunk: np.ndarray) -> None:
-        """Producer side: non-blocking put, drop the OLDEST chunk on overflow (:221-237)."""
-        try:
-            self._q.put(chunk, block=False)
-        except self._queue_mod.Full:
-            try:
-                old = self._q.get_nowait()
-                self.stats["samples_dropped"] += len(old)
-                self.stats["queue_overflows"] += 1
-            except self._queue_mod.Empty:
-                pass
-            self._q.put(chunk, block=False)
-
-    def read_samples(self, count: int):
-        import time
-        if count <= 0:
-            return np.array([], dtype=np.complex64)
-        fresh = None
-        while True:                                               # :269-276
-            try:
-                fresh = self._q.get_nowait()
-            except self._queue_mod.Empty:
-                break
-        if fresh is not None:
-            self._reservoir = fresh
-        if len(self._reservoir) >= count:                         # :281-284
-            result = self._reservoir[-count:]
-            self._reservoir = self._reservoir[:-count]
-            return result
-        start = time.time()
-        while len(self._reservoir) < count:                       # :287-301
-            if time.time() - start > self.timeout:
-                return None
-            try:
-                chunk = self._q.get(timeout=0.01)
-                while True:
-                    try:
-                        chunk = self._q.get_nowait()
-                    except self._queue_mod.Empty:
-                        break
-                self._reservoir = chunk
-            except self._queue_mod.Empty:
-                continue
-        result = self._reservoir[-count:]
-        self._reservoir = self._reservoir[:-count]
-        return result
-
-    def close(self):
-        pass
 
 
 class B200SampleDataSource(SampleDataSource):
@@ -175,8 +44,11 @@ class B200SampleDataSource(SampleDataSource):
         self.running = False
         self.last_sample_rate = sample_rate
         self.sdr = feed                          # same attribute name as RtlSamplesDataSource
+        self._owns_feed = False                  # True when start() opened the device itself
         self._gain = "auto"
+        self.lna_gain, self.vga_gain, self.amplifier = 16, 20, True          # hackrf_samples.py:45-47
         self._flush_reads_remaining = 0
+        self._h2d_done: Optional[torch.cuda.Event] = None
         self._device_name = device
         self._plan: Optional[SpectrumPlan] = None
         self._state: Optional[TraceState] = None
@@ -240,45 +112,85 @@ class B200SampleDataSource(SampleDataSource):
             return "mag20", LOG_FLOOR                                 # hackrf_samples.py:383
         return "power", POWER_LOG_FLOOR                               # rtl_samples.py:184 / hackrf_samples.py:381
 
+    def _open_own_feed(self):
+        """No feed was injected: open the device this style stands for (what the reference's start() does)."""
+        if self.style == "rtl":
+            return open_rtlsdr(self.sample_rate, self.centre_freq, self._gain)            # rtl_samples.py:42-46
+        feed = HackrfDeviceFeed(self.sample_rate, self.centre_freq, self.lna_gain, self.vga_gain, self.amplifier)
+        feed.open()                                                                        # hackrf_samples.py:97-104
+        return feed
+
     def start(self, frequency=None):
-        """rtl_samples.py:30-58: span -> sample rate, centre -> centre_freq; RuntimeError on failure."""
+        """Contract of rtl_samples.py:30-58 / hackrf_samples.py:82-106: the span becomes the sample rate, the hardware's
+        actual rate is read back, failures surface as RuntimeError (SourceManager shows them, source_manager.py:490-494)."""
         if frequency:
-            self.centre_freq = int(frequency.centre)
-            self.sample_rate = int(frequency.span)
+            self.centre_freq, self.sample_rate = int(frequency.centre), int(frequency.span)
         if self.running:
             return
         try:
             if self.sdr is None:
-                raise RuntimeError("no IQ feed attached (pass feed=... or set .sdr)")
-            for attr, val in (("sample_rate", self.sample_rate), ("center_freq", self.centre_freq)):
-                try:
-                    setattr(self.sdr, attr, val)
-                except Exception:
-                    pass
-            actual = self.sdr.get_sample_rate()
-            self.sample_rate = actual
-            self.last_sample_rate = actual
+                self.sdr, self._owns_feed = self._open_own_feed(), True
+            else:
+                self._push_to_feed(sample_rate=self.sample_rate, center_freq=self.centre_freq)
+                if isinstance(self.sdr, HackrfDeviceFeed):
+                    self.sdr.open()
+            self.sample_rate = self.last_sample_rate = self.sdr.get_sample_rate()
             self._ensure_plan()
-            self.running = True
         except Exception as e:
             self.running = False
+            if self._owns_feed:
+                self._drop_feed()
             logger.error("B200 source initialisation failed: %s", e)
-            raise RuntimeError(f"B200 source initialisation failed: {e}")
+            raise RuntimeError(f"B200 source initialisation failed: {e}") from e
+        self.running = True
+
+    def _push_to_feed(self, **settings) -> None:
+        """Best-effort attribute pushes for feeds that are plain objects (replay, synthetic)."""
+        for name, value in settings.items():
+            try:
+                setattr(self.sdr, name, value)
+            except Exception:                                  # noqa: BLE001 - a read-only feed is fine
+                pass
+
+    def _drop_feed(self) -> None:
+        feed, self.sdr, self._owns_feed = self.sdr, None, False
+        closer = getattr(feed, "close", None)
+        if closer is not None:
+            try:
+                closer()
+            except Exception as e:                             # noqa: BLE001
+                logger.error("Error closing feed: %s", e)
+
+    @property
+    def thread(self):
+        """Reader thread, if the feed has one (SourceManager joins it, source_manager.py:361-369)."""
+        return getattr(self.sdr, "thread", None)
+
+    @thread.setter
+    def thread(self, value):
+        pass
 
     def pause(self):
-        self.running = False
+        self.running = False                                   # device stays open (rtl_samples.py:60-63)
 
     def resume(self):
-        if self.sdr is not None:
-            self.running = True
+        self.running = self.sdr is not None or self.running    # nothing to resume without a device (:65-71)
 
     def stop(self):
-        if self.sdr is not None and hasattr(self.sdr, "close"):
-            try:
-                self.sdr.close()
-            except Exception as e:
-                logger.error("Error closing feed: %s", e)
+        """Close the feed. A feed this object opened itself is forgotten, so the next start() opens a fresh one
+        (rtl_samples.py:73-82); an injected feed stays attached for tests that restart the source."""
         self.running = False
+        if self.sdr is None:
+            return
+        if self._owns_feed:
+            self._drop_feed()
+        else:
+            closer = getattr(self.sdr, "close", None)
+            if closer is not None:
+                try:
+                    closer()
+                except Exception as e:                         # noqa: BLE001
+                    logger.error("Error closing feed: %s", e)
 
     # ---- configuration (same names as the reference sources) ---------------------------------
     def set_window_type(self, window_type: str):
@@ -336,41 +248,73 @@ class B200SampleDataSource(SampleDataSource):
         if self._state is not None:
             self._state.reset_averaging()
 
-    def update_centre_frequency(self, centre_freq: float):
-        """rtl_samples.py:85-105 (flush count included)."""
-        if not self.running:
+    # ---- re-tuning: one path, three public spellings -------------------------------------------------------
+    _PLL_SETTLE_S = 0.006        # reads discarded after a centre change cover this much signal (rtl_samples.py:99-101)
+
+    def _retune(self, rate: Optional[int] = None, centre: Optional[int] = None) -> None:
+        """Re-program the feed. ``rate`` / ``centre`` are None when that quantity is not being changed.
+
+        rtl style (rtl_samples.py:85-146): the dongle is re-programmed in place; a new rate is read back from the
+        hardware and the centre is written again afterwards because the tuner may shift with the rate (:125-129);
+        a new centre schedules max(3, 6 ms worth) of discarded reads.
+        hackrf style (hackrf_samples.py:460-548): streaming stops, the device is re-programmed, buffered chunks and
+        the held frame are dropped, the DC estimate survives."""
+        live = self.running and self.sdr is not None
+        if self.style == "hackrf":
+            if rate is not None:
+                self.sample_rate = self.last_sample_rate = rate
+            if centre is not None:
+                self.centre_freq = centre
+            self._last_good_power = None
+            if live:
+                if hasattr(self.sdr, "retune"):
+                    self.sdr.retune(rate, centre)
+                else:
+                    self._push_to_feed(**({"sample_rate": rate} if rate is not None else {}),
+                                       **({"center_freq": centre} if centre is not None else {}))
+                    if hasattr(self.sdr, "flush"):
+                        self.sdr.flush()
             return
-        centre_freq = int(centre_freq)
-        if centre_freq == self.centre_freq:
-            return
-        self.centre_freq = centre_freq
         try:
-            self.sdr.center_freq = centre_freq
-            self._flush_reads_remaining = max(3, int(0.006 * self.sample_rate / self.fft_size))
+            if rate is not None:
+                if live:
+                    self.sdr.sample_rate = rate
+                    self.sample_rate = self.last_sample_rate = self.sdr.get_sample_rate()
+                    self.sdr.center_freq = self.centre_freq if centre is None else centre
+                    self.centre_freq = self.sdr.get_center_freq()
+                    if centre is not None:
+                        centre = None if int(self.centre_freq) == centre else centre
+                else:
+                    self.sample_rate = rate
+            if centre is not None and live:
+                self.centre_freq = centre
+                self.sdr.center_freq = centre
+                self._flush_reads_remaining = max(3, int(self._PLL_SETTLE_S * self.sample_rate / self.fft_size))
         except Exception as e:
-            raise RuntimeError(f"Error updating centre frequency: {e}")
+            what = "sample rate" if rate is not None else "centre frequency"
+            logger.error("Error updating %s: %s", what, e)
+            raise RuntimeError(f"Error updating {what}: {e}") from e
+
+    def update_centre_frequency(self, centre_freq: float):
+        centre = int(centre_freq)
+        if centre == self.centre_freq or (self.style == "rtl" and not self.running):
+            return                                             # rtl ignores a re-tune while stopped (:87-89)
+        self._retune(centre=centre)
 
     def update_sample_rate(self, sample_rate: float):
-        sample_rate = int(sample_rate)
-        if sample_rate == self.last_sample_rate:
-            return
-        if self.running and self.sdr is not None:
-            try:
-                self.sdr.sample_rate = sample_rate
-                actual = self.sdr.get_sample_rate()
-                self.sample_rate = actual
-                self.last_sample_rate = actual
-            except Exception as e:
-                raise RuntimeError(f"Error updating sample rate: {e}")
-        else:
-            self.sample_rate = sample_rate
+        rate = int(sample_rate)
+        if rate != self.last_sample_rate:
+            self._retune(rate=rate)
 
     def update_frequency(self, sample_rate: float, centre_freq: float):
-        sample_rate, centre_freq = int(sample_rate), int(centre_freq)
-        if sample_rate != self.last_sample_rate:
-            self.update_sample_rate(sample_rate)
-        if centre_freq != self.centre_freq:
-            self.update_centre_frequency(centre_freq)
+        rate, centre = int(sample_rate), int(centre_freq)
+        if self.style == "hackrf":                             # one stop/re-program/start for both (:520-548)
+            rate_new, centre_new = rate != self.last_sample_rate, centre != self.centre_freq
+            if rate_new or centre_new:
+                self._retune(rate if rate_new else None, centre if centre_new else None)
+            return
+        self.update_sample_rate(rate)                          # rtl_samples.py:136-146: rate first, then centre
+        self.update_centre_frequency(centre)
 
     # ---- the hot call -----------------------------------------------------------------------
     def _zeros(self):
@@ -439,8 +383,13 @@ class B200SampleDataSource(SampleDataSource):
         mode, floor = self._mode_and_floor()
         if (plan.mode, plan.log_floor, plan.fs) != (mode, floor, float(fs)):
             plan.set_mode(mode, floor, float(fs))
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()                       # the previous frame's async copy has left the staging buffer
         self._pin_in.numpy()[:] = samples                      # complex128 feeds narrow to complex64 here
         self._x_dev.copy_(self._pin_in, non_blocking=True)
+        if self._h2d_done is None:
+            self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record()
         x = self._x_dev.view(1, self.fft_size)
         st = self._state
         st.avg_mode, st.avg_n = self._avg_settings.mode, self._avg_settings.n
@@ -474,16 +423,81 @@ class B200SampleDataSource(SampleDataSource):
         return plan.psd_db_host(iq), self._bins(fs, fc)
 
 
-def register_with_source_manager(source_type: str = "b200_samples", display_name: str = "B200 Samples",
-                                 like: str = "rtl_samples"):
-    """Add this backend to the reference's registry (core/source_manager.py:24-70) without editing it.
+class B200RtlSamples(B200SampleDataSource):
+    """What ``SourceManager._initialise_rtl_samples`` constructs when the B200 backend is installed:
+    ``cls(sample_rate=span, centre_freq=centre)`` (core/source_manager.py:554-572). Opens the RTL-SDR itself."""
 
-    Only meaningful inside the reference application; returns the SourceManager class.
+    def __init__(self, sample_rate: int, centre_freq: int, feed=None, **kw):
+        super().__init__(sample_rate, centre_freq, feed=feed, style="rtl", **kw)
+
+
+class B200HackrfSamples(B200SampleDataSource):
+    """Replacement for ``HackrfSamplesDataSource`` in ``SourceManager._initialise_hackrf_samples``
+    (core/source_manager.py:535-552), which sets ``lna_gain`` / ``vga_gain`` before ``start()``."""
+
+    def __init__(self, sample_rate: int, centre_freq: int, feed=None, **kw):
+        super().__init__(sample_rate, centre_freq, feed=feed, style="hackrf", **kw)
+
+    def set_gains(self, lna_gain=None, vga_gain=None):         # hackrf_samples.py:624-649
+        if lna_gain is not None:
+            self.lna_gain = lna_gain
+        if vga_gain is not None:
+            self.vga_gain = vga_gain
+        if hasattr(self.sdr, "set_gains"):
+            self.sdr.set_gains(lna_gain, vga_gain)
+
+    def set_amplifier(self, enabled: bool):                    # hackrf_samples.py:656-666
+        self.amplifier = bool(enabled)
+        if hasattr(self.sdr, "set_amplifier"):
+            self.sdr.set_amplifier(enabled)
+
+    def set_dc_alpha(self, alpha: float) -> None:              # hackrf_samples.py:651-654
+        self._DC_ALPHA = max(0.0, min(1.0, float(alpha)))
+
+    def get_stats(self) -> dict:                               # hackrf_samples.py:679-696 (the counters the feed keeps)
+        stats = dict(getattr(self.sdr, "stats", {}))
+        stats.update(is_running=self.running, num_samples=self.fft_size, sample_rate=self.sample_rate,
+                     centre_freq=self.centre_freq, queue_size=getattr(self.sdr, "pending", 0),
+                     queue_capacity=getattr(self.sdr, "SLOTS", 0))
+        return stats
+
+
+BACKEND_ENV = "TDSA_BACKEND"
+
+
+def install_backend(force: bool = False):
+    """Make the reference application use the B200 backend for its two IQ sample sources.
+
+    ``SourceManager.set_source`` validates the id against ``SOURCE_CLASSES`` and then constructs through a fixed
+    ``if/elif`` over the five built-in ids (core/source_manager.py:389-448), so a NEW id is never constructed; the
+    backend therefore REPLACES the classes behind ``"rtl_samples"`` and ``"hackrf_samples"``.  The replacements are
+    registered as virtual subclasses of the classes they stand in for, because ``SourceManager`` branches on
+    ``isinstance(src, RtlSamplesDataSource / HackrfSamplesDataSource)`` (:319, :254-257).
+
+    Active when ``TDSA_BACKEND=b200`` or ``force``; returns the ``SourceManager`` class, or None
+    when the switch is off.  Only meaningful with the reference's root on ``sys.path``.
     """
-    from core.source_manager import SourceManager          # type: ignore  (reference module)
-    SourceManager.SOURCE_CLASSES[source_type] = B200SampleDataSource
-    SourceManager.SOURCE_DISPLAY_NAMES[source_type] = display_name
-    SourceManager._SAMPLE_SOURCES = frozenset(set(SourceManager._SAMPLE_SOURCES) | {source_type})
-    SourceManager._SOURCE_LIMITS[source_type] = dict(SourceManager._SOURCE_LIMITS[like])
-    SourceManager._SOURCE_DEFAULTS[source_type] = dict(SourceManager._SOURCE_DEFAULTS[like])
+    import os
+    if not force and os.environ.get(BACKEND_ENV, "").lower() != "b200":
+        return None
+    from core.source_manager import SourceManager              # type: ignore  (reference module)
+    from datasources.hackrf_samples import HackrfSamplesDataSource   # type: ignore
+    from datasources.rtl_samples import RtlSamplesDataSource   # type: ignore
+    RtlSamplesDataSource.register(B200RtlSamples)
+    HackrfSamplesDataSource.register(B200HackrfSamples)
+    if not IN_REFERENCE_APP:                                   # this package was imported before the reference's root was on sys.path
+        from datasources.base import SampleDataSource as RefBase   # type: ignore
+        RefBase.register(B200SampleDataSource)
+    SourceManager.SOURCE_CLASSES["rtl_samples"] = B200RtlSamples
+    SourceManager.SOURCE_CLASSES["hackrf_samples"] = B200HackrfSamples
+    return SourceManager
+
+
+def uninstall_backend():
+    """Put the reference's own classes back (tests)."""
+    from core.source_manager import SourceManager              # type: ignore
+    from datasources.hackrf_samples import HackrfSamplesDataSource   # type: ignore
+    from datasources.rtl_samples import RtlSamplesDataSource   # type: ignore
+    SourceManager.SOURCE_CLASSES["rtl_samples"] = RtlSamplesDataSource
+    SourceManager.SOURCE_CLASSES["hackrf_samples"] = HackrfSamplesDataSource
     return SourceManager

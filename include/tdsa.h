@@ -131,11 +131,35 @@ int tdsa_psd_db_avg_hold(tdsa_handle_t h, const void* iq, int64_t n_frames, int6
 
 /* tdsa_psd_db_avg_hold with the HackRF front end of tdsa_psd_db_batch_dc in front of it
  * (hackrf_samples.py:351-381): silent frames update nothing and repeat the previous row;
- * silent_out: device int32[n_frames]. Synchronises the stream once per chunk (reads the flags). */
+ * silent_out: device int32[n_frames]. Synchronises the stream once (the host scalars depend on how many frames were
+ * live); tdsa_psd_db_avg_hold_dev does not. */
 int tdsa_psd_db_avg_hold_dc(tdsa_handle_t h, const void* iq, int64_t n_frames, int64_t frame_stride,
                             double dc_alpha, double* dc_state, int32_t* silent_out, int avg_mode, int avg_n,
                             double* avg_state, int32_t* count_state_host, float* max_hold,
                             float* min_hold, int32_t* hold_valid_host, int last_only, float* db_out);
+
+/* Device-resident flavour of tdsa_psd_db_avg_hold[_dc]: nothing is read back, the call is fully asynchronous.
+ * flags_dev: DEVICE int32[TDSA_FLAG_WORDS], the scalars the reference keeps in Python attributes:
+ *   [TDSA_FLAG_COUNT] TraceAverager._count (0 = empty buffer), [TDSA_FLAG_MAX_VALID] / [TDSA_FLAG_MIN_VALID] "hold
+ *   initialised", [TDSA_FLAG_LIVE] live (non-silent) frames folded by the last call; zero the block to reset.
+ * last_row_dev: DEVICE float32[n_fft] or NULL: last good dB row, carried across calls; silent frames repeat it
+ *   (hackrf_samples.py:351-355).  use_dc != 0 puts the HackRF front end of tdsa_psd_db_batch_dc in front.
+ * Large batches take a fused path when the request is order-free (running average with last_only and no holds;
+ * holds without averaging): the FFT kernel's accumulating epilogue keeps per-bin sums / maxima / minima in tensor
+ * memory and a finish kernel folds them into the state, moving 8 B per input sample (+ 4 B per stored dB value).
+ * Everything else scans float64 rows that are produced and consumed in L2-sized chunks. */
+#define TDSA_FLAG_COUNT 0
+#define TDSA_FLAG_MAX_VALID 1
+#define TDSA_FLAG_MIN_VALID 2
+#define TDSA_FLAG_LIVE 3
+#define TDSA_FLAG_TARE_COLLECTING 4
+#define TDSA_FLAG_TARE_ACTIVE 5
+#define TDSA_FLAG_TARE_COUNT 6
+#define TDSA_FLAG_WORDS 8
+int tdsa_psd_db_avg_hold_dev(tdsa_handle_t h, const void* iq, int64_t n_frames, int64_t frame_stride, int use_dc,
+                             double dc_alpha, double* dc_state, int32_t* silent_out, int avg_mode, int avg_n,
+                             double* avg_state, float* max_hold, float* min_hold, int32_t* flags_dev,
+                             float* last_row_dev, int last_only, float* db_out);
 
 /* Config 4 (per sub-band rows): iq holds n_groups * frames_per_group contiguous frames; each
  * group is averaged in the linear domain as TraceAverager('lin', n >= frames_per_group) does
@@ -155,7 +179,8 @@ int tdsa_welch(tdsa_handle_t h, const void* iq_stream, int64_t n_samples, int64_
  * cal offset (display_data_processor.py:317-327), sweep-domain averaging (:214-218),
  * max/min hold (:371-395). rows: float32 [n_rows][width]. Any state pointer may be NULL.
  * row_flags_scratch: device int32[n_rows] work area. Rows that are entirely NaN are skipped
- * (display_data_processor.py:211). Synchronises the stream once (reads the row flags). */
+ * (display_data_processor.py:211). Synchronises the stream once (the host scalars depend on how many rows were live);
+ * tdsa_trace_update_dev does not. */
 int tdsa_trace_update(const float* rows, int64_t n_rows, int64_t width, double cal_offset_db,
                       int avg_mode, int avg_n, double* avg_state, int32_t* count_state_host,
                       float* max_hold, float* min_hold, int32_t* hold_valid_host, float* rows_out,
@@ -172,6 +197,14 @@ int tdsa_trace_update_tare(const float* rows, int64_t n_rows, int64_t width, dou
                            void* cuda_stream, int32_t* row_flags_scratch, int32_t* tare_flags_host,
                            int32_t* tare_count_host, int tare_target, double* tare_buf,
                            double* tare_baseline);
+
+/* Device-resident flavour of tdsa_trace_update_tare: the flag block (see tdsa_psd_db_avg_hold_dev; the tare words are
+ * TareState.collecting / .active / .count) lives on the device, nothing is read back, no synchronisation.
+ * tare_buf / tare_baseline may be NULL when tare is not used. */
+int tdsa_trace_update_dev(const float* rows, int64_t n_rows, int64_t width, double cal_offset_db, int avg_mode,
+                          int avg_n, double* avg_state, float* max_hold, float* min_hold, int32_t* flags_dev,
+                          float* rows_out, void* cuda_stream, int32_t* row_flags_scratch, int tare_target,
+                          double* tare_buf, double* tare_baseline);
 
 /* Waterfall colour map, core/export_manager.py:72-79: index = uint8(clip((x - lo)/max(hi - lo, 1e-9), 0, 1) * 255)
  * in float32, rgba_out[i] = lut_rgba[index] (lut: device uint8[256][4]; rgba_out: device uint8[n][4]). */
@@ -219,6 +252,26 @@ int tdsa_stitch(const float* rows, const double* row_lo_hz, double row_hz, int64
  * *ptr_host is read and updated on the host (it is a scalar of widget state). */
 int tdsa_ring_push(const float* rows, int64_t n_rows, float* ring, int64_t H, int64_t W,
                    int64_t* ptr_host, void* cuda_stream);
+
+/* tdsa_ring_push with the widget's duplicate filter (displays/waterfall.py:330-336: a row identical to the previous
+ * one, np.array_equal semantics, is not added) and the write pointer on the device, because the number of new rows is
+ * only known there.  state_dev: DEVICE int64[4] = {ptr, has_last, rows added by the last call, -}; zero it to reset.
+ * last_row_dev: DEVICE float32[W], the last row added (may be NULL when dedupe == 0).
+ * slot_scratch: DEVICE int64[n_rows]; differs_scratch: DEVICE int32[n_rows] (dedupe only). Asynchronous. */
+int tdsa_ring_push_dev(const float* rows, int64_t n_rows, float* ring, int64_t H, int64_t W, int64_t* state_dev,
+                       float* last_row_dev, int dedupe, int64_t* slot_scratch, int32_t* differs_scratch,
+                       void* cuda_stream);
+
+/* The ring's display view (displays/waterfall.py:179-180: rows ptr .. ptr+H, newest first) colour-mapped to the RGBA
+ * image core/export_manager.py:67-84 builds: rgba_out uint8 [H][W][4]; lut_rgba: device uint8[256][4]. */
+int tdsa_ring_image_rgba(const float* ring, int64_t H, int64_t W, const int64_t* state_dev, float lo_db, float hi_db,
+                         const uint8_t* lut_rgba, uint8_t* rgba_out, void* cuda_stream);
+
+/* Marker snap, core/marker_manager.py:74-99: scipy.signal.find_peaks(levels, height, prominence, distance) and the
+ * position of the highest surviving peak; np.argmax(levels) when none survives. width <= 16384.
+ * out: DEVICE int32[3] = {bin index, number of surviving peaks, 1 if the argmax fallback was used}. */
+int tdsa_find_peaks_snap(const float* levels, int64_t width, float height, float prominence, int distance,
+                         int32_t* out, void* cuda_stream);
 
 /* Pinned-host -> device copy on a side stream with a completion event (config 5).
  * done_event may be NULL. */

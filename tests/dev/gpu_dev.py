@@ -29,7 +29,7 @@ def stats(n, prec, b=4):
 
 sizes = [64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536]
 if len(sys.argv) > 1 and sys.argv[1] == "quick":
-    sizes = [1024, 4096]
+    sizes = [1024, 4096, 8192]
 for n in sizes:
     for prec in ("f64", "f32"):
         stats(n, prec)

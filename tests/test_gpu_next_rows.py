@@ -111,7 +111,7 @@ def test_top_peaks_matches_reference(dev, golden):
     plan.close()
 
 
-def test_frame_pipeline_matches_reference_sequence(dev, golden):
+def test_frame_pipeline_matches_reference_sequence(dev, golden, parity_log):
     """source -> cal -> tare -> holds -> peaks on the device vs the same chain of reference primitives."""
     from topdogspectrumanalyser_b200 import synth
     from topdogspectrumanalyser_b200.datasources import B200SampleDataSource, ReplayFeed
@@ -125,6 +125,7 @@ def test_frame_pipeline_matches_reference_sequence(dev, golden):
     pipe.max_peak_search_enabled = pipe.min_hold_enabled = True
     w = O.make_window("hanning", n)
     tare, mx, mn = O.Tare(), None, None
+    worst = 0.0
     for i, f in enumerate(iq):
         if i == 3:
             pipe.start_tare()
@@ -134,11 +135,12 @@ def test_frame_pipeline_matches_reference_sequence(dev, golden):
         db = tare.apply(db)
         mx = O.max_hold_update(mx, db.copy())
         mn = O.min_hold_update(mn, db.copy())
-        assert np.abs(pipe.live_power_levels - db).max() <= 2e-4
-        assert np.abs(pipe.max_power_levels - mx).max() <= 2e-4
-        assert np.abs(pipe.min_power_levels - mn).max() <= 2e-4
+        worst = max(worst, np.abs(pipe.live_power_levels - db).max(), np.abs(pipe.max_power_levels - mx).max(),
+                    np.abs(pipe.min_power_levels - mn).max())
         assert pipe.tare_active == tare.active
-    assert tare.active and np.abs(pipe.baseline_power_levels - tare.baseline).max() <= 2e-4
+    worst = max(worst, np.abs(pipe.baseline_power_levels - tare.baseline).max())
+    parity_log("frame_pipeline_live_holds_tare", worst, tol=1e-4)
+    assert tare.active and worst <= 1e-4
     assert 1 <= len(pipe.peaks) <= 5 and all(pipe.frequency_bins[0] <= f <= pipe.frequency_bins[-1] for f, _ in pipe.peaks)
     # size change drops the holds like the reference's shape-mismatch rule (display_data_processor.py:375-377)
     src.sdr = ReplayFeed(synth.cfg2_frames(b=2, n=2048, seed=92), fs, fc)

@@ -91,7 +91,7 @@ def test_datasource_setters_follow_reference_semantics(dev, golden):
     assert not p.any()
 
 
-def test_datasource_hackrf_style(dev, golden):
+def test_datasource_hackrf_style(dev, golden, parity_log):
     """DC removal + RMS-normalised float32 Hann + the three dB branches + silence hold."""
     g = golden("hackrf_chain.npz")
     fs, fc = float(g["fs"]), float(g["fc"])
@@ -116,12 +116,15 @@ def test_datasource_hackrf_style(dev, golden):
         if avg:
             src.set_averaging(*avg)
         want = truth(use_psd, avg)
+        worst = 0.0
         for i in range(len(want)):
             p, bins = src.get_power_levels()
             assert p.dtype == np.float32
-            assert np.abs(p.astype(np.float64) - want[i]).max() <= 2e-4, (key, i)   # float32 result rows
+            worst = max(worst, float(np.abs(p.astype(np.float64) - want[i]).max()))
             strong = g[key][i] > g[key][i].max() - 60
             assert np.abs(p - g[key][i])[strong].max() < 5e-3                       # executed reference (f32 FFT)
+        parity_log(f"hackrf_chain_{key}_vs_f64_oracle", worst, tol=TOL_DB)
+        assert worst <= TOL_DB, (key, worst)                                        # north_star's bar, no slack
         np.testing.assert_array_equal(bins, g["bins"])
 
 

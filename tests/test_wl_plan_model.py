@@ -18,6 +18,13 @@ def test_three_passes_reproduce_the_dft():
     assert np.abs(M.model_fft(x) - np.fft.fft(x)).max() < 1e-10
 
 
+def test_two_engine_8192_plan_reproduces_the_dft():
+    """Radix-2 DIF on the staged read + half-bin tables on engine 1 (csrc/tdsa_fft_wl.cuh, NB = 2)."""
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal(8192) + 1j * rng.standard_normal(8192)
+    assert np.abs(M.model_fft8192(x) - np.fft.fft(x)).max() < 1e-10
+
+
 def test_thread_identity_and_window_permutation():
     ids = [M.thread_identity(t) for t in range(M.TH)]
     assert len(set(ids)) == M.TH and all(0 <= r < 16 and 0 <= c < 16 for r, c in ids)

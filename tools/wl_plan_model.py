@@ -69,6 +69,46 @@ def model_fft(x):
     return spec
 
 
+def engine_tables(e):
+    """Twiddle tables of engine e (tdsa_api.cu: build_wl_tables): pass B [j][ka] and last pass [j][kk].
+    Engine 0 is the plain 4096-point plan; engine 1 evaluates every table at the half-integer bin k + 1/2."""
+    j = np.arange(16)[:, None]
+    if e == 0:
+        return np.exp(-2j * np.pi * j * np.arange(16)[None, :] / 256), np.exp(-2j * np.pi * j * np.arange(256)[None, :] / 4096)
+    return (np.exp(-2j * np.pi * j * (2 * np.arange(16)[None, :] + 1) / 512),
+            np.exp(-2j * np.pi * j * (2 * np.arange(256)[None, :] + 1) / 8192))
+
+
+def model_fft8192(x):
+    """N = 8192 on two engines: radix-2 DIF on the staged read, engine 0 = even bins (sum), engine 1 = odd bins
+    (difference, half-bin tables, pass-A inputs pre-twiddled by the constants W32^j)."""
+    spec = np.zeros(8192, dtype=np.complex128)
+    w32 = np.exp(-2j * np.pi * np.arange(16) / 32)
+    for e in range(2):
+        s = x[:4096] + (1 - 2 * e) * x[4096:]
+        twb, twl = engine_tables(e)
+        region = np.zeros((16, 272), dtype=np.complex128)
+        y = np.zeros((16, 272), dtype=np.complex128)
+        for tid in range(TH):
+            r, c = thread_identity(tid)
+            inp = np.array([s[r + 16 * c + 256 * j] for j in range(16)])
+            out = dft16(inp * (w32 if e == 1 else 1.0))
+            for q in range(16):
+                region[r, c + 17 * q] = out[q]
+        for tid in range(TH):
+            r, ka = thread_identity(tid)
+            inp = np.array([region[r, 17 * ka + j] for j in range(16)])
+            out = dft16(inp * twb[:, ka])
+            for kb in range(16):
+                y[r, ka + 17 * kb] = out[kb]
+        for kk in range(TH):
+            inp = np.array([y[r, kk + (kk >> 4)] for r in range(16)])
+            out = dft16(inp * twl[:, kk])
+            for q in range(16):
+                spec[2 * (kk + 256 * q) + e] = out[q]
+    return spec
+
+
 def wavefronts(byte_addrs, elem_bytes):
     """Shared-memory wavefronts of one warp-wide access (32 byte addresses), processed in phases of 128/elem lanes."""
     lanes = 128 // elem_bytes
@@ -122,6 +162,8 @@ if __name__ == "__main__":
     rng = np.random.default_rng(0)
     x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
     print("max |model - numpy.fft| =", np.abs(model_fft(x) - np.fft.fft(x)).max())
+    x8 = rng.standard_normal(8192) + 1j * rng.standard_normal(8192)
+    print("max |model8192 - numpy.fft| =", np.abs(model_fft8192(x8) - np.fft.fft(x8)).max())
     print("stage offsets match the 128B swizzle:", check_swizzle())
     print("thread identity is a bijection:", len({thread_identity(t) for t in range(TH)}) == TH)
     for eb in (8, 16):

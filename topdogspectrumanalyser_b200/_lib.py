@@ -46,6 +46,9 @@ SIGNATURES = {
     "tdsa_psd_db_avg_hold": (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _pi32, _vp, _vp, _pi32, _i32, _vp]),
     "tdsa_psd_db_avg_hold_dc": (_i32, [_vp, _vp, _i64, _i64, _f64, _vp, _vp, _i32, _i32, _vp, _pi32, _vp, _vp, _pi32,
                                        _i32, _vp]),
+    "tdsa_psd_db_avg_hold_dev": (_i32, [_vp, _vp, _i64, _i64, _i32, _f64, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32,
+                                        _vp]),
+    "tdsa_trace_update_dev": (_i32, [_vp, _i64, _i64, _f64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "tdsa_group_avg_db": (_i32, [_vp, _vp, _i64, _i64, _vp]),
     "tdsa_welch": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "tdsa_trace_update": (_i32, [_vp, _i64, _i64, _f64, _i32, _i32, _vp, _pi32, _vp, _vp, _pi32, _vp, _vp, _vp]),
@@ -61,6 +64,9 @@ SIGNATURES = {
                                             C.POINTER(C.c_int64)]),
     "tdsa_stitch": (_i32, [_vp, _vp, _f64, _i64, _i64, _f64, _f64, _i64, _vp, _vp, _vp]),
     "tdsa_ring_push": (_i32, [_vp, _i64, _vp, _i64, _i64, C.POINTER(C.c_int64), _vp]),
+    "tdsa_ring_push_dev": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "tdsa_ring_image_rgba": (_i32, [_vp, _i64, _i64, _vp, C.c_float, C.c_float, _vp, _vp, _vp]),
+    "tdsa_find_peaks_snap": (_i32, [_vp, _i64, C.c_float, C.c_float, _i32, _vp, _vp]),
     "tdsa_h2d_async": (_i32, [_vp, _vp, C.c_size_t, _vp, _vp]),
     "tdsa_psd_db_batch_host": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64]),
     "tdsa_plan_info": (_i32, [_vp, _pi32, _pi32, _pi32, _pi32, _pi32]),

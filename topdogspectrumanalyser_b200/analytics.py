@@ -70,3 +70,18 @@ def top_peaks(freq_bins, power_db: torch.Tensor, n: int = 5, min_sep_bins: int =
     k = int(cnt.item())
     ii, pp = idx[:k].cpu().tolist(), pwr[:k].cpu().tolist()
     return [(float(freq_bins[i]), float(p)) for i, p in zip(ii, pp)]
+
+
+def snap_to_peak(freq_bins, levels_db: torch.Tensor, threshold_db: float = -200.0, excursion_db: float = 6.0,
+                 distance: int = 3) -> Tuple[float, int, bool]:
+    """Marker snap (core/marker_manager.py:74-99): ``scipy.signal.find_peaks(levels, height=threshold,
+    prominence=excursion, distance=3)``, then the highest surviving peak; ``argmax(levels)`` when there is none.
+    Returns ``(frequency, bin index, used_fallback)``."""
+    _require_cuda()
+    if levels_db.dtype != torch.float32 or not levels_db.is_cuda:
+        raise ValueError("levels_db must be a float32 CUDA tensor")
+    out = torch.empty(3, dtype=torch.int32, device=levels_db.device)
+    L.check(L.load().tdsa_find_peaks_snap(levels_db.contiguous().data_ptr(), levels_db.numel(), float(threshold_db),
+                                          float(excursion_db), int(distance), out.data_ptr(), _stream_ptr()))
+    idx, _, fb = out.cpu().tolist()
+    return float(freq_bins[idx]), int(idx), bool(fb)

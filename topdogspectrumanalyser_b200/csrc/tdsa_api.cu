@@ -12,6 +12,8 @@
 
 #include "../../include/tdsa.h"
 #include "tdsa_aux.cuh"
+#include "tdsa_trace.cuh"
+#include "tdsa_display.cuh"
 #include "tdsa_big.cuh"
 #include "tdsa_launch.cuh"
 
@@ -58,11 +60,22 @@ struct tdsa_plan {
   double* d_win64 = nullptr; float* d_win32 = nullptr;        // with (-1)^n folded in
   double2* d_tw64 = nullptr; float2* d_tw32 = nullptr;
   bool win_dirty = true;
-  // warp-local 4096-point kernel (tdsa_fft_wl.cuh): window permuted to its thread order, frame scheduler
-  // words {next, done}, and the tensor map of the last input batch
+  // warp-local kernels (tdsa_fft_wl.cuh; N = 4096: one engine, N = 8192: two): window permuted to thread order,
+  // per-engine twiddle tables (N = 8192 only; N = 4096 uses d_tw*), frame scheduler words {next, done}, and the
+  // tensor map of the last input batch
+  int wl_nb = 0;                                              // engines, 0 = this size has no warp-local kernel
   double* d_wperm64 = nullptr; float* d_wperm32 = nullptr;
+  double2* d_wltw64 = nullptr; float2* d_wltw32 = nullptr;
   int* d_sched = nullptr;
   CUtensorMap tmap; const void* tmap_ptr = nullptr; int64_t tmap_frames = -1, tmap_stride = -1;
+  // accumulating epilogue: per-CTA partial rows, per-frame weights, {carry, count0, count1, max_valid0, min_valid0}
+  void* acc_parts = nullptr; size_t acc_parts_bytes = 0;
+  void* acc_weights = nullptr; size_t acc_weights_bytes = 0;
+  double* d_meta = nullptr;
+  // trace state owned by the plan for the host-scalar entry points: flag block and last good dB row
+  int32_t* d_flags = nullptr; float* d_last_row = nullptr;
+  // HackRF front end: per-frame mean / power / DC estimate (its own allocation: the large-FFT path uses scratch2)
+  void* scratch_dc = nullptr; size_t scratch_dc_bytes = 0;
   // large-FFT (two-kernel) tables: inner plan size M = N/256
   double2* d_twin64 = nullptr; float2* d_twin32 = nullptr;    // twiddles of the M-point inner transform
   double2* d_twh64 = nullptr; float2* d_twh32 = nullptr;      // DIF tables of big_head_kernel (passes 0, 1)
@@ -74,6 +87,16 @@ struct tdsa_plan {
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr};
   void* d_in[2] = {nullptr, nullptr}; void* d_out[2] = {nullptr, nullptr};
   size_t d_in_bytes = 0, d_out_bytes = 0;
+};
+
+// Every entry point that takes a plan runs on the plan's device, whatever device is current in the calling thread.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
 };
 
 static bool is_big(const tdsa_plan* p) {
@@ -128,21 +151,32 @@ static int upload_window(tdsa_plan* p) {
     w64[i] = s * p->window_host[i];
     w32[i] = (float)w64[i];
   }
+  // launches that still read the old tables may be queued on the plan's (non-blocking) stream: drain it first
+  CK(cudaStreamSynchronize(p->stream));
   CK(cudaMemcpy(p->d_win64, w64.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(p->d_win32, w32.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
-  if (p->d_wperm64) {   // thread tid of fft_wl_kernel owns samples r + 16 c + 256 j
-    std::vector<double> p64(n);
-    std::vector<float> p32(n);
-    for (int tid = 0; tid < 256; ++tid) {
+  if (p->d_wperm64) {
+    // fft_wl_kernel: thread tid (engine e = tid >> 8) owns samples n0 = r + 16 c + 256 j of each 4096-sample half;
+    // table entry [jj][tid], jj < 16: first half; jj >= 16 (two engines): second half, negated for engine 1
+    // (radix-2 DIF: engine 0 transforms x[n] w[n] + x[n+4096] w[n+4096], engine 1 the difference)
+    const int nb = p->wl_nb, th = 256 * nb;
+    const size_t cnt = (size_t)n * nb;                       // every engine reads the whole window
+    std::vector<double> p64(cnt);
+    std::vector<float> p32(cnt);
+    for (int tid = 0; tid < th; ++tid) {
       int r, c;
       wl_thread_identity(tid, &r, &c);
-      for (int j = 0; j < 16; ++j) {
-        p64[j * 256 + tid] = w64[r + 16 * c + 256 * j];
-        p32[j * 256 + tid] = w32[r + 16 * c + 256 * j];
+      const int e = tid >> 8;
+      for (int jj = 0; jj < 16 * nb; ++jj) {
+        const int half = jj >> 4, j = jj & 15;
+        const int idx = 4096 * half + r + 16 * c + 256 * j;
+        const double sg = (half == 1 && e == 1) ? -1.0 : 1.0;
+        p64[jj * th + tid] = sg * w64[idx];
+        p32[jj * th + tid] = (float)(sg * w64[idx]);
       }
     }
-    CK(cudaMemcpy(p->d_wperm64, p64.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(p->d_wperm32, p32.data(), sizeof(float) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->d_wperm64, p64.data(), sizeof(double) * cnt, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->d_wperm32, p32.data(), sizeof(float) * cnt, cudaMemcpyHostToDevice));
   }
   p->win_dirty = false;
   return TDSA_OK;
@@ -185,14 +219,15 @@ static bool wl_enabled() {
   return on;
 }
 
-// true when this batch can take the warp-local kernel; fills p->tmap
-static bool wl_prepare(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t stride, int epi) {
-  if (!wl_enabled() || p->log2n != 12 || !p->d_wperm64 || (epi != kEpiDb && epi != kEpiLinear)) return false;
+// true when this batch can take a warp-local kernel (epilogue / accumulator combination instantiated, frames
+// describable by a tensor map); fills p->tmap: [frame][256 * nb rows][32 floats], 128-byte swizzle, box = 256 rows
+static bool wl_prepare(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t stride, int epi, int acc_flags, bool dc) {
+  if (!wl_enabled() || p->wl_nb == 0 || !p->d_wperm64 || !wl_supported(p->wl_nb, epi, acc_flags, dc)) return false;
   if (((uintptr_t)iq & 15) != 0 || (stride & 1) != 0 || stride <= 0 || n_frames <= 0 || n_frames >= (1 << 30)) return false;
   if (p->tmap_ptr == iq && p->tmap_frames == n_frames && p->tmap_stride == stride) return true;
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return false;
-  const cuuint64_t dims[3] = {32, 256, (cuuint64_t)n_frames};
+  const cuuint64_t dims[3] = {32, (cuuint64_t)256 * p->wl_nb, (cuuint64_t)n_frames};
   const cuuint64_t strides[2] = {128, (cuuint64_t)stride * 8};
   const cuuint32_t box[3] = {32, 256, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
@@ -312,33 +347,102 @@ static EpiParams make_epi(const tdsa_plan* p, float* db, double* lin) {
 static int run_big(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t stride, const double2* dc, int epi, float* db,
                    double* lin, LaunchInfo* info, bool dry);
 
+// Twiddle tables of the two-engine N = 8192 warp-local kernel (tdsa_fft_wl.cuh): per engine, pass B [j][ka] then the
+// last pass [j][kk]; engine 1 evaluates both at the half-integer bin (ka + 1/2, kk + 1/2).
+static void build_wl_tables_8192(std::vector<double2>& t64) {
+  t64.clear();
+  for (int e = 0; e < 2; ++e) {
+    for (int j = 0; j < 16; ++j)
+      for (int ka = 0; ka < 16; ++ka) {
+        double2 w;
+        if (e == 0) twiddle((int64_t)j * ka, 256, &w.x, &w.y);
+        else twiddle((int64_t)j * (2 * ka + 1), 512, &w.x, &w.y);
+        t64.push_back(w);
+      }
+    for (int j = 0; j < 16; ++j)
+      for (int kk = 0; kk < 256; ++kk) {
+        double2 w;
+        if (e == 0) twiddle((int64_t)j * kk, 4096, &w.x, &w.y);
+        else twiddle((int64_t)j * (2 * kk + 1), 8192, &w.x, &w.y);
+        t64.push_back(w);
+      }
+  }
+}
+
+// one launch of a warp-local kernel (N = 4096 / 8192); the caller has called wl_prepare
+static int run_wl(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t stride, const double2* dc, int epi, float* db,
+                  double* lin, int acc_flags, const WlAcc& acc, LaunchInfo* info, bool dry) {
+  WlLaunch L;
+  L.tmap = &p->tmap; L.sched = WlSched{p->d_sched, p->d_sched + 1}; L.acc = acc; L.nb = p->wl_nb; L.acc_flags = acc_flags;
+  L.device = p->device; L.sm_count = p->sm_count;
+  cudaError_t e;
+  if (p->precision == TDSA_PREC_F32) {
+    FftArgs<float> a;
+    a.iq = (const float2*)iq; a.n_frames = n_frames; a.frame_stride = stride; a.window = p->d_win32;
+    a.tw = p->wl_nb == 2 ? p->d_wltw32 : p->d_tw32; a.dc = dc; a.in_ct = nullptr; a.ep = make_epi(p, db, lin);
+    L.wperm = p->d_wperm32;
+    e = launch_wl_f32(epi, a, L, p->stream, info, dry);
+  } else {
+    FftArgs<double> a;
+    a.iq = (const float2*)iq; a.n_frames = n_frames; a.frame_stride = stride; a.window = p->d_win64;
+    a.tw = p->wl_nb == 2 ? p->d_wltw64 : p->d_tw64; a.dc = dc; a.in_ct = nullptr; a.ep = make_epi(p, db, lin);
+    L.wperm = p->d_wperm64;
+    e = launch_wl_f64(epi, a, L, p->stream, info, dry);
+  }
+  if (e != cudaSuccess) return fail(TDSA_ERR_CUDA, "warp-local FFT launch failed (N=%d, acc=%d): %s", p->n, acc_flags, cudaGetErrorString(e));
+  return TDSA_OK;
+}
+
 // one launch of the fused path for frames already in device memory
 static int run_fused(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t stride, const double2* dc, int epi,
                      float* db, double* lin, LaunchInfo* info, bool dry) {
   if (p->win_dirty && !dry) { int rc = upload_window(p); if (rc) return rc; }
   if (is_big(p)) return run_big(p, iq, n_frames, stride, dc, epi, db, lin, info, dry);
-  cudaError_t e;
   // dry runs (launch geometry queries) describe the warp-local kernel whenever the size has one
-  const bool wl = dry ? (wl_enabled() && p->log2n == 12 && p->d_wperm64 && (epi == kEpiDb || epi == kEpiLinear) && encode_tiled_fn())
-                      : wl_prepare(p, iq, n_frames, stride, epi);
-  const WlSched sched{p->d_sched, p->d_sched ? p->d_sched + 1 : nullptr};
+  const bool wl = dry ? (wl_enabled() && p->wl_nb != 0 && p->d_wperm64 && wl_supported(p->wl_nb, epi, 0, dc != nullptr) && encode_tiled_fn())
+                      : wl_prepare(p, iq, n_frames, stride, epi, 0, dc != nullptr);
+  if (wl) return run_wl(p, iq, n_frames, stride, dc, epi, db, lin, 0, WlAcc(), info, dry);
+  cudaError_t e;
   if (p->precision == TDSA_PREC_F32) {
     FftArgs<float> a;
     a.iq = (const float2*)iq; a.n_frames = n_frames; a.frame_stride = stride;
     a.window = p->d_win32; a.tw = p->d_tw32; a.dc = dc; a.in_ct = nullptr; a.ep = make_epi(p, db, lin);
     a.sched = (dyn_enabled() && n_frames < (1 << 30)) ? p->d_sched : nullptr;
-    e = wl ? launch_wl_f32(epi, a, p->tmap, p->d_wperm32, sched, p->sm_count, p->stream, info, dry)
-           : launch_fft_f32(p->log2n, epi, a, p->sm_count, p->stream, info, dry);
+    e = launch_fft_f32(p->log2n, epi, a, p->sm_count, p->stream, info, dry);
   } else {
     FftArgs<double> a;
     a.iq = (const float2*)iq; a.n_frames = n_frames; a.frame_stride = stride;
     a.window = p->d_win64; a.tw = p->d_tw64; a.dc = dc; a.in_ct = nullptr; a.ep = make_epi(p, db, lin);
     a.sched = (dyn_enabled() && n_frames < (1 << 30)) ? p->d_sched : nullptr;
-    e = wl ? launch_wl_f64(epi, a, p->tmap, p->d_wperm64, sched, p->sm_count, p->stream, info, dry)
-           : launch_fft_f64(p->log2n, epi, a, p->sm_count, p->stream, info, dry);
+    e = launch_fft_f64(p->log2n, epi, a, p->sm_count, p->stream, info, dry);
   }
   if (e != cudaSuccess) return fail(TDSA_ERR_CUDA, "fused FFT launch failed (N=%d): %s", p->n, cudaGetErrorString(e));
   return TDSA_OK;
+}
+
+// scratch for the accumulating epilogue: per-CTA partial rows {sum f64, max f32, min f32} for up to `ctas` CTAs
+static int ensure_acc(tdsa_plan* p, int ctas, int64_t n_frames, double** part_sum, float** part_max, float** part_min,
+                      double** weights) {
+  const size_t per = (size_t)p->n * (sizeof(double) + 2 * sizeof(float));
+  int rc = ensure_scratch(&p->acc_parts, &p->acc_parts_bytes, per * (size_t)ctas);
+  if (rc) return rc;
+  *part_sum = (double*)p->acc_parts;
+  *part_max = (float*)(*part_sum + (size_t)ctas * p->n);
+  *part_min = *part_max + (size_t)ctas * p->n;
+  if (weights) {
+    rc = ensure_scratch(&p->acc_weights, &p->acc_weights_bytes, sizeof(double) * (size_t)std::max<int64_t>(n_frames, 1));
+    if (rc) return rc;
+    *weights = (double*)p->acc_weights;
+  }
+  return TDSA_OK;
+}
+
+// grid the warp-local kernel will use for this many claimable units (= number of partial rows it writes)
+static int wl_grid(tdsa_plan* p, int64_t n_units, int acc_flags) {
+  LaunchInfo info;
+  WlAcc acc;
+  if (run_wl(p, nullptr, n_units, p->n, nullptr, kEpiDb, nullptr, nullptr, acc_flags, acc, &info, true) != TDSA_OK) return 0;
+  return info.grid;
 }
 
 #include "tdsa_big_host.inl"
@@ -378,10 +482,21 @@ int tdsa_create(int n_fft, int window_id, int window_norm, int mode, double log_
     if (rc) break;
     if (cudaMalloc(&p->d_sched, 2 * sizeof(int)) != cudaSuccess ||
         cudaMemset(p->d_sched, 0, 2 * sizeof(int)) != cudaSuccess) { rc = fail(TDSA_ERR_NOMEM, "scheduler alloc failed"); break; }
-    if (p->log2n == 12 && effective_logr_f64(12) == 4 && effective_logr_f32(12) == 4) {   // warp-local kernel tables
-      if (cudaMalloc(&p->d_wperm64, sizeof(double) * n_fft) != cudaSuccess ||
-          cudaMalloc(&p->d_wperm32, sizeof(float) * n_fft) != cudaSuccess) { rc = fail(TDSA_ERR_NOMEM, "warp-local tables alloc failed"); break; }
+    if ((p->log2n == 12 && effective_logr_f64(12) == 4 && effective_logr_f32(12) == 4) || p->log2n == 13) {   // warp-local kernels
+      p->wl_nb = p->log2n == 12 ? 1 : 2;
+      if (cudaMalloc(&p->d_wperm64, sizeof(double) * n_fft * p->wl_nb) != cudaSuccess ||
+          cudaMalloc(&p->d_wperm32, sizeof(float) * n_fft * p->wl_nb) != cudaSuccess) { rc = fail(TDSA_ERR_NOMEM, "warp-local tables alloc failed"); break; }
+      if (p->wl_nb == 2) {
+        std::vector<double2> tw;
+        build_wl_tables_8192(tw);
+        rc = upload_pair(tw, &p->d_wltw64, &p->d_wltw32, true, true);
+        if (rc) break;
+      }
     }
+    if (cudaMalloc(&p->d_meta, 8 * sizeof(double)) != cudaSuccess || cudaMalloc(&p->d_flags, kFlagWords * sizeof(int32_t)) != cudaSuccess ||
+        cudaMalloc(&p->d_last_row, sizeof(float) * n_fft) != cudaSuccess ||
+        cudaMemset(p->d_flags, 0, kFlagWords * sizeof(int32_t)) != cudaSuccess ||
+        cudaMemset(p->d_last_row, 0, sizeof(float) * n_fft) != cudaSuccess) { rc = fail(TDSA_ERR_NOMEM, "trace state alloc failed"); break; }
     if (p->log2n > MaxLog2<float>::value || p->log2n > MaxLog2<double>::value) {
       // tables for the inner (N/256)-point transform of the two-kernel path
       rc = upload_twiddles(p->log2n - 4 * big_head_passes(p), 4, 4, &p->d_twin64, &p->d_twin32);
@@ -399,8 +514,11 @@ int tdsa_create(int n_fft, int window_id, int window_norm, int mode, double log_
 
 int tdsa_destroy(tdsa_handle_t p) {
   if (!p) return TDSA_OK;
+  DeviceGuard guard(p->device);
   cudaFree(p->d_win64); cudaFree(p->d_win32); cudaFree(p->d_tw64); cudaFree(p->d_tw32);
-  cudaFree(p->d_wperm64); cudaFree(p->d_wperm32); cudaFree(p->d_sched);
+  cudaFree(p->d_wperm64); cudaFree(p->d_wperm32); cudaFree(p->d_sched); cudaFree(p->d_wltw64); cudaFree(p->d_wltw32);
+  cudaFree(p->acc_parts); cudaFree(p->acc_weights); cudaFree(p->d_meta); cudaFree(p->d_flags); cudaFree(p->d_last_row);
+  cudaFree(p->scratch_dc);
   cudaFree(p->d_twin64); cudaFree(p->d_twin32); cudaFree(p->d_twh64); cudaFree(p->d_twh32);
   cudaFree(p->scratch); cudaFree(p->scratch2);
   for (int i = 0; i < 2; ++i) {
@@ -467,13 +585,34 @@ static int check_batch(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_
 int tdsa_psd_db_batch(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, float* db_out) {
   int rc = check_batch(p, iq, n_frames, stride, db_out);
   if (rc) return rc;
+  DeviceGuard guard(p->device);
   return run_fused(p, iq, n_frames, stride, nullptr, kEpiDb, db_out, nullptr, nullptr, false);
 }
 
 int tdsa_power_linear_batch(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, double* lin_out) {
   int rc = check_batch(p, iq, n_frames, stride, lin_out);
   if (rc) return rc;
+  DeviceGuard guard(p->device);
   return run_fused(p, iq, n_frames, stride, nullptr, kEpiLinear, nullptr, lin_out, nullptr, false);
+}
+
+// HackRF front end (hackrf_samples.py:351-365): per-frame mean and power, then the DC tracker; fills dc[] and silent[]
+static int run_dc_front(tdsa_plan* p, const float2* iq, int64_t n_frames, int64_t stride, double dc_alpha, double* dc_state,
+                        int32_t* silent_out, const double2** dc_out) {
+  const size_t need = (size_t)n_frames * (sizeof(double2) * 2 + sizeof(double));
+  int rc = ensure_scratch(&p->scratch_dc, &p->scratch_dc_bytes, need);
+  if (rc) return rc;
+  double2* mean = (double2*)p->scratch_dc;
+  double2* dc = mean + n_frames;
+  double* pw = (double*)(dc + n_frames);
+  const int grid = (int)std::min<int64_t>(n_frames, (int64_t)p->sm_count * 8);
+  frame_stats_kernel<<<grid, 256, 0, p->stream>>>(iq, n_frames, stride, p->n, mean, pw);
+  count_launch();
+  dc_scan_kernel<<<1, 32, 0, p->stream>>>(mean, pw, n_frames, dc_alpha, dc_state, dc, silent_out);
+  count_launch();
+  CK(cudaGetLastError());
+  *dc_out = dc;
+  return TDSA_OK;
 }
 
 int tdsa_psd_db_batch_dc(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, double dc_alpha,
@@ -482,107 +621,175 @@ int tdsa_psd_db_batch_dc(tdsa_handle_t p, const void* iq, int64_t n_frames, int6
   if (rc) return rc;
   if (!dc_state) return fail(TDSA_ERR_INVALID, "dc_state is NULL");
   if (n_frames == 0) return TDSA_OK;
-  // scratch2: mean[F] (double2) | pw[F] (double) | dc[F] (double2)
-  const size_t need = (size_t)n_frames * (sizeof(double2) * 2 + sizeof(double));
-  rc = ensure_scratch(&p->scratch2, &p->scratch2_bytes, need);
+  DeviceGuard guard(p->device);
+  const double2* dc = nullptr;
+  rc = run_dc_front(p, (const float2*)iq, n_frames, stride, dc_alpha, dc_state, silent_out, &dc);
   if (rc) return rc;
-  double2* mean = (double2*)p->scratch2;
-  double2* dc = mean + n_frames;
-  double* pw = (double*)(dc + n_frames);
-  const int grid = (int)std::min<int64_t>(n_frames, (int64_t)p->sm_count * 8);
-  frame_stats_kernel<<<grid, 256, 0, p->stream>>>((const float2*)iq, n_frames, stride, p->n, mean, pw);
-  count_launch();
-  dc_scan_kernel<<<1, 32, 0, p->stream>>>(mean, pw, n_frames, dc_alpha, dc_state, dc, silent_out);
-  count_launch();
-  CK(cudaGetLastError());
   return run_fused(p, iq, n_frames, stride, dc, kEpiDb, db_out, nullptr, nullptr, false);
 }
 
-static int avg_hold_impl(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, bool with_dc,
-                         double dc_alpha, double* dc_state, int32_t* silent_out, int avg_mode, int avg_n,
-                         double* avg_state, int32_t* count_state_host, float* max_hold, float* min_hold,
-                         int32_t* hold_valid_host, int last_only, float* db_out) {
+// frames below this count are not worth the fused epilogue's extra launches (weights / finish kernels)
+static int64_t fused_min_frames() {
+  static const int64_t v = [] { const char* e = getenv("TDSA_FUSED_MIN_FRAMES"); return (int64_t)(e ? atoll(e) : 64); }();
+  return v;
+}
+// linear rows of the general path are produced and consumed chunk by chunk so that they never leave the L2
+static int64_t scan_chunk_bytes() {
+  static const int64_t v = [] { const char* e = getenv("TDSA_SCAN_CHUNK_MB"); return (int64_t)(e ? atoll(e) : 32) << 20; }();
+  return v;
+}
+
+// Frames -> device-resident trace state. Three shapes:
+//   fused running average (last row only, no holds): weighted sum in the FFT kernel's accumulating epilogue;
+//   fused holds (no averaging): dB rows + running max/min of |X|^2 in the same epilogue;
+//   general: float64 linear rows of an L2-sized chunk -> frame-ordered scan (averager + dB + holds per frame).
+static int avg_hold_dev_impl(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, bool with_dc,
+                             double dc_alpha, double* dc_state, int32_t* silent_out, int avg_mode, int avg_n,
+                             double* avg_state, float* max_hold, float* min_hold, int32_t* flags, float* last_row,
+                             int last_only, float* db_out) {
   int rc = check_batch(p, iq, n_frames, stride, db_out);
   if (rc) return rc;
   const bool averaging = avg_mode != TDSA_AVG_OFF && avg_n > 1;
-  if (averaging && (!avg_state || !count_state_host)) return fail(TDSA_ERR_INVALID, "averaging needs avg_state and count_state");
-  if ((max_hold || min_hold) && !hold_valid_host) return fail(TDSA_ERR_INVALID, "holds need hold_valid");
+  if (!flags) return fail(TDSA_ERR_INVALID, "flags block (device int32[8]) is required");
+  if (averaging && !avg_state) return fail(TDSA_ERR_INVALID, "averaging needs avg_state");
   if (p->mode == TDSA_MODE_MAG20 && averaging) return fail(TDSA_ERR_INVALID, "mag20 branch is never averaged (hackrf_samples.py:378-383)");
   if (with_dc && (!dc_state || !silent_out)) return fail(TDSA_ERR_INVALID, "dc path needs dc_state and silent_out");
   if (n_frames == 0) return TDSA_OK;
-  // frames are folded in chunks so the float64 linear-power scratch stays bounded (<= 256 MiB)
-  const int64_t chunk_max = std::max<int64_t>(1, ((int64_t)256 << 20) / ((int64_t)p->n * 8));
-  int count = averaging ? *count_state_host : 0;
-  int mxv = hold_valid_host ? hold_valid_host[0] : 0, mnv = hold_valid_host ? hold_valid_host[1] : 0;
-  std::vector<int32_t> silent_h;
+  DeviceGuard guard(p->device);
+  if (p->win_dirty) { rc = upload_window(p); if (rc) return rc; }
+  const double scale = (p->mode == TDSA_MODE_PSD) ? 1.0 / (p->fs * (double)p->n) : 1.0;
+  const int fin_grid = (p->n + 255) / 256;
+  const bool big_enough = n_frames >= fused_min_frames() && !with_dc && !is_big(p);
+  // ---- fused running average -------------------------------------------------------------------------------
+  if (big_enough && averaging && last_only && !max_hold && !min_hold &&
+      wl_prepare(p, iq, n_frames, stride, kEpiDb, kAccAvg, false)) {
+    const int grid = wl_grid(p, n_frames, kAccAvg);
+    double *ps, *wts; float *pmx, *pmn;
+    rc = ensure_acc(p, grid, n_frames, &ps, &pmx, &pmn, &wts);
+    if (rc) return rc;
+    avg_weights_kernel<<<(int)std::min<int64_t>((n_frames + 255) / 256, 1024), 256, 0, p->stream>>>(avg_mode, avg_n, n_frames, flags, wts, p->d_meta);
+    count_launch();
+    WlAcc acc;
+    acc.weight = wts; acc.part_sum = ps;
+    rc = run_wl(p, iq, n_frames, stride, nullptr, kEpiDb, nullptr, nullptr, kAccAvg, acc, nullptr, false);
+    if (rc) return rc;
+    avg_finish_kernel<<<fin_grid, 256, 0, p->stream>>>(ps, grid, p->n, p->d_meta, scale, p->floor, p->mode, avg_state, flags,
+                                                      n_frames, db_out, last_row);
+    count_launch();
+    CK(cudaGetLastError());
+    return TDSA_OK;
+  }
+  // ---- fused holds on un-averaged rows ------------------------------------------------------------------------
+  if (big_enough && !averaging && (max_hold || min_hold) && wl_prepare(p, iq, n_frames, stride, kEpiDb, kAccHold, false)) {
+    const int grid = wl_grid(p, n_frames, kAccHold);
+    double* ps; float *pmx, *pmn;
+    rc = ensure_acc(p, grid, n_frames, &ps, &pmx, &pmn, nullptr);
+    if (rc) return rc;
+    flags_prepare_kernel<<<1, 32, 0, p->stream>>>(flags, p->d_meta, avg_mode, avg_n, n_frames, max_hold != nullptr, min_hold != nullptr);
+    count_launch();
+    WlAcc acc;
+    acc.part_max = pmx; acc.part_min = pmn; acc.only_row = last_only ? n_frames - 1 : -1;
+    rc = run_wl(p, iq, n_frames, stride, nullptr, kEpiDb, db_out, nullptr, kAccHold, acc, nullptr, false);
+    if (rc) return rc;
+    hold_finish_kernel<<<fin_grid, 256, 0, p->stream>>>(pmx, pmn, grid, p->n, p->d_meta, scale, p->floor, p->mode, max_hold, min_hold);
+    count_launch();
+    if (last_row) {
+      CK(cudaMemcpyAsync(last_row, last_only ? db_out : db_out + (n_frames - 1) * p->n, sizeof(float) * p->n,
+                         cudaMemcpyDeviceToDevice, p->stream));
+    }
+    CK(cudaGetLastError());
+    return TDSA_OK;
+  }
+  // ---- general path ---------------------------------------------------------------------------------------------
+  const int64_t chunk_max = std::max<int64_t>(1, scan_chunk_bytes() / ((int64_t)p->n * 8));
   for (int64_t f0 = 0; f0 < n_frames; f0 += chunk_max) {
     const int64_t nf = std::min(chunk_max, n_frames - f0);
-    rc = ensure_scratch(&p->scratch, &p->scratch_bytes, (size_t)nf * p->n * sizeof(double));
+    rc = ensure_scratch(&p->scratch, &p->scratch_bytes, (size_t)std::min(chunk_max, n_frames) * p->n * sizeof(double));
     if (rc) return rc;
     double* lin = (double*)p->scratch;
     const float2* src = (const float2*)iq + f0 * stride;
     const double2* dc = nullptr;
-    int64_t live = nf;
     if (with_dc) {
-      const size_t need = (size_t)nf * (sizeof(double2) * 2 + sizeof(double));
-      rc = ensure_scratch(&p->scratch2, &p->scratch2_bytes, need);
+      rc = run_dc_front(p, src, nf, stride, dc_alpha, dc_state, silent_out + f0, &dc);
       if (rc) return rc;
-      double2* mean = (double2*)p->scratch2;
-      double2* dcv = mean + nf;
-      double* pw = (double*)(dcv + nf);
-      const int grid = (int)std::min<int64_t>(nf, (int64_t)p->sm_count * 8);
-      frame_stats_kernel<<<grid, 256, 0, p->stream>>>(src, nf, stride, p->n, mean, pw);
-      count_launch();
-      dc_scan_kernel<<<1, 32, 0, p->stream>>>(mean, pw, nf, dc_alpha, dc_state, dcv, silent_out + f0);
-      count_launch();
-      CK(cudaGetLastError());
-      dc = dcv;
-      // the host-side scalars (count, valid) depend on how many frames were live
-      silent_h.resize(nf);
-      CK(cudaMemcpyAsync(silent_h.data(), silent_out + f0, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, p->stream));
-      CK(cudaStreamSynchronize(p->stream));
-      live = 0;
-      for (int32_t v : silent_h) live += v == 0;
     }
     rc = run_fused(p, src, nf, stride, dc, kEpiLinear, nullptr, lin, nullptr, false);
     if (rc) return rc;
-    TraceScanArgs a;
+    TraceScanDevArgs a;
     a.lin = lin; a.skip = with_dc ? silent_out + f0 : nullptr;
-    a.n_frames = nf; a.width = p->n; a.avg_mode = avg_mode; a.avg_n = avg_n; a.count0 = count;
-    a.avg_state = avg_state; a.max_hold = max_hold; a.min_hold = min_hold; a.max_valid0 = mxv; a.min_valid0 = mnv;
+    a.n_frames = nf; a.width = p->n; a.avg_mode = avg_mode; a.avg_n = avg_n; a.flags = flags;
+    a.avg_state = avg_state; a.max_hold = max_hold; a.min_hold = min_hold; a.last_row = last_row;
     a.last_only = last_only;
+    // last_only: every chunk writes its last row into db_out[0..N); the final chunk's survives
     a.db_out = last_only ? db_out : db_out + f0 * p->n;
     a.floor = p->floor; a.mode = p->mode;
-    trace_scan_kernel<<<(p->n + 255) / 256, 256, 0, p->stream>>>(a);
+    trace_scan_dev_kernel<<<fin_grid, 256, 0, p->stream>>>(a);
+    count_launch();
+    trace_flags_after_scan_kernel<<<1, 256, 0, p->stream>>>(flags, a.skip, nf, avg_mode, avg_n, max_hold != nullptr,
+                                                          min_hold != nullptr, f0 == 0);
     count_launch();
     CK(cudaGetLastError());
-    if (live > 0) {
-      if (averaging) {   // TraceAverager._count after `live` more frames (signal_processing.py:46-58)
-        if (avg_mode == TDSA_AVG_LIN) count = (int)std::min<int64_t>((int64_t)avg_n, (int64_t)count + live);
-        else count = std::max(count, 1);
-      }
-      if (max_hold) mxv = 1;
-      if (min_hold) mnv = 1;
-    }
   }
-  if (averaging) *count_state_host = count;
-  if (hold_valid_host) { hold_valid_host[0] = mxv; hold_valid_host[1] = mnv; }
+  return TDSA_OK;
+}
+
+int tdsa_psd_db_avg_hold_dev(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, int use_dc, double dc_alpha,
+                             double* dc_state, int32_t* silent_out, int avg_mode, int avg_n, double* avg_state,
+                             float* max_hold, float* min_hold, int32_t* flags_dev, float* last_row_dev, int last_only,
+                             float* db_out) {
+  if (!p) return fail(TDSA_ERR_INVALID, "null plan");
+  return avg_hold_dev_impl(p, iq, n_frames, stride, use_dc != 0, dc_alpha, dc_state, silent_out, avg_mode, avg_n, avg_state,
+                           max_hold, min_hold, flags_dev, last_row_dev, last_only, db_out);
+}
+
+// Host-scalar flavour: the plan's own flag block is seeded from the host values, the device path runs, and the host
+// values are brought up to date: arithmetically when every frame is live, by reading the block back (one stream
+// synchronisation) on the HackRF path, where the number of live frames is only known on the device.
+static int avg_hold_host_scalars(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, bool with_dc,
+                                 double dc_alpha, double* dc_state, int32_t* silent_out, int avg_mode, int avg_n,
+                                 double* avg_state, int32_t* count_state_host, float* max_hold, float* min_hold,
+                                 int32_t* hold_valid_host, int last_only, float* db_out) {
+  if (!p) return fail(TDSA_ERR_INVALID, "null plan");
+  const bool averaging = avg_mode != TDSA_AVG_OFF && avg_n > 1;
+  if (averaging && !count_state_host) return fail(TDSA_ERR_INVALID, "averaging needs avg_state and count_state");
+  if ((max_hold || min_hold) && !hold_valid_host) return fail(TDSA_ERR_INVALID, "holds need hold_valid");
+  if (n_frames <= 0) return n_frames == 0 ? TDSA_OK : fail(TDSA_ERR_INVALID, "n_frames < 0");
+  DeviceGuard guard(p->device);
+  int32_t h[kFlagWords] = {};
+  h[kFlagCount] = averaging ? *count_state_host : 0;
+  h[kFlagMaxValid] = hold_valid_host ? hold_valid_host[0] : 0;
+  h[kFlagMinValid] = hold_valid_host ? hold_valid_host[1] : 0;
+  CK(cudaMemcpyAsync(p->d_flags, h, sizeof h, cudaMemcpyHostToDevice, p->stream));
+  int rc = avg_hold_dev_impl(p, iq, n_frames, stride, with_dc, dc_alpha, dc_state, silent_out, avg_mode, avg_n, avg_state,
+                             max_hold, min_hold, p->d_flags, p->d_last_row, last_only, db_out);
+  if (rc) return rc;
+  if (with_dc) {
+    CK(cudaMemcpyAsync(h, p->d_flags, sizeof h, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+  } else {            // TraceAverager._count after n_frames more frames (signal_processing.py:46-58)
+    if (averaging) h[kFlagCount] = avg_mode == TDSA_AVG_LIN ? (int32_t)std::min<int64_t>(avg_n, (int64_t)h[kFlagCount] + n_frames)
+                                                            : std::max(h[kFlagCount], 1);
+    if (max_hold) h[kFlagMaxValid] = 1;
+    if (min_hold) h[kFlagMinValid] = 1;
+  }
+  if (averaging) *count_state_host = h[kFlagCount];
+  if (hold_valid_host) { hold_valid_host[0] = h[kFlagMaxValid]; hold_valid_host[1] = h[kFlagMinValid]; }
   return TDSA_OK;
 }
 
 int tdsa_psd_db_avg_hold(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, int avg_mode, int avg_n,
                          double* avg_state, int32_t* count_state_host, float* max_hold, float* min_hold,
                          int32_t* hold_valid_host, int last_only, float* db_out) {
-  return avg_hold_impl(p, iq, n_frames, stride, false, 1.0, nullptr, nullptr, avg_mode, avg_n, avg_state,
-                       count_state_host, max_hold, min_hold, hold_valid_host, last_only, db_out);
+  return avg_hold_host_scalars(p, iq, n_frames, stride, false, 1.0, nullptr, nullptr, avg_mode, avg_n, avg_state,
+                               count_state_host, max_hold, min_hold, hold_valid_host, last_only, db_out);
 }
 
 int tdsa_psd_db_avg_hold_dc(tdsa_handle_t p, const void* iq, int64_t n_frames, int64_t stride, double dc_alpha,
                             double* dc_state, int32_t* silent_out, int avg_mode, int avg_n, double* avg_state,
                             int32_t* count_state_host, float* max_hold, float* min_hold, int32_t* hold_valid_host,
                             int last_only, float* db_out) {
-  return avg_hold_impl(p, iq, n_frames, stride, true, dc_alpha, dc_state, silent_out, avg_mode, avg_n, avg_state,
-                       count_state_host, max_hold, min_hold, hold_valid_host, last_only, db_out);
+  return avg_hold_host_scalars(p, iq, n_frames, stride, true, dc_alpha, dc_state, silent_out, avg_mode, avg_n, avg_state,
+                               count_state_host, max_hold, min_hold, hold_valid_host, last_only, db_out);
 }
 
 int tdsa_group_avg_db(tdsa_handle_t p, const void* iq, int64_t n_groups, int64_t frames_per_group, float* db_rows) {
@@ -591,11 +798,22 @@ int tdsa_group_avg_db(tdsa_handle_t p, const void* iq, int64_t n_groups, int64_t
   if (p->mode == TDSA_MODE_MAG20) return fail(TDSA_ERR_INVALID, "group average works on power; use power or psd mode");
   if (n_groups == 0) return TDSA_OK;
   if (!iq || !db_rows) return fail(TDSA_ERR_INVALID, "null buffer");
+  DeviceGuard guard(p->device);
   const int64_t n = p->n;
+  // N = 4096 / 8192: the group mean is formed in the FFT kernel's accumulating epilogue (one launch, one dB row
+  // per group out; no linear rows at all)
+  if (frames_per_group < (1 << 20) && n_groups * frames_per_group < (1 << 30)) {
+    if (p->win_dirty) { int rcw = upload_window(p); if (rcw) return rcw; }
+    if (wl_prepare(p, iq, n_groups * frames_per_group, n, kEpiDb, kAccGroupMean, false)) {
+      WlAcc acc;
+      acc.group = (int)frames_per_group; acc.group_db = db_rows;
+      return run_wl(p, iq, n_groups * frames_per_group, n, nullptr, kEpiDb, nullptr, nullptr, kAccGroupMean, acc, nullptr, false);
+    }
+  }
   const int64_t per_group = frames_per_group * n * (int64_t)sizeof(double);
   // groups per launch: the float64 rows of a chunk are written by the FFT kernel and read straight back by the
   // group-mean kernel, so a chunk that fits the 126 MB L2 keeps that traffic off HBM (TDSA_GROUP_CHUNK_MB to tune)
-  static const int64_t chunk_mb = [] { const char* e = getenv("TDSA_GROUP_CHUNK_MB"); return (int64_t)(e ? atoi(e) : 256); }();
+  static const int64_t chunk_mb = [] { const char* e = getenv("TDSA_GROUP_CHUNK_MB"); return (int64_t)(e ? atoi(e) : 48); }();
   const int64_t chunk = std::max<int64_t>(1, (std::max<int64_t>(chunk_mb, 1) << 20) / per_group);
   for (int64_t g0 = 0; g0 < n_groups; g0 += chunk) {
     const int64_t ng = std::min(chunk, n_groups - g0);
@@ -620,6 +838,27 @@ int tdsa_welch(tdsa_handle_t p, const void* iq_stream, int64_t n_samples, int64_
   if (p->mode == TDSA_MODE_MAG20) return fail(TDSA_ERR_INVALID, "welch averages power; use power or psd mode");
   const int64_t nseg = (n_samples - p->n) / hop + 1;
   const int64_t n = p->n;
+  DeviceGuard guard(p->device);
+  // segments that fit one CTA of the warp-local kernel: mean and peak accumulate in its epilogue (TMEM), one launch
+  if (!is_big(p) && nseg < (1 << 30)) {
+    if (p->win_dirty) { int rcw = upload_window(p); if (rcw) return rcw; }
+    if (wl_prepare(p, iq_stream, nseg, hop, kEpiDb, kAccWelch, false)) {
+      const int grid = wl_grid(p, nseg, kAccWelch);
+      double* ps; float *pmx, *pmn;
+      int rca = ensure_acc(p, grid, nseg, &ps, &pmx, &pmn, nullptr);
+      if (rca) return rca;
+      WlAcc acc;
+      acc.part_sum = ps; acc.part_max = pmx;
+      rca = run_wl(p, iq_stream, nseg, hop, nullptr, kEpiDb, nullptr, nullptr, kAccWelch, acc, nullptr, false);
+      if (rca) return rca;
+      const double scale = (p->mode == TDSA_MODE_PSD) ? 1.0 / (p->fs * (double)n) : 1.0;
+      welch_acc_finish_kernel<<<(int)((n + 255) / 256), 256, 0, p->stream>>>(ps, pmx, grid, n, nseg, scale, p->floor, p->mode,
+                                                                           avg_db, peak_db);
+      count_launch();
+      CK(cudaGetLastError());
+      return TDSA_OK;
+    }
+  }
   // 65536-point segments: one cluster kernel keeps everything but the IQ samples on the SMs (tdsa_welch_cluster.cuh)
   if (p->log2n == kWcLog2N && welch_cluster_enabled()) {
     int max_clusters = 0;
@@ -681,13 +920,55 @@ int tdsa_welch(tdsa_handle_t p, const void* iq_stream, int64_t n_samples, int64_
   return TDSA_OK;
 }
 
+// dB rows -> device-resident DataProcessor state (cal offset, tare, sweep-domain averaging, holds); flag block on
+// the device, nothing read back
+static int trace_update_dev_impl(const float* rows, int64_t n_rows, int64_t width, double cal_offset_db, int avg_mode, int avg_n,
+                                 double* avg_state, float* max_hold, float* min_hold, int32_t* flags, float* rows_out,
+                                 void* cuda_stream, int32_t* row_flags_scratch, int tare_target, double* tare_buf,
+                                 double* tare_baseline) {
+  if (!rows || n_rows < 0 || width < 1) return fail(TDSA_ERR_INVALID, "bad rows");
+  if (!row_flags_scratch) return fail(TDSA_ERR_INVALID, "row_flags_scratch (int32[n_rows], device) is required");
+  if (!flags) return fail(TDSA_ERR_INVALID, "flags block (device int32[8]) is required");
+  const bool averaging = avg_mode != TDSA_AVG_OFF && avg_n > 1;
+  if (averaging && !avg_state) return fail(TDSA_ERR_INVALID, "averaging needs avg_state");
+  const bool has_tare = tare_buf != nullptr && tare_baseline != nullptr;
+  if (has_tare && tare_target < 1) return fail(TDSA_ERR_INVALID, "tare needs a target >= 1");
+  if (n_rows == 0) return TDSA_OK;
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  CK(cudaMemsetAsync(row_flags_scratch, 0, sizeof(int32_t) * n_rows, s));
+  dim3 g((unsigned)((width + 255) / 256), (unsigned)n_rows);
+  row_allnan_kernel<<<g, 256, 0, s>>>(rows, n_rows, width, row_flags_scratch);
+  count_launch();
+  TraceUpdateDevArgs a;
+  a.rows = rows; a.n_rows = n_rows; a.width = width; a.cal = cal_offset_db;
+  a.avg_mode = avg_mode; a.avg_n = avg_n; a.flags = flags;
+  a.avg_state = avg_state; a.max_hold = max_hold; a.min_hold = min_hold;
+  a.has_value = row_flags_scratch; a.rows_out = rows_out;
+  a.tare_target = tare_target; a.tare_buf = tare_buf; a.tare_baseline = tare_baseline;
+  trace_update_dev_kernel<<<(unsigned)((width + 255) / 256), 256, 0, s>>>(a);
+  count_launch();
+  trace_flags_after_update_kernel<<<1, 256, 0, s>>>(flags, row_flags_scratch, n_rows, avg_mode, avg_n, max_hold != nullptr,
+                                                  min_hold != nullptr, has_tare ? 1 : 0, tare_target);
+  count_launch();
+  CK(cudaGetLastError());
+  return TDSA_OK;
+}
+
+int tdsa_trace_update_dev(const float* rows, int64_t n_rows, int64_t width, double cal_offset_db, int avg_mode, int avg_n,
+                          double* avg_state, float* max_hold, float* min_hold, int32_t* flags_dev, float* rows_out,
+                          void* cuda_stream, int32_t* row_flags_scratch, int tare_target, double* tare_buf,
+                          double* tare_baseline) {
+  return trace_update_dev_impl(rows, n_rows, width, cal_offset_db, avg_mode, avg_n, avg_state, max_hold, min_hold, flags_dev,
+                               rows_out, cuda_stream, row_flags_scratch, tare_target, tare_buf, tare_baseline);
+}
+
+// Host-scalar flavour of the above (count / valid / tare flags are host values, read and updated): a temporary flag
+// block carries them to the device and back, which costs one stream synchronisation per call.
 static int trace_update_impl(const float* rows, int64_t n_rows, int64_t width, double cal_offset_db, int avg_mode, int avg_n,
                              double* avg_state, int32_t* count_state_host, float* max_hold, float* min_hold,
                              int32_t* hold_valid_host, float* rows_out, void* cuda_stream, int32_t* row_flags_scratch,
                              int32_t* tare_flags_host, int32_t* tare_count_host, int tare_target, double* tare_buf,
                              double* tare_baseline) {
-  if (!rows || n_rows < 0 || width < 1) return fail(TDSA_ERR_INVALID, "bad rows");
-  if (!row_flags_scratch) return fail(TDSA_ERR_INVALID, "row_flags_scratch (int32[n_rows], device) is required");
   const bool averaging = avg_mode != TDSA_AVG_OFF && avg_n > 1;
   if (averaging && (!avg_state || !count_state_host)) return fail(TDSA_ERR_INVALID, "averaging needs avg_state and count_state");
   if ((max_hold || min_hold) && !hold_valid_host) return fail(TDSA_ERR_INVALID, "holds need hold_valid");
@@ -696,45 +977,28 @@ static int trace_update_impl(const float* rows, int64_t n_rows, int64_t width, d
     return fail(TDSA_ERR_INVALID, "tare needs count, buffer, baseline and a target >= 1");
   if (n_rows == 0) return TDSA_OK;
   cudaStream_t s = (cudaStream_t)cuda_stream;
-  CK(cudaMemsetAsync(row_flags_scratch, 0, sizeof(int32_t) * n_rows, s));
-  dim3 g((unsigned)((width + 255) / 256), (unsigned)n_rows);
-  row_allnan_kernel<<<g, 256, 0, s>>>(rows, n_rows, width, row_flags_scratch);
-  count_launch();
-  TraceUpdateArgs a;
-  a.rows = rows; a.n_rows = n_rows; a.width = width; a.cal = cal_offset_db;
-  a.avg_mode = avg_mode; a.avg_n = avg_n; a.count0 = averaging ? *count_state_host : 0;
-  a.avg_state = avg_state; a.max_hold = max_hold; a.min_hold = min_hold;
-  a.max_valid0 = hold_valid_host ? hold_valid_host[0] : 0;
-  a.min_valid0 = hold_valid_host ? hold_valid_host[1] : 0;
-  a.has_value = row_flags_scratch; a.rows_out = rows_out;
-  a.tare_mode = tare ? ((tare_flags_host[0] ? 1 : 0) | (tare_flags_host[1] ? 2 : 0)) : 0;
-  a.tare_count0 = tare ? *tare_count_host : 0; a.tare_target = tare_target; a.tare_buf = tare_buf; a.tare_baseline = tare_baseline;
-  trace_update_kernel<<<(unsigned)((width + 255) / 256), 256, 0, s>>>(a);
-  count_launch();
-  CK(cudaGetLastError());
-  // host-side scalars need the number of non-NaN rows: read the flags back (tiny, synchronous)
-  std::vector<int32_t> flags(n_rows);
-  CK(cudaMemcpyAsync(flags.data(), row_flags_scratch, sizeof(int32_t) * n_rows, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
-  int64_t live = 0;
-  for (int32_t v : flags) live += v != 0;
-  if (live > 0) {
-    if (tare && tare_flags_host[0]) {            // TareState bookkeeping, display_data_processor.py:335-358
-      const int64_t c = (int64_t)*tare_count_host + live;
-      if (c >= tare_target) { tare_flags_host[0] = 0; tare_flags_host[1] = 1; *tare_count_host = 0; }
-      else *tare_count_host = (int32_t)c;
-    }
-    if (averaging) {
-      int c = *count_state_host;
-      if (avg_mode == TDSA_AVG_LIN) c = (int)std::min<int64_t>(avg_n, (int64_t)c + live);
-      else c = std::max(c, 1);
-      *count_state_host = c;
-    }
-    if (hold_valid_host) {
-      if (max_hold) hold_valid_host[0] = 1;
-      if (min_hold) hold_valid_host[1] = 1;
-    }
+  int32_t* d_flags = nullptr;
+  CK(cudaMallocAsync((void**)&d_flags, kFlagWords * sizeof(int32_t), s));
+  int32_t h[kFlagWords] = {};
+  h[kFlagCount] = averaging ? *count_state_host : 0;
+  h[kFlagMaxValid] = hold_valid_host ? hold_valid_host[0] : 0;
+  h[kFlagMinValid] = hold_valid_host ? hold_valid_host[1] : 0;
+  if (tare) { h[kFlagTareCollecting] = tare_flags_host[0]; h[kFlagTareActive] = tare_flags_host[1]; h[kFlagTareCount] = *tare_count_host; }
+  cudaError_t e = cudaMemcpyAsync(d_flags, h, sizeof h, cudaMemcpyHostToDevice, s);
+  int rc = e == cudaSuccess ? trace_update_dev_impl(rows, n_rows, width, cal_offset_db, avg_mode, avg_n, avg_state, max_hold, min_hold,
+                                                    d_flags, rows_out, cuda_stream, row_flags_scratch, tare_target,
+                                                    tare ? tare_buf : nullptr, tare ? tare_baseline : nullptr)
+                            : fail(TDSA_ERR_CUDA, "flag upload failed: %s", cudaGetErrorString(e));
+  if (rc == TDSA_OK) {
+    e = cudaMemcpyAsync(h, d_flags, sizeof h, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = fail(TDSA_ERR_CUDA, "flag read-back failed: %s", cudaGetErrorString(e));
   }
+  cudaFreeAsync(d_flags, s);
+  if (rc) return rc;
+  if (averaging) *count_state_host = h[kFlagCount];
+  if (hold_valid_host) { hold_valid_host[0] = h[kFlagMaxValid]; hold_valid_host[1] = h[kFlagMinValid]; }
+  if (tare) { tare_flags_host[0] = h[kFlagTareCollecting]; tare_flags_host[1] = h[kFlagTareActive]; *tare_count_host = h[kFlagTareCount]; }
   return TDSA_OK;
 }
 
@@ -791,8 +1055,9 @@ int tdsa_top_peaks(const float* power, int64_t width, int n, int min_sep_bins, f
   if (n < 1 || n > 16) return fail(TDSA_ERR_INVALID, "n must be in [1, 16]");
   if (width > 16384) return fail(TDSA_ERR_UNSUPPORTED, "top_peaks supports rows of up to 16384 bins");
   constexpr int kSmem = 8192 * 8;
-  static bool once = false;
-  if (!once) { CK(cudaFuncSetAttribute(top_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); once = true; }
+  static bool once[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!once[dev]) { CK(cudaFuncSetAttribute(top_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); once[dev] = true; }
   if (width < 3) { CK(cudaMemsetAsync(count_out, 0, sizeof(int32_t), (cudaStream_t)cuda_stream)); return TDSA_OK; }
   top_peaks_kernel<<<1, 1024, kSmem, (cudaStream_t)cuda_stream>>>(power, (int)width, n, min_sep_bins, min_excursion_db, idx_out,
                                                                pwr_out, count_out);
@@ -908,6 +1173,52 @@ int tdsa_ring_push(const float* rows, int64_t n_rows, float* ring, int64_t H, in
   return TDSA_OK;
 }
 
+int tdsa_ring_push_dev(const float* rows, int64_t n_rows, float* ring, int64_t H, int64_t W, int64_t* state_dev,
+                       float* last_row_dev, int dedupe, int64_t* slot_scratch, int32_t* differs_scratch, void* cuda_stream) {
+  if (!rows || !ring || !state_dev || !slot_scratch || H < 1 || W < 1 || n_rows < 0) return fail(TDSA_ERR_INVALID, "bad argument");
+  if (dedupe && (!last_row_dev || !differs_scratch)) return fail(TDSA_ERR_INVALID, "dedupe needs last_row_dev and differs_scratch");
+  if (n_rows == 0) return TDSA_OK;
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  if (dedupe) {
+    ring_row_differs_kernel<<<(unsigned)n_rows, 256, 0, s>>>(rows, n_rows, W, last_row_dev, state_dev, differs_scratch);
+    count_launch();
+  }
+  ring_assign_kernel<<<1, 32, 0, s>>>(differs_scratch, n_rows, H, state_dev, slot_scratch, dedupe ? 1 : 0);
+  count_launch();
+  dim3 g((unsigned)((W + 255) / 256), (unsigned)n_rows);
+  ring_scatter_kernel<<<g, 256, 0, s>>>(rows, n_rows, W, H, slot_scratch, state_dev, ring, last_row_dev);
+  count_launch();
+  CK(cudaGetLastError());
+  return TDSA_OK;
+}
+
+int tdsa_ring_image_rgba(const float* ring, int64_t H, int64_t W, const int64_t* state_dev, float lo_db, float hi_db,
+                         const uint8_t* lut_rgba, uint8_t* rgba_out, void* cuda_stream) {
+  if (!ring || !state_dev || !lut_rgba || !rgba_out || H < 1 || W < 1) return fail(TDSA_ERR_INVALID, "bad argument");
+  const float den = fmaxf(hi_db - lo_db, 1e-9f);
+  const int64_t total = H * W;
+  ring_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(ring, H, W, state_dev, lo_db, den,
+                                                                                         (const uchar4*)lut_rgba, (uchar4*)rgba_out);
+  count_launch();
+  CK(cudaGetLastError());
+  return TDSA_OK;
+}
+
+int tdsa_find_peaks_snap(const float* levels, int64_t width, float height, float prominence, int distance, int32_t* out,
+                         void* cuda_stream) {
+  if (!levels || !out) return fail(TDSA_ERR_INVALID, "null argument");
+  if (width < 1) return fail(TDSA_ERR_INVALID, "empty trace");
+  if (width > 16384) return fail(TDSA_ERR_UNSUPPORTED, "find_peaks_snap supports rows of up to 16384 bins");
+  constexpr int kSmem = 8192 * (4 + 4 + 4 + 1);
+  static bool once[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!once[dev]) { CK(cudaFuncSetAttribute(find_peaks_snap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); once[dev] = true; }
+  find_peaks_snap_kernel<<<1, 1024, kSmem, (cudaStream_t)cuda_stream>>>(levels, (int)width, height, prominence, distance < 1 ? 1 : distance, out);
+  count_launch();
+  CK(cudaGetLastError());
+  return TDSA_OK;
+}
+
 int tdsa_h2d_async(const void* pinned_host, void* dev, size_t bytes, void* side_stream, void* done_event) {
   if (!pinned_host || !dev) return fail(TDSA_ERR_INVALID, "null pointer");
   CK(cudaMemcpyAsync(dev, pinned_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)side_stream));
@@ -921,6 +1232,7 @@ int tdsa_psd_db_batch_host(tdsa_handle_t p, const void* iq_host, int64_t n_frame
   if (n_frames < 0 || stride < 1) return fail(TDSA_ERR_INVALID, "bad frame geometry");
   if (n_frames == 0) return TDSA_OK;
   if (!iq_host || !db_out_host) return fail(TDSA_ERR_INVALID, "null buffer");
+  DeviceGuard guard(p->device);
   const int64_t n = p->n;
   if (chunk_frames < 1) chunk_frames = std::max<int64_t>(1, ((int64_t)16 << 20) / (n * 8));   // ~16 MiB of IQ per chunk (measured best of 4..64 MiB)
   chunk_frames = std::min(chunk_frames, n_frames);
@@ -966,6 +1278,7 @@ int tdsa_psd_db_batch_host(tdsa_handle_t p, const void* iq_host, int64_t n_frame
 int tdsa_plan_info(tdsa_handle_t p, int* n_fft, int* threads, int* ctas_per_sm, int* smem, int* grid) {
   if (!p) return fail(TDSA_ERR_INVALID, "null plan");
   LaunchInfo info;
+  DeviceGuard guard(p->device);
   int rc = run_fused(p, nullptr, 1 << 20, p->n, nullptr, kEpiDb, nullptr, nullptr, &info, true);
   if (rc) return rc;
   if (n_fft) *n_fft = p->n;

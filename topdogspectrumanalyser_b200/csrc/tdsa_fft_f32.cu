@@ -8,10 +8,6 @@ int effective_logr_f32(int log2n) { return effective_logr<float>(log2n); }
 cudaError_t launch_welch_cluster_f32(const WelchClusterArgs<float>& a, int clusters, cudaStream_t s, int* max_clusters) {
   return launch_welch_cluster_impl<float>(a, clusters, s, max_clusters);
 }
-cudaError_t launch_wl_f32(int epi, const FftArgs<float>& a, const CUtensorMap& tmap, const float* wperm, WlSched sched,
-                          int sm, cudaStream_t s, LaunchInfo* info, bool dry) {
-  return launch_wl_impl<float>(epi, a, tmap, wperm, sched, sm, s, info, dry);
-}
 }  // namespace tdsa
 
 #include "tdsa_big.cuh"
@@ -25,11 +21,12 @@ cudaError_t launch_big_head_f32(const BigArgs<float>& a, int sm, cudaStream_t s,
     return cudaGetLastError();
   }
   constexpr int kSmem = 4096 * 2 * sizeof(float);
-  static bool once = false;
-  if (!once) {
+  static bool once[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!once[dev]) {
     cudaError_t e = cudaFuncSetAttribute(big_head_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return e;
-    once = true;
+    once[dev] = true;
   }
   const int64_t work = a.n_frames * (((int64_t)1 << a.log2n) >> 12);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(work, (int64_t)sm * 4));

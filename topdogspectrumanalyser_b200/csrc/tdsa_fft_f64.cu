@@ -8,10 +8,6 @@ int effective_logr_f64(int log2n) { return effective_logr<double>(log2n); }
 cudaError_t launch_welch_cluster_f64(const WelchClusterArgs<double>& a, int clusters, cudaStream_t s, int* max_clusters) {
   return launch_welch_cluster_impl<double>(a, clusters, s, max_clusters);
 }
-cudaError_t launch_wl_f64(int epi, const FftArgs<double>& a, const CUtensorMap& tmap, const double* wperm, WlSched sched,
-                          int sm, cudaStream_t s, LaunchInfo* info, bool dry) {
-  return launch_wl_impl<double>(epi, a, tmap, wperm, sched, sm, s, info, dry);
-}
 }  // namespace tdsa
 
 #include "tdsa_big.cuh"
@@ -25,11 +21,12 @@ cudaError_t launch_big_head_f64(const BigArgs<double>& a, int sm, cudaStream_t s
     return cudaGetLastError();
   }
   constexpr int kSmem = 4096 * 2 * sizeof(double);
-  static bool once = false;
-  if (!once) {
+  static bool once[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!once[dev]) {
     cudaError_t e = cudaFuncSetAttribute(big_head_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return e;
-    once = true;
+    once[dev] = true;
   }
   const int64_t work = a.n_frames * (((int64_t)1 << a.log2n) >> 12);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(work, (int64_t)sm * 2));

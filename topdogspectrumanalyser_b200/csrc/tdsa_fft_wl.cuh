@@ -1,4 +1,5 @@
-// tdsa_fft_wl.cuh — "warp-local" variant of the fused window + FFT + |.|^2 + dB kernel for N = 4096.
+// tdsa_fft_wl.cuh — "warp-local" fused window + FFT + |.|^2 + dB kernel for N = 4096 (one engine) and N = 8192
+// (two engines), with an optional accumulating epilogue whose per-bin state lives in tensor memory (TMEM).
 //
 // Same arithmetic as fft_fused_kernel (tdsa_fft.cuh; reference datasources/rtl_samples.py:169-184), different
 // schedule.  Phase time stamps of fft_fused_kernel (profiles/r01_phase_timing.md) showed that its three CTA-wide
@@ -6,18 +7,32 @@
 // shared-memory pipe are used one after the other instead of together, and that the two CTAs of an SM run at
 // very different speeds, which a static frame assignment turns into an idle tail.  Here:
 //
-//   * decimation in time over the FIRST factor: N = 16 x 256, n = r + 16 m.  The sixteen 256-point
-//     sub-transforms Y_r = FFT256(x[r + 16 m] w[r + 16 m]) are each computed by a team of 16 lanes (two teams
-//     per warp): radix-16 pass A, a 16x16 transpose through the team's private shared-memory region ordered by
-//     __syncwarp only, radix-16 pass B.  Warps are independent of each other for two of the three passes.
-//   * one CTA-wide exchange: X[kk + 256 q] = sum_r W16^(r q) W4096^(r kk) Y_r[kk]; thread kk reads the sixteen
-//     Y_r[kk] (stride = region pitch, conflict-free) and stores bins kk + 256 q (coalesced), as before.
-//   * the frame is staged by ONE cp.async.bulk.tensor (TMA, 3-D tensor map [frame][256 rows][128 B]) with the
-//     128-byte swizzle, so that a team's stride-16 sample reads (row m, column r) are bank-conflict free.
+//   * an ENGINE is 256 threads computing one 4096-point transform by decimation in time over the first factor,
+//     4096 = 16 x 256, n = r + 16 m.  The sixteen 256-point sub-transforms Y_r are each computed by a team of 16
+//     lanes (two teams per warp): radix-16 pass A, a 16x16 transpose through the team's private shared-memory
+//     region ordered by __syncwarp only, radix-16 pass B.  Warps are independent for two of the three passes.
+//   * one engine-wide exchange: X[kk + 256 q] = sum_r W16^(r q) W4096^(r kk) Y_r[kk]; thread kk reads the sixteen
+//     Y_r[kk] (stride = region pitch, conflict-free) and owns bins kk + 256 q (coalesced stores).
+//   * the frame is staged by cp.async.bulk.tensor (TMA, 3-D tensor map [frame][rows][128 B]) with the 128-byte
+//     swizzle, so that a team's stride-16 sample reads (row m, column r) are bank-conflict free.
 //   * frames are claimed from a global counter (dynamic scheduling): the faster CTA of an SM simply takes
 //     more frames; the counter re-arms itself when the last CTA leaves.
 //
-// Twiddle tables are the ones of the 4096-point DIT plan (pass 1: [j][K] = W256^(jK); last pass: [j][b]).
+// N = 8192 (NB = 2): one radix-2 decimation-in-frequency step is folded into the staged read.  Both engines read
+// x[n] w[n] and x[n + 4096] w[n + 4096] from the same 64 KB stage; engine 0 transforms their sum (even bins),
+// engine 1 their difference with every twiddle table evaluated at the half-integer bin k + 1/2 (odd bins:
+// X[2k+1] = sum_n d[n] W4096^(n (k + 1/2))), which costs fifteen constant W32^j multiplies in pass A and nothing
+// else.  The engines synchronise internally with named barriers and meet only at the stage hand-back (mbarrier).
+//
+// Accumulating epilogue (ACC != 0): per-bin running state over the frames a CTA processes — weighted sum of
+// |X|^2 (float64), max and min of |X|^2 (float32) — for order-free reductions: the running average of
+// TraceAverager (utils/signal_processing.py:35-61) written as a weighted sum, max/min hold on un-averaged rows
+// (core/display_data_processor.py:371-395), Welch mean + peak (config 3) and per-sub-band means (config 4).
+// Sixteen bins x 16 bytes per thread do not fit the register budget next to a float64 radix-16 butterfly, so the
+// state is kept in TMEM (tcgen05.alloc / tcgen05.ld / tcgen05.st, 64 columns per thread's lane; no tensor-core
+// math is involved) and flushed to per-CTA partial rows at the end of the launch.
+//
+// Twiddle tables per engine: [0, 256): pass B, entry [j][ka]; [256, 4352): last pass, entry [j][kk].
 #pragma once
 #include <cuda.h>
 
@@ -25,14 +40,31 @@
 
 namespace tdsa {
 
-template <typename T> struct WlPlan {
-  static constexpr int N = 4096, TH = 256;
+enum : int { kAccSum = 1, kAccMax = 2, kAccMin = 4, kAccGroup = 8, kAccRows = 16 };
+
+// arguments of the accumulating epilogue
+struct WlAcc {
+  const double* weight = nullptr;   // [n_frames] weight of frame f in the sum; nullptr = 1
+  const int32_t* skip = nullptr;    // [n_frames] 1 = the frame leaves all state untouched (hackrf silence hold); nullptr = none
+  double* part_sum = nullptr;       // [grid][N] per-CTA partial weighted sums (kAccSum without kAccGroup)
+  float* part_max = nullptr;        // [grid][N] per-CTA running max of |X|^2 (-inf = no live frame)
+  float* part_min = nullptr;        // [grid][N] per-CTA running min of |X|^2 (+inf = no live frame)
+  float* group_db = nullptr;        // kAccGroup: [n_frames / group][N] dB of each group's mean
+  int group = 1;                    // frames per claimed unit (kAccGroup: frames per group)
+  int64_t only_row = -1;            // kAccRows: >= 0 stores the dB row of this frame only (at row 0), -1 stores every row
+};
+
+constexpr int kWlTwPerEngine = 256 + 4096;
+
+template <typename T, int NB = 1> struct WlPlan {
+  static constexpr int N = 4096 * NB, TH = 256 * NB;
   static constexpr int REGION = 272 + (sizeof(T) == 4 ? 8 : 0);      // elements per team region (pitch-17 rows + bank offset)
-  static constexpr int EX_ELEMS = 16 * REGION;
-  static constexpr int TW_SMEM = 256;                                 // pass-B table [j][K]
-  static constexpr size_t EX_BYTES = (size_t)(EX_ELEMS + TW_SMEM) * 2 * sizeof(T);
+  static constexpr int EX_ELEMS = 16 * REGION;                        // per engine
+  static constexpr int TW_SMEM = 256;                                 // pass-B table [j][ka], per engine
+  static constexpr size_t ENGINE_BYTES = (size_t)(EX_ELEMS + TW_SMEM) * 2 * sizeof(T);
+  static constexpr size_t EX_BYTES = ENGINE_BYTES * NB;
   static constexpr size_t STAGE_BYTES = (size_t)N * 8;
-  static constexpr size_t CTRL_BYTES = 128;                           // mbarriers + frame slots
+  static constexpr size_t CTRL_BYTES = 128;                           // mbarriers (full[4], empty[4]), frame slots, TMEM base
   static __host__ __device__ constexpr size_t smem_bytes(int nstage) {
     return ((EX_BYTES + CTRL_BYTES + 1023) & ~(size_t)1023) + 1024 + (size_t)nstage * STAGE_BYTES;
   }
@@ -45,98 +77,190 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst_smem, const CUtensorMap
       : "memory");
 }
 
-// L2 prefetch of one frame through the tensor map (no shared-memory destination, no completion)
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1),
-               "r"(c2)
-               : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// ---- tensor memory as per-thread scratch: 32x32b shape = lane <-> thread, consecutive columns <-> registers ------
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, int cols) {
+  if (cols == 128) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_dst) : "memory");
+  else asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_dst) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, int cols) {
+  if (cols == 128) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(taddr) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+               "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 struct WlSched {
-  int* next;       // next unclaimed frame
+  int* next;       // next unclaimed unit (frame, or group of frames)
   int* done;       // CTAs that have left the frame loop
 };
 
-template <typename T, typename Epi, int TWMODE, int NSTAGE, bool HAS_DC, int MIN_CTAS, bool L2_AHEAD, bool TWB_BASE>
-__global__ void __launch_bounds__(256, MIN_CTAS)
-fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, const T* __restrict__ wperm, WlSched sched) {
-  using W = WlPlan<T>;
+// W32^j = exp(-2 pi i j / 32), j = 0..15 (pass-A pre-twiddles of the half-bin engine); j is a compile-time constant
+// at every use (unrolled loops), so these fold to immediates
+template <typename T> __device__ __forceinline__ T w32_cos(int j) {
+  constexpr double c[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                            0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785,
+                            0.0, -0.19509032201612826785, -0.38268343236508977173, -0.55557023301960222474,
+                            -0.70710678118654752440, -0.83146961230254523708, -0.92387953251128675613, -0.98078528040323044913};
+  return (T)c[j];
+}
+template <typename T> __device__ __forceinline__ T w32_msin(int j) {   // imaginary part: -sin(2 pi j / 32)
+  constexpr double s[16] = {0.0, -0.19509032201612826785, -0.38268343236508977173, -0.55557023301960222474,
+                            -0.70710678118654752440, -0.83146961230254523708, -0.92387953251128675613, -0.98078528040323044913,
+                            -1.0, -0.98078528040323044913, -0.92387953251128675613, -0.83146961230254523708,
+                            -0.70710678118654752440, -0.55557023301960222474, -0.38268343236508977173, -0.19509032201612826785};
+  return (T)s[j];
+}
+
+template <typename T, typename Epi, int TWMODE, int NSTAGE, bool HAS_DC, int MIN_CTAS, bool TWB_BASE, int NB, int ACC>
+__global__ void __launch_bounds__(256 * NB, MIN_CTAS)
+fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, const T* __restrict__ wperm, WlSched sched,
+              const WlAcc acc) {
+  using W = WlPlan<T, NB>;
   using CT = typename CplxOf<T>::type;
   constexpr int N = W::N, TH = W::TH, REGION = W::REGION;
+  constexpr int kTmemCols = 64 * 2 * NB;                                   // 64 columns per warp, NB * 2 warps per lane quarter
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  CT* ex = reinterpret_cast<CT*>(smem_raw);
-  CT* tws = ex + W::EX_ELEMS;
   const uint32_t base_u32 = smem_u32(smem_raw);
-  const uint32_t ctrl_u32 = base_u32 + (uint32_t)W::EX_BYTES;                    // NSTAGE mbarriers, then frame slots
-  volatile int* slot = reinterpret_cast<volatile int*>(smem_raw + W::EX_BYTES + 64);
+  const uint32_t ctrl_u32 = base_u32 + (uint32_t)W::EX_BYTES;              // full[4] at +0, empty[4] at +32
+  volatile int* slot = reinterpret_cast<volatile int*>(smem_raw + W::EX_BYTES + 64);      // staged frame per stage
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + W::EX_BYTES + 96);
   const uint32_t stage_u32 = (base_u32 + (uint32_t)(W::EX_BYTES + W::CTRL_BYTES) + 1023u) & ~1023u;
   const unsigned char* stage_ptr = smem_raw + (stage_u32 - base_u32);
 
   const int tid = (int)threadIdx.x;
-  const int w = tid >> 5, l = tid & 31;
+  const int e = NB == 1 ? 0 : (tid >> 8);                   // engine
+  const int te = tid & 255;                                 // thread inside the engine = bin identity kk of the last pass
+  const int w = te >> 5, l = tid & 31;
   // lane -> (team half h, team lane c): each half-warp of lanes covers all eight 16-byte swizzle chunks and both
   // 8-byte halves, so the 64-bit staged reads are conflict free
   const int h = (l >> 3) & 1, c = (l & 7) + 8 * (l >> 4);
   const int r = 2 * w + h;                                  // sub-transform (team) 0..15
+  CT* ex = reinterpret_cast<CT*>(smem_raw + (size_t)e * W::ENGINE_BYTES);
+  CT* tws = ex + W::EX_ELEMS;
   CT* reg = ex + r * REGION;
+  const CT* twe = a.tw + e * kWlTwPerEngine;                // this engine's tables
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) mbar_init(ctrl_u32 + 8 * s, 1);
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(ctrl_u32 + 8 * s, 1);
+      if constexpr (NB > 1) mbar_init(ctrl_u32 + 32 + 8 * s, 8 * NB);     // one arrival per warp
+    }
     fence_mbar_init();
   }
-  for (int i = tid; i < W::TW_SMEM; i += TH) tws[i] = a.tw[i];
+  for (int i = te; i < W::TW_SMEM; i += 256) tws[i] = twe[i];
+  uint32_t tacc = 0;                                        // TMEM address of this thread's 64 accumulator columns
+  if constexpr (ACC != 0) {
+    if ((tid >> 5) == 0) tmem_alloc(base_u32 + (uint32_t)W::EX_BYTES + 96, kTmemCols);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
 
-  // per-thread constants: window values of pass A (team identity) and last-pass pre-twiddles (bin identity tid)
-  const CT* tw_last = a.tw + 256;                           // Plan<T,12>::tw_offset(2)
-  T win[16];
+  // per-thread constants: window values of pass A (team identity) and last-pass pre-twiddles (bin identity te)
+  const CT* tw_last = twe + 256;
+  constexpr int NWIN = 16 * NB;
+  T win[NWIN];
   T twlr[16], twli[16];
   if constexpr (TWMODE == 1) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) win[j] = wperm[j * TH + tid];
+    for (int j = 0; j < NWIN; ++j) win[j] = wperm[j * TH + tid];
 #pragma unroll
-    for (int j = 1; j < 16; ++j) { const CT x = tw_last[j * 256 + tid]; twlr[j] = x.x; twli[j] = x.y; }
+    for (int j = 1; j < 16; ++j) { const CT x = tw_last[j * 256 + te]; twlr[j] = x.x; twli[j] = x.y; }
   } else {
 #pragma unroll
     for (int j = 1; j < 16; ++j) {
-      if (j < 4 || (j & 3) == 0) { const CT x = tw_last[j * 256 + tid]; twlr[j] = x.x; twli[j] = x.y; }
+      if (j < 4 || (j & 3) == 0) { const CT x = tw_last[j * 256 + te]; twlr[j] = x.x; twli[j] = x.y; }
     }
   }
 
-  // pass-B twiddles W256^(j c) depend on the thread's team lane only: optionally six of them stay in registers
+  // pass-B twiddles depend on the thread's team lane only: optionally six of them stay in registers
   T twbr[TWB_BASE ? 16 : 1], twbi[TWB_BASE ? 16 : 1];
   if constexpr (TWB_BASE) {
 #pragma unroll
     for (int j = 1; j < 16; ++j) {
-      if (j < 4 || (j & 3) == 0) { const CT x = a.tw[j * 16 + c]; twbr[j] = x.x; twbi[j] = x.y; }
+      if (j < 4 || (j & 3) == 0) { const CT x = twe[j * 16 + c]; twbr[j] = x.x; twbi[j] = x.y; }
     }
   }
-  // claim the first NSTAGE frames and start their copies
-  int pend = 0;                                             // thread 0: frame claimed one refill ahead (L2_AHEAD)
+  // frame claims are made in units of `group` consecutive frames (1 unless the epilogue averages groups)
+  const int group = (ACC & kAccGroup) ? acc.group : 1;
+  int unit_base = 0, unit_pos = 0;                          // thread 0: the unit being handed out, frames already taken from it
+  auto next_frame = [&]() -> int {                          // thread 0 only
+    if (unit_pos == 0 || unit_pos == group) {
+      const int u = atomicAdd(sched.next, 1);
+      if ((int64_t)u * group >= a.n_frames) { unit_pos = group; return 0x7fffffff; }
+      unit_base = u * group; unit_pos = 0;
+    }
+    return unit_base + unit_pos++;
+  };
+  // thread 0 only: publish the frame staged in slot s and start its copy; with no frame left the stage's barrier is
+  // completed by a plain arrival so that every waiter wakes up, reads the sentinel and leaves the loop
+  auto issue_stage = [&](int s, int f) {
+    slot[s] = f;
+    if (f < a.n_frames) {
+      mbar_arrive_expect_tx(ctrl_u32 + 8 * s, (uint32_t)W::STAGE_BYTES);
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+        tma_load_3d(stage_u32 + (uint32_t)(s * W::STAGE_BYTES) + (uint32_t)b * 32768u, &tmap, 0, 256 * b, f, ctrl_u32 + 8 * s);
+    } else {
+      mbar_arrive(ctrl_u32 + 8 * s);
+    }
+  };
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) {
-      const int fs = atomicAdd(sched.next, 1);
-      slot[s] = fs;
-      if (fs < a.n_frames) {
-        mbar_arrive_expect_tx(ctrl_u32 + 8 * s, (uint32_t)W::STAGE_BYTES);
-        tma_load_3d(stage_u32 + (uint32_t)(s * W::STAGE_BYTES), &tmap, 0, 0, fs, ctrl_u32 + 8 * s);
-      }
-    }
-    if constexpr (L2_AHEAD) {                               // the frame after those: claimed now, copied one iteration later
-      pend = atomicAdd(sched.next, 1);
-      if (pend < a.n_frames) tma_prefetch_3d(&tmap, 0, 0, pend);
-    }
+    for (int s = 0; s < NSTAGE; ++s) issue_stage(s, next_frame());
   }
   __syncthreads();
+  if constexpr (ACC != 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tacc = *tmem_slot + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)((tid >> 7) * 64);
+    // state: columns [0, 32) sixteen float64 sums, [32, 48) sixteen float32 maxima, [48, 64) sixteen float32 minima
+    uint32_t z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0u;
+    tmem_st16(tacc, z); tmem_st16(tacc + 16, z);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0xff800000u;        // -inf
+    tmem_st16(tacc + 32, z);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = 0x7f800000u;        // +inf
+    tmem_st16(tacc + 48, z);
+    tmem_wait_st();
+  }
   const bool mag20 = a.ep.mode == kModeMag20;
-  // swizzled offset of (row m = c + 16 j, column r) inside a staged frame: 128-byte rows, 16-byte chunk index
-  // XOR (row & 7); r >> 1 == w, r & 1 == h, (c + 16 j) & 7 == c & 7
+  // swizzled offset of (row m = c + 16 j, column r) inside a staged 4096-sample block: 128-byte rows, 16-byte chunk
+  // index XOR (row & 7); r >> 1 == w, r & 1 == h, (c + 16 j) & 7 == c & 7
   const int stage_off = c * 128 + (((w ^ c) & 7) << 4) + h * 8;
+  // engine-internal barriers: NB == 1 uses barrier 0 (__syncthreads), NB == 2 named barriers 1 + e over 256 threads
+  auto engine_sync = [&]() {
+    if constexpr (NB == 1) __syncthreads(); else bar_sync(1 + e, 256);
+  };
 
   for (int it = 0;; ++it) {
     const int stg = it % NSTAGE;
-    const int f = slot[stg];
+    if constexpr (TWMODE != 1) {                             // window values for pass A, re-read every frame (register budget)
+#pragma unroll
+      for (int j = 0; j < NWIN; ++j) win[j] = wperm[j * TH + tid];
+    }
+    TDSA_STAMP(0);
+    mbar_wait(ctrl_u32 + 8 * stg, (uint32_t)((it / NSTAGE) & 1));
+    const int f = slot[stg];                                 // written by thread 0 before it armed / completed the barrier
     if (f >= a.n_frames) break;
 #ifdef TDSA_DEBUG_TIMING
     if (it == 0 && tid == 0 && a.dbg != nullptr) {
@@ -144,75 +268,60 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       a.dbg[(int64_t)gridDim.x * 8 * 32 * 16 + blockIdx.x] = smid;
     }
 #endif
-    TDSA_STAMP(0);
     T re[16], im[16];
     // ---- pass A: staged samples -> registers, window, radix 16 over j (samples r + 16 c + 256 j) ----------
     {
-      if constexpr (TWMODE != 1) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) win[j] = wperm[j * TH + tid];
-      }
       T dcr = T(0), dci = T(0);
       if constexpr (HAS_DC) { const double2 d = a.dc[f]; dcr = (T)d.x; dci = (T)d.y; }
-      mbar_wait(ctrl_u32 + 8 * stg, (uint32_t)((it / NSTAGE) & 1));
       TDSA_STAMP(1);
       const unsigned char* src = stage_ptr + (size_t)stg * W::STAGE_BYTES + stage_off;
       float2 v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(src + j * 2048);
-      if constexpr (sizeof(T) == 8 && TDSA_INT_WIDEN == 2) {
-        float probe = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          nonfinite_probe(v[j].x, probe); nonfinite_probe(v[j].y, probe);
-          re[j] = widen_lean(v[j].x); im[j] = widen_lean(v[j].y);
-        }
-        if (probe != probe) re[0] = (T)probe;                // an Inf/NaN sample: the whole frame becomes NaN, as in the reference
-        if constexpr (HAS_DC) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { re[j] -= dcr; im[j] -= dci; }
-        }
-      } else if constexpr (sizeof(T) == 8 && TDSA_INT_WIDEN == 1) {
-        // integer-pipe widening; the largest |bits| seen tells whether an Inf/NaN went through (exponent 0xFF)
-        uint32_t top = 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          re[j] = widen_track(v[j].x, top);
-          im[j] = widen_track(v[j].y, top);
-        }
-        if (top >= 0x7f800000u) {                            // rare: redo from the staged frame with the hardware conversion
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 x = *reinterpret_cast<const float2*>(src + j * 2048);
-            re[j] = (T)x.x; im[j] = (T)x.y;
-          }
-        }
-        if constexpr (HAS_DC) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { re[j] -= dcr; im[j] -= dci; }
-        }
+      for (int j = 0; j < 16; ++j) {
+        if constexpr (HAS_DC) { re[j] = (T)v[j].x - dcr; im[j] = (T)v[j].y - dci; }
+        else { re[j] = (T)v[j].x; im[j] = (T)v[j].y; }
+      }
+      if constexpr (NB == 1) {
+        dft16_win<T>(re, im, win);
       } else {
+        // radix-2 DIF step on the staged read: s[n] = x[n] w[n] +- x[n + 4096] w[n + 4096] (the sign lives in the table)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(src + 32768 + j * 2048);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          if constexpr (HAS_DC) { re[j] = (T)v[j].x - dcr; im[j] = (T)v[j].y - dci; }
-          else { re[j] = (T)v[j].x; im[j] = (T)v[j].y; }
+          T hr = (T)v[j].x, hi = (T)v[j].y;
+          if constexpr (HAS_DC) { hr -= dcr; hi -= dci; }
+          re[j] = fm<T>(hr, win[16 + j], re[j] * win[j]);
+          im[j] = fm<T>(hi, win[16 + j], im[j] * win[j]);
+        }
+        if (e == 0) {
+          dft16<T>(re, im);
+        } else {                                             // half-bin transform: inputs carry W32^j
+          T cr[16], ci[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { cr[j] = w32_cos<T>(j); ci[j] = w32_msin<T>(j); }
+          dft16_pretw<T>(re, im, cr, ci);
         }
       }
-      dft16_win<T>(re, im, win);
     }
     TDSA_STAMP(2);
     // ---- team-local 16x16 transpose: A_c[ka] at position c + 16 ka, row pitch 17 ---------------------------
 #pragma unroll
     for (int q = 0; q < 16; ++q) reg[c + 17 * q] = mk<T>(re[q], im[q]);
     __syncwarp();
+    if constexpr (NB > 1) {                                  // this warp's samples of the stage are consumed
+      if (l == 0) mbar_arrive(ctrl_u32 + 32 + 8 * stg);
+    }
     int fnext = 0;
-    if (tid == 0) fnext = atomicAdd(sched.next, 1);          // consumed after the CTA-wide barrier below
+    if (tid == 0) fnext = next_frame();                      // consumed after the barrier below
     TDSA_STAMP(3);
-    // ---- pass B: thread ka = c reads A_j[ka] (j = 0..15), pre-twiddle W256^(j ka), radix 16 over j ----------
+    // ---- pass B: thread ka = c reads A_j[ka] (j = 0..15), pre-twiddle [j][ka], radix 16 over j --------------
     {
       T wr[16], wi[16];
       wr[0] = T(1); wi[0] = T(0);
-      if constexpr (TWB_BASE) {                              // W256^(j c) from six base twiddles held in registers
+      if constexpr (TWB_BASE) {                              // powers of one root: six base twiddles held in registers
 #pragma unroll
         for (int j = 1; j < 16; ++j) {
           if (j < 4 || (j & 3) == 0) { wr[j] = twbr[j]; wi[j] = twbi[j]; }
@@ -232,29 +341,20 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
 #pragma unroll
     for (int q = 0; q < 16; ++q) reg[c + 17 * q] = mk<T>(re[q], im[q]);
     TDSA_STAMP(5);
-    __syncthreads();                                         // all sixteen Y_r complete; every warp has left this stage
+    engine_sync();                                           // all sixteen Y_r complete; every warp has left this stage
     TDSA_STAMP(6);
     if (tid == 0) {
-      // L2_AHEAD: copy the frame claimed (and prefetched into L2) one iteration ago, prefetch the one claimed now
-      const int fcopy = L2_AHEAD ? pend : fnext;
-      slot[stg] = fcopy;
-      if (fcopy < a.n_frames) {
-        fence_proxy_async();
-        mbar_arrive_expect_tx(ctrl_u32 + 8 * stg, (uint32_t)W::STAGE_BYTES);
-        tma_load_3d(stage_u32 + (uint32_t)(stg * W::STAGE_BYTES), &tmap, 0, 0, fcopy, ctrl_u32 + 8 * stg);
-      }
-      if constexpr (L2_AHEAD) {
-        pend = fnext;
-        if (pend < a.n_frames) tma_prefetch_3d(&tmap, 0, 0, pend);
-      }
+      if constexpr (NB > 1) mbar_wait(ctrl_u32 + 32 + 8 * stg, (uint32_t)((it / NSTAGE) & 1));   // the other engine too
+      fence_proxy_async();
+      issue_stage(stg, fnext);
     }
-    // ---- last pass: thread kk = tid reads Y_j[kk], pre-twiddle W4096^(j kk), radix 16 over j ----------------
+    // ---- last pass: thread kk = te reads Y_j[kk], pre-twiddle [j][kk], radix 16 over j ----------------------
     {
-      const CT* col = ex + tid + (tid >> 4);
+      const CT* col = ex + te + (te >> 4);
 #pragma unroll
       for (int j = 0; j < 16; ++j) { const CT x = col[j * REGION]; re[j] = x.x; im[j] = x.y; }
     }
-    __syncthreads();                                         // regions may be overwritten by the next frame's pass A
+    engine_sync();                                           // regions may be overwritten by the next frame's pass A
     TDSA_STAMP(7);
     {
       T wr[16], wi[16];
@@ -270,16 +370,112 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       dft16_pretw<T>(re, im, wr, wi);
     }
     TDSA_STAMP(8);
-    auto emit = [&](auto mag_tag) {
-      constexpr bool MAG = decltype(mag_tag)::value;
+    // bin of output q: NB == 1: te + 256 q; NB == 2: engine e owns bins of parity e
+    auto bin_of = [&](int q) { return NB == 1 ? te + 256 * q : 2 * (te + 256 * q) + e; };
+    if constexpr (ACC == 0 || (ACC & kAccRows) != 0) {
+      const bool store_row = (ACC == 0) || acc.only_row < 0 || acc.only_row == (int64_t)f;
+      const int64_t row = (ACC != 0 && acc.only_row >= 0) ? 0 : (int64_t)f;
+      auto emit = [&](auto mag_tag) {
+        constexpr bool MAG = decltype(mag_tag)::value;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const T pw = re[q] * re[q] + im[q] * im[q];
-        Epi::template store<T, MAG>(a.ep, (int64_t)f, N, tid + 256 * q, pw);
+        for (int q = 0; q < 16; ++q) {
+          const T pw = re[q] * re[q] + im[q] * im[q];
+          if constexpr (ACC != 0) re[q] = pw;                // keep the power for the accumulators
+          if (store_row) Epi::template store<T, MAG>(a.ep, row, N, bin_of(q), pw);
+        }
+      };
+      if (mag20) emit(std::true_type{}); else emit(std::false_type{});
+    } else {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) re[q] = re[q] * re[q] + im[q] * im[q];
+    }
+    if constexpr (ACC != 0) {
+      // ---- accumulate |X|^2 of the thread's sixteen bins into its TMEM columns -------------------------------
+      const bool live = acc.skip == nullptr || acc.skip[f] == 0;
+      tmem_wait_st();                                        // the previous frame's updates have landed
+      if (live) {
+        if constexpr ((ACC & kAccSum) != 0) {
+          const double wgt = acc.weight != nullptr ? acc.weight[f] : 1.0;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t u[16];
+            tmem_ld16(tacc + 16 * half, u);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const double s = __hiloint2double((int)u[2 * i + 1], (int)u[2 * i]);
+              const double t = __fma_rn(wgt, (double)re[8 * half + i], s);
+              u[2 * i] = (uint32_t)__double2loint(t); u[2 * i + 1] = (uint32_t)__double2hiint(t);
+            }
+            tmem_st16(tacc + 16 * half, u);
+          }
+        }
+        if constexpr ((ACC & kAccMax) != 0) {
+          uint32_t u[16];
+          tmem_ld16(tacc + 32, u);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) u[i] = __float_as_uint(fmaxf(__uint_as_float(u[i]), (float)re[i]));
+          tmem_st16(tacc + 32, u);
+        }
+        if constexpr ((ACC & kAccMin) != 0) {
+          uint32_t u[16];
+          tmem_ld16(tacc + 48, u);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) u[i] = __float_as_uint(fminf(__uint_as_float(u[i]), (float)re[i]));
+          tmem_st16(tacc + 48, u);
+        }
       }
-    };
-    if (mag20) emit(std::true_type{}); else emit(std::false_type{});
+      if constexpr ((ACC & kAccGroup) != 0) {
+        if ((f + 1) % group == 0) {                          // last frame of its group: emit the mean as one dB row, clear
+          tmem_wait_st();
+          float* row = acc.group_db + (int64_t)(f / group) * N;
+          const double inv = 1.0 / (double)group;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t u[16];
+            tmem_ld16(tacc + 16 * half, u);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const double s = __hiloint2double((int)u[2 * i + 1], (int)u[2 * i]);
+              row[bin_of(8 * half + i)] = to_db_m<double, false>(s * inv, a.ep);
+              u[2 * i] = 0u; u[2 * i + 1] = 0u;
+            }
+            tmem_st16(tacc + 16 * half, u);
+          }
+        }
+      }
+    }
     TDSA_STAMP(9);
+  }
+  if constexpr (ACC != 0) {
+    // ---- flush the per-CTA partial rows, release the tensor memory ---------------------------------------------
+    tmem_wait_st();
+    auto bin_of = [&](int q) { return NB == 1 ? te + 256 * q : 2 * (te + 256 * q) + e; };
+    const int64_t base = (int64_t)blockIdx.x * N;
+    if constexpr ((ACC & kAccSum) != 0 && (ACC & kAccGroup) == 0) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t u[16];
+        tmem_ld16(tacc + 16 * half, u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          acc.part_sum[base + bin_of(8 * half + i)] = __hiloint2double((int)u[2 * i + 1], (int)u[2 * i]);
+      }
+    }
+    if constexpr ((ACC & kAccMax) != 0) {
+      uint32_t u[16];
+      tmem_ld16(tacc + 32, u);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc.part_max[base + bin_of(i)] = __uint_as_float(u[i]);
+    }
+    if constexpr ((ACC & kAccMin) != 0) {
+      uint32_t u[16];
+      tmem_ld16(tacc + 48, u);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc.part_min[base + bin_of(i)] = __uint_as_float(u[i]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((tid >> 5) == 0) tmem_dealloc(*tmem_slot, kTmemCols);
   }
   // leave: the last CTA out re-arms the scheduler for the next launch
   if (tid == 0) {

@@ -28,6 +28,9 @@ struct LaunchInfo {
 
 extern std::atomic<int64_t> g_launch_count;
 
+constexpr int kMaxDevices = 64;   // per-device caches of launch attributes (function attributes are per device)
+inline int current_device() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < kMaxDevices) ? d : 0; }
+
 // Largest single-CTA size per element type (shared-memory bound): f32 2^14, f64 2^13.
 template <typename T> struct MaxLog2 { static constexpr int value = sizeof(T) == 4 ? 14 : 13; };
 constexpr int kMinLog2 = 6;
@@ -99,15 +102,17 @@ cudaError_t launch_final(const FftArgs<T>& a, int sm_count, cudaStream_t stream,
   constexpr int kTwMode = (kThreads > 512) ? 0 : (sizeof(T) == 4 ? TDSA_F32_TWMODE : TDSA_F64_TWMODE);
   constexpr int kMinCtas = (kGroups > 1) ? 1 : target_ctas<T, LOG2N, LOGR>();
   auto kern = fft_fused_kernel<T, LOG2N, Epi, kTwMode, kMinCtas, TAIL, NSTAGE, kGroups, HAS_DC, LOGR>;
-  static int occ = -1;          // per instantiation, per process (single device type)
-  if (occ < 0) {
+  static int occ_of[kMaxDevices] = {};          // per instantiation and device (function attributes are per device)
+  const int dev = current_device();
+  if (occ_of[dev] == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
     if (e != cudaSuccess) return e;
     int o = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, kSmem);
     if (e != cudaSuccess) return e;
-    occ = std::max(o, 1);
+    occ_of[dev] = std::max(o, 1);
   }
+  const int occ = occ_of[dev];
   const int64_t want = (int64_t)sm_count * occ;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((a.n_frames + kGroups - 1) / kGroups, want));
   if (info) {
@@ -232,15 +237,9 @@ template <typename T> int effective_logr(int log2n) {
   return (log2n >= kMinLog2R8 && log2n <= kMaxLog2R8 && runtime_logr<T>() == 3) ? 3 : 4;
 }
 
-// ---- warp-local 4096-point kernel (tdsa_fft_wl.cuh) ----------------------------------------------------
+// ---- warp-local kernels (tdsa_fft_wl.cuh): N = 4096 on one engine, N = 8192 on two ---------------------------
 #ifndef TDSA_WL_STAGES_F32
 #define TDSA_WL_STAGES_F32 2
-#endif
-#ifndef TDSA_WL_L2AHEAD_F32     // claim one frame further ahead and prefetch it into L2 (shorter staged copy)
-#define TDSA_WL_L2AHEAD_F32 0
-#endif
-#ifndef TDSA_WL_L2AHEAD_F64
-#define TDSA_WL_L2AHEAD_F64 0
 #endif
 #ifndef TDSA_WL_TWB_BASE_F32    // float32: pass-B twiddles from six base values in registers instead of 15 LDS.64 per frame
 #define TDSA_WL_TWB_BASE_F32 1   // measured: 80.7 -> 78.8 us
@@ -249,34 +248,41 @@ template <typename T> int effective_logr(int log2n) {
 #define TDSA_WL_STAGES_F64 1
 #endif
 
-// lane -> (sub-transform r, team lane c) of fft_wl_kernel; the host permutes the window with the same map
+// lane -> (sub-transform r, team lane c) of an engine of fft_wl_kernel; the host permutes the window with the same map
 inline void wl_thread_identity(int tid, int* r, int* c) {
-  const int w = tid >> 5, l = tid & 31;
+  const int w = (tid & 255) >> 5, l = tid & 31;
   *r = 2 * w + ((l >> 3) & 1);
   *c = (l & 7) + 8 * (l >> 4);
 }
 
-template <typename T, typename Epi, bool HAS_DC>
-cudaError_t launch_wl_final(const FftArgs<T>& a, const CUtensorMap& tmap, const T* wperm, WlSched sched, int sm_count,
-                            cudaStream_t stream, LaunchInfo* info, bool dry) {
-  constexpr int kStages = sizeof(T) == 4 ? TDSA_WL_STAGES_F32 : TDSA_WL_STAGES_F64;
+
+// n_units: claimable units = frames, or groups of acc.group frames (kAccGroup)
+template <typename T, typename Epi, bool HAS_DC, int NB, int ACC>
+cudaError_t launch_wl_final(const FftArgs<T>& a, const CUtensorMap& tmap, const T* wperm, WlSched sched, const WlAcc& acc,
+                            int device, int sm_count, cudaStream_t stream, LaunchInfo* info, bool dry) {
+  constexpr int kStages = (NB == 2 && sizeof(T) == 8) ? 1 : (sizeof(T) == 4 ? TDSA_WL_STAGES_F32 : TDSA_WL_STAGES_F64);
   constexpr int kTwMode = sizeof(T) == 4 ? TDSA_F32_TWMODE : TDSA_F64_TWMODE;
+  constexpr int kThreads = 256 * NB;
+  constexpr int kMinCtas = NB == 1 ? 2 : 1;
   static const size_t kExtraSmem = [] { const char* e = getenv("TDSA_DEBUG_EXTRA_SMEM"); return e ? (size_t)atol(e) : (size_t)0; }();
-  const size_t kSmem = std::min<size_t>(WlPlan<T>::smem_bytes(kStages) + kExtraSmem, 227 * 1024);
-  auto kern = fft_wl_kernel<T, Epi, kTwMode, kStages, HAS_DC, 2, (sizeof(T) == 4 ? TDSA_WL_L2AHEAD_F32 : TDSA_WL_L2AHEAD_F64) != 0,
-                            (sizeof(T) == 4 ? TDSA_WL_TWB_BASE_F32 : 0) != 0>;
-  static int occ = -1;
-  if (occ < 0) {
+  const size_t kSmem = std::min<size_t>(WlPlan<T, NB>::smem_bytes(kStages) + kExtraSmem, 227 * 1024);
+  auto kern = fft_wl_kernel<T, Epi, kTwMode, kStages, HAS_DC, kMinCtas, (sizeof(T) == 4 ? TDSA_WL_TWB_BASE_F32 : 0) != 0, NB, ACC>;
+  static int occ_of[kMaxDevices] = {};          // 0 = not queried on that device yet
+  if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
+  if (occ_of[device] == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
     if (e != cudaSuccess) return e;
     int o = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, 256, kSmem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, kSmem);
     if (e != cudaSuccess) return e;
-    occ = std::max(o, 1);
+    occ_of[device] = std::max(o, 1);
   }
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(a.n_frames, (int64_t)sm_count * occ));
+  const int occ = occ_of[device];
+  const int group = (ACC & kAccGroup) ? std::max(acc.group, 1) : 1;
+  const int64_t n_units = a.n_frames / group;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_units, (int64_t)sm_count * occ));
   if (info) {
-    info->threads = 256; info->smem = (int)kSmem; info->ctas_per_sm = occ; info->grid = grid;
+    info->threads = kThreads; info->smem = (int)kSmem; info->ctas_per_sm = occ; info->grid = grid;
     info->stages = kStages; info->logr = 4;
   }
   if (dry || a.n_frames <= 0) return cudaSuccess;
@@ -285,13 +291,13 @@ cudaError_t launch_wl_final(const FftArgs<T>& a, const CUtensorMap& tmap, const 
   static long long* d_dbg = nullptr;
   const size_t dbg_count = (size_t)grid * 8 * 32 * 16 + grid;
   const char* dbg_path = getenv("TDSA_DEBUG_TIMING_OUT");
-  if (dbg_path) {
+  if (dbg_path && NB == 1) {
     if (!d_dbg) cudaMalloc(&d_dbg, sizeof(long long) * ((size_t)1024 * 8 * 32 * 16 + 1024));
     cudaMemsetAsync(d_dbg, 0, sizeof(long long) * dbg_count, stream);
     b.dbg = d_dbg;
   }
 #endif
-  kern<<<grid, 256, kSmem, stream>>>(b, tmap, wperm, sched);
+  kern<<<grid, kThreads, kSmem, stream>>>(b, tmap, wperm, sched, acc);
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
 #ifdef TDSA_DEBUG_TIMING
   if (b.dbg) {
@@ -306,24 +312,63 @@ cudaError_t launch_wl_final(const FftArgs<T>& a, const CUtensorMap& tmap, const 
   return cudaGetLastError();
 }
 
+// what the warp-local launchers need besides FftArgs
+struct WlLaunch {
+  const CUtensorMap* tmap;
+  const void* wperm;       // T[N]: window in thread order (two halves for two engines)
+  WlSched sched;
+  WlAcc acc;
+  int nb;                  // engines: 1 (N = 4096) or 2 (N = 8192)
+  int acc_flags;           // 0, or one of the instantiated kAcc* combinations below
+  int device, sm_count;
+};
+constexpr int kAccAvg = kAccSum;                               // running average as a weighted sum (last row only)
+constexpr int kAccHold = kAccMax | kAccMin | kAccRows;         // dB rows + max/min hold on un-averaged frames
+constexpr int kAccWelch = kAccSum | kAccMax;                   // Welch mean + peak
+constexpr int kAccGroupMean = kAccSum | kAccGroup;             // one dB row per group of frames
+
 template <typename T>
-cudaError_t launch_wl_impl(int epi, const FftArgs<T>& a, const CUtensorMap& tmap, const T* wperm, WlSched sched, int sm,
-                           cudaStream_t s, LaunchInfo* info, bool dry) {
+cudaError_t launch_wl_impl(int epi, const FftArgs<T>& a, const WlLaunch& L, cudaStream_t s, LaunchInfo* info, bool dry) {
   const bool dc = a.dc != nullptr;
-  if (epi == kEpiDb) {
-    return dc ? launch_wl_final<T, EpiDb, true>(a, tmap, wperm, sched, sm, s, info, dry)
-              : launch_wl_final<T, EpiDb, false>(a, tmap, wperm, sched, sm, s, info, dry);
+  const T* wperm = (const T*)L.wperm;
+#define TDSA_WL_GO(EPI, DC, NB, ACC) \
+  return launch_wl_final<T, EPI, DC, NB, ACC>(a, *L.tmap, wperm, L.sched, L.acc, L.device, L.sm_count, s, info, dry)
+  if (L.nb == 1) {
+    switch (L.acc_flags) {
+      case 0:
+        if (epi == kEpiDb) { if (dc) TDSA_WL_GO(EpiDb, true, 1, 0); TDSA_WL_GO(EpiDb, false, 1, 0); }
+        if (epi == kEpiLinear) { if (dc) TDSA_WL_GO(EpiLinear, true, 1, 0); TDSA_WL_GO(EpiLinear, false, 1, 0); }
+        break;
+      case kAccAvg: if (!dc) TDSA_WL_GO(EpiDb, false, 1, kAccAvg); break;
+      case kAccHold: if (!dc) TDSA_WL_GO(EpiDb, false, 1, kAccHold); break;
+      case kAccWelch: if (!dc) TDSA_WL_GO(EpiDb, false, 1, kAccWelch); break;
+      case kAccGroupMean: if (!dc) TDSA_WL_GO(EpiDb, false, 1, kAccGroupMean); break;
+      default: break;
+    }
+  } else if (L.nb == 2 && !dc) {
+    switch (L.acc_flags) {
+      case 0:
+        if (epi == kEpiDb) TDSA_WL_GO(EpiDb, false, 2, 0);
+        if (epi == kEpiLinear) TDSA_WL_GO(EpiLinear, false, 2, 0);
+        break;
+      case kAccGroupMean: TDSA_WL_GO(EpiDb, false, 2, kAccGroupMean);
+      default: break;
+    }
   }
-  if (epi == kEpiLinear) {
-    return dc ? launch_wl_final<T, EpiLinear, true>(a, tmap, wperm, sched, sm, s, info, dry)
-              : launch_wl_final<T, EpiLinear, false>(a, tmap, wperm, sched, sm, s, info, dry);
-  }
+#undef TDSA_WL_GO
   return cudaErrorInvalidValue;
 }
-cudaError_t launch_wl_f32(int epi, const FftArgs<float>& a, const CUtensorMap& tmap, const float* wperm, WlSched sched,
-                          int sm, cudaStream_t s, LaunchInfo* info, bool dry);
-cudaError_t launch_wl_f64(int epi, const FftArgs<double>& a, const CUtensorMap& tmap, const double* wperm, WlSched sched,
-                          int sm, cudaStream_t s, LaunchInfo* info, bool dry);
+// true when launch_wl_impl has an instantiation for this combination
+inline bool wl_supported(int nb, int epi, int acc_flags, bool dc) {
+  if (nb == 1) {
+    if (acc_flags == 0) return epi == kEpiDb || epi == kEpiLinear;
+    return !dc && (acc_flags == kAccAvg || acc_flags == kAccHold || acc_flags == kAccWelch || acc_flags == kAccGroupMean);
+  }
+  if (nb == 2 && !dc) return acc_flags == 0 ? (epi == kEpiDb || epi == kEpiLinear) : acc_flags == kAccGroupMean;
+  return false;
+}
+cudaError_t launch_wl_f32(int epi, const FftArgs<float>& a, const WlLaunch& L, cudaStream_t s, LaunchInfo* info, bool dry);
+cudaError_t launch_wl_f64(int epi, const FftArgs<double>& a, const WlLaunch& L, cudaStream_t s, LaunchInfo* info, bool dry);
 
 // ---- cluster Welch kernel (tdsa_welch_cluster.cuh): clusters of 16 CTAs, one CTA per SM -------------------------
 // max_clusters != nullptr: only report how many clusters can be co-resident (0 = this device cannot run it)
@@ -331,7 +376,11 @@ template <typename T>
 cudaError_t launch_welch_cluster_impl(const WelchClusterArgs<T>& a, int clusters, cudaStream_t stream, int* max_clusters) {
   auto kern = welch_cluster_kernel<T>;
   constexpr size_t kSmem = WelchClusterPlan<T>::SMEM_BYTES;
-  static int max_active = -1;
+  static int max_active_of[kMaxDevices];
+  static bool queried[kMaxDevices] = {};
+  const int dev = current_device();
+  int& max_active = max_active_of[dev];
+  if (!queried[dev]) { max_active = -1; queried[dev] = true; }
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

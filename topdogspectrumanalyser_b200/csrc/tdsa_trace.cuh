@@ -1,0 +1,365 @@
+// tdsa_trace.cuh — trace state kept entirely on the device: TraceAverager count and the hold / tare flags live in a
+// small int32 block next to the float64 buffer, so that no entry point has to read anything back to the host.
+//
+// Reference semantics: utils/signal_processing.py:35-61 (TraceAverager), core/display_data_processor.py:211-218
+// (sweep-domain averaging), :317-369 (cal offset, tare), :371-395 + :473-480 (max/min hold, _nan_safe),
+// datasources/hackrf_samples.py:351-355 (silent frames repeat the last good row).
+#pragma once
+#include "tdsa_aux.cuh"
+
+namespace tdsa {
+
+// layout of the device flag block (include/tdsa.h: TDSA_FLAG_*)
+enum : int { kFlagCount = 0, kFlagMaxValid = 1, kFlagMinValid = 2, kFlagLive = 3, kFlagTareCollecting = 4,
+             kFlagTareActive = 5, kFlagTareCount = 6, kFlagWords = 8 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Running average as a weighted sum (fused path).  TraceAverager folds frames x_1..x_L into its buffer s as
+//   exp:  s <- (1 - a) s + a x_i, a = 1/n                 (first frame of an empty buffer: s <- x_1)
+//   lin:  c_i = min(c_{i-1} + 1, n);  s <- s + (x_i - s)/c_i
+// which is  s_L = carry * s_0 + sum_i w_i x_i  with weights that depend only on (mode, n, c_0, L, i):
+//   exp:  w_i = a (1-a)^(L-i)   (w_1 = (1-a)^(L-1) when c_0 = 0);  carry = (1-a)^L  (0 when c_0 = 0)
+//   lin:  P_i = prod_{u>i} (1 - 1/c_u) = [c_i / c_J for the uncapped steps, J = min(L, n - c_0)] * (1 - 1/n)^(capped steps),
+//         w_i = P_i / c_i,  carry = P_0 (0 when c_0 = 0, because c_1 = 1)
+// Frames can then be folded in any order by any CTA.  meta: {carry, c_0, new count}.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double lin_tail_product(int64_t i, int64_t L, int64_t c0, int64_t n) {
+  // prod_{u = i+1 .. L} (1 - 1/c_u), c_u = min(c0 + u, n); i >= 0; for i = 0 with c0 = 0 the first factor is 0
+  const int64_t U = n > c0 ? n - c0 : 0;          // steps u <= U are uncapped (c_u = c0 + u)
+  const int64_t J = L < U ? L : U;
+  double p = 1.0;
+  if (i < J) {                                    // telescoping part: prod_{u=i+1..J} (c_u - 1)/c_u = c_i / c_J
+    if (c0 + i == 0) return 0.0;
+    p = (double)(c0 + i) / (double)(c0 + J);
+  }
+  const int64_t from = i > U ? i : U;             // capped steps u = from+1 .. L
+  if (L > from) p *= pow(1.0 - 1.0 / (double)n, (double)(L - from));
+  return p;
+}
+
+__global__ void __launch_bounds__(256) avg_weights_kernel(int avg_mode, int avg_n, int64_t n_frames,
+                                                         int32_t* __restrict__ flags, double* __restrict__ weight,
+                                                         double* __restrict__ meta) {
+  const int64_t c0 = flags[kFlagCount];
+  const int64_t L = n_frames, n = avg_n;
+  const double a = 1.0 / (double)avg_n;
+  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_frames; f += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = f + 1;
+    double w;
+    if (avg_mode == 1) w = (c0 == 0 && i == 1) ? pow(1.0 - a, (double)(L - 1)) : a * pow(1.0 - a, (double)(L - i));
+    else w = lin_tail_product(i, L, c0, n) / (double)((c0 + i) < n ? (c0 + i) : n);
+    weight[f] = w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double carry;
+    int64_t cnew;
+    if (avg_mode == 1) { carry = c0 == 0 ? 0.0 : pow(1.0 - a, (double)L); cnew = c0 > 1 ? c0 : 1; }
+    else { carry = lin_tail_product(0, L, c0, n); cnew = (c0 + L) < n ? (c0 + L) : n; }
+    meta[0] = carry; meta[1] = (double)c0; meta[2] = (double)cnew;
+  }
+}
+
+// snapshot of the flag block for kernels that follow, then the flags as they will be after `live` frames
+__global__ void flags_prepare_kernel(int32_t* __restrict__ flags, double* __restrict__ meta, int avg_mode, int avg_n,
+                                     int64_t live, int has_max, int has_min) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  meta[1] = (double)flags[kFlagCount];
+  meta[3] = (double)flags[kFlagMaxValid];
+  meta[4] = (double)flags[kFlagMinValid];
+  flags[kFlagLive] = (int32_t)live;
+  if (live > 0) {
+    if (has_max) flags[kFlagMaxValid] = 1;
+    if (has_min) flags[kFlagMinValid] = 1;
+    (void)avg_mode; (void)avg_n;
+  }
+}
+
+// fused running average, last step: state <- carry * state + scale * sum over CTAs; one dB row out
+__global__ void __launch_bounds__(256) avg_finish_kernel(const double* __restrict__ part_sum, int n_parts, int64_t width,
+                                                        const double* __restrict__ meta, double scale, double floor, int mode,
+                                                        double* __restrict__ avg_state, int32_t* __restrict__ flags,
+                                                        int64_t live, float* __restrict__ db_out, float* __restrict__ last_row) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= width) return;
+  double s = 0.0;
+  for (int c = 0; c < n_parts; ++c) s += part_sum[(int64_t)c * width + k];
+  s *= scale;
+  const double carry = meta[0];
+  const double v = carry != 0.0 ? __fma_rn(carry, avg_state[k], s) : s;
+  avg_state[k] = v;
+  EpiParams ep;
+  ep.db_out = nullptr; ep.lin_out = nullptr; ep.scale = 1.0; ep.floor = floor; ep.mode = mode;
+  const float db = to_db<double>(v, ep);
+  db_out[k] = db;
+  if (last_row) last_row[k] = db;
+  if (k == 0) { flags[kFlagCount] = (int32_t)meta[2]; flags[kFlagLive] = (int32_t)live; }
+}
+
+// fused max/min hold on un-averaged rows: hold <- fmax(hold, dB(max_f |X_f|^2)) (dB is monotonic), first use initialises
+__global__ void __launch_bounds__(256) hold_finish_kernel(const float* __restrict__ part_max, const float* __restrict__ part_min,
+                                                         int n_parts, int64_t width, const double* __restrict__ meta,
+                                                         double scale, double floor, int mode, float* __restrict__ max_hold,
+                                                         float* __restrict__ min_hold) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= width) return;
+  EpiParams ep;
+  ep.db_out = nullptr; ep.lin_out = nullptr; ep.scale = scale; ep.floor = floor; ep.mode = mode;
+  if (max_hold) {
+    float m = -INFINITY;
+    bool nan_only = true;                                 // every live frame had NaN in this bin
+    for (int c = 0; c < n_parts; ++c) m = fmaxf(m, part_max[(int64_t)c * width + k]);
+    nan_only = (m == -INFINITY);
+    const float db = nan_only ? -500.0f : to_db<float>(m, ep);     // _nan_safe: NaN -> -500 on the initialising frame
+    if (meta[3] != 0.0) { if (!nan_only) max_hold[k] = fmaxf(max_hold[k], db); }
+    else max_hold[k] = db;
+  }
+  if (min_hold) {
+    float m = INFINITY;
+    for (int c = 0; c < n_parts; ++c) m = fminf(m, part_min[(int64_t)c * width + k]);
+    const bool nan_only = (m == INFINITY);
+    const float db = nan_only ? 500.0f : to_db<float>(m, ep);
+    if (meta[4] != 0.0) { if (!nan_only) min_hold[k] = fminf(min_hold[k], db); }
+    else min_hold[k] = db;
+  }
+}
+
+// Welch (config 3) from the accumulating epilogue: avg = dB(scale * sum / n_seg), peak = dB(scale * max)
+__global__ void __launch_bounds__(256) welch_acc_finish_kernel(const double* __restrict__ part_sum, const float* __restrict__ part_max,
+                                                              int n_parts, int64_t width, int64_t n_seg, double scale,
+                                                              double floor, int mode, float* __restrict__ avg_db,
+                                                              float* __restrict__ peak_db) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= width) return;
+  double s = 0.0;
+  float m = -INFINITY;
+  for (int c = 0; c < n_parts; ++c) { s += part_sum[(int64_t)c * width + k]; m = fmaxf(m, part_max[(int64_t)c * width + k]); }
+  EpiParams ep;
+  ep.db_out = nullptr; ep.lin_out = nullptr; ep.scale = 1.0; ep.floor = floor; ep.mode = mode;
+  avg_db[k] = to_db<double>(s * scale / (double)n_seg, ep);
+  ep.scale = scale;
+  peak_db[k] = to_db<float>(m, ep);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// General path: frame-ordered scan over float64 linear rows (one thread per bin), flags read from the device.
+// The rows of a chunk are written by the FFT kernel and consumed here while still in L2 (the caller sizes chunks).
+// ---------------------------------------------------------------------------------------------------------------
+struct TraceScanDevArgs {
+  const double* lin;       // [F][W] linear power (already scaled for PSD)
+  const int32_t* skip;     // [F] or null
+  int64_t n_frames, width;
+  int avg_mode, avg_n;
+  const int32_t* flags;    // device flag block (read only here; trace_flags_after_scan_kernel updates it)
+  double* avg_state;
+  float* max_hold;
+  float* min_hold;
+  float* last_row;         // [W] or null: last good dB row, carried across launches (silent frames repeat it)
+  int last_only;
+  float* db_out;           // [F][W], or [W] when last_only
+  double floor;
+  int mode;
+};
+
+__global__ void __launch_bounds__(256) trace_scan_dev_kernel(const TraceScanDevArgs a) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.width) return;
+  const bool averaging = a.avg_mode != 0 && a.avg_n > 1;
+  int count = averaging ? a.flags[kFlagCount] : 0;
+  double buf = (averaging && count > 0) ? a.avg_state[k] : 0.0;
+  const double alpha = 1.0 / (double)a.avg_n;
+  bool mxv = a.flags[kFlagMaxValid] != 0, mnv = a.flags[kFlagMinValid] != 0;
+  float mx = (a.max_hold && mxv) ? a.max_hold[k] : 0.f;
+  float mn = (a.min_hold && mnv) ? a.min_hold[k] : 0.f;
+  EpiParams ep;
+  ep.db_out = nullptr; ep.lin_out = nullptr; ep.scale = 1.0; ep.floor = a.floor; ep.mode = a.mode;
+  float last_db = a.last_row ? a.last_row[k] : 0.0f;     // what a skipped frame repeats (hackrf_samples.py:351-355)
+  bool any = false;
+  constexpr int kAhead = 8;                              // rows fetched ahead of the recurrence (they come from L2)
+  for (int64_t f0 = 0; f0 < a.n_frames; f0 += kAhead) {
+    double pre[kAhead];
+#pragma unroll
+    for (int u = 0; u < kAhead; ++u) pre[u] = (f0 + u < a.n_frames) ? a.lin[(f0 + u) * a.width + k] : 0.0;
+#pragma unroll
+    for (int u = 0; u < kAhead; ++u) {
+      const int64_t f = f0 + u;
+      if (f >= a.n_frames) break;
+      if (a.skip != nullptr && a.skip[f]) {
+        if (!a.last_only) a.db_out[f * a.width + k] = last_db;
+        else if (f == a.n_frames - 1) a.db_out[k] = last_db;
+        continue;
+      }
+      const double p = pre[u];
+      double v = p;
+      if (averaging) {
+        if (count == 0) {
+          buf = p;
+          count = 1;
+        } else if (a.avg_mode == 1) {
+          buf = __dmul_rn(buf, 1.0 - alpha);              // buffer *= (1 - alpha)
+          buf = __dadd_rn(buf, __dmul_rn(alpha, p));      // buffer += alpha * x
+        } else {
+          if (count < a.avg_n) ++count;
+          buf = __dadd_rn(buf, __ddiv_rn(__dsub_rn(p, buf), (double)count));   // buffer += (x - buffer)/count
+        }
+        v = buf;
+      }
+      const float db = to_db<double>(v, ep);
+      last_db = db;
+      any = true;
+      if (!a.last_only) a.db_out[f * a.width + k] = db;
+      else if (f == a.n_frames - 1) a.db_out[k] = db;
+      if (a.max_hold) {
+        if (!mxv) { mx = isnan(db) ? -500.0f : db; mxv = true; }
+        else mx = fmaxf(mx, db);
+      }
+      if (a.min_hold) {
+        if (!mnv) { mn = isnan(db) ? 500.0f : db; mnv = true; }
+        else mn = fminf(mn, db);
+      }
+    }
+  }
+  if (averaging && any) a.avg_state[k] = buf;
+  if (a.max_hold && mxv) a.max_hold[k] = mx;
+  if (a.min_hold && mnv) a.min_hold[k] = mn;
+  if (a.last_row && any) a.last_row[k] = last_db;
+}
+
+// after a scan: fold the number of live (not skipped) frames into the flag block
+__global__ void trace_flags_after_scan_kernel(int32_t* __restrict__ flags, const int32_t* __restrict__ skip, int64_t n_frames,
+                                              int avg_mode, int avg_n, int has_max, int has_min, int first_chunk) {
+  __shared__ int s_live;
+  if (threadIdx.x == 0) s_live = 0;
+  __syncthreads();
+  int live = 0;
+  for (int64_t f = threadIdx.x; f < n_frames; f += blockDim.x) live += (skip == nullptr || skip[f] == 0) ? 1 : 0;
+  atomicAdd(&s_live, live);
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  live = s_live;
+  const bool averaging = avg_mode != 0 && avg_n > 1;
+  if (live > 0) {
+    if (averaging) {
+      const int64_t c = flags[kFlagCount];
+      flags[kFlagCount] = avg_mode == 2 ? (int32_t)((c + live) < avg_n ? (c + live) : avg_n) : (int32_t)(c > 1 ? c : 1);
+    }
+    if (has_max) flags[kFlagMaxValid] = 1;
+    if (has_min) flags[kFlagMinValid] = 1;
+  }
+  flags[kFlagLive] = (first_chunk ? 0 : flags[kFlagLive]) + live;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dB-row trace update (cal offset, tare, sweep-domain averaging, holds) with the flag block on the device.
+// Same per-bin arithmetic as trace_update_kernel; the bookkeeping the host used to do is
+// trace_flags_after_update_kernel.
+// ---------------------------------------------------------------------------------------------------------------
+struct TraceUpdateDevArgs {
+  const float* rows;
+  int64_t n_rows, width;
+  double cal;
+  int avg_mode, avg_n;
+  const int32_t* flags;
+  double* avg_state;
+  float* max_hold;
+  float* min_hold;
+  const int32_t* has_value;   // per row
+  float* rows_out;
+  int tare_target;
+  double* tare_buf;
+  double* tare_baseline;
+};
+
+__global__ void __launch_bounds__(256) trace_update_dev_kernel(const TraceUpdateDevArgs a) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.width) return;
+  const bool averaging = a.avg_mode != 0 && a.avg_n > 1;
+  int count = averaging ? a.flags[kFlagCount] : 0;
+  double buf = (averaging && count > 0) ? a.avg_state[k] : 0.0;
+  const double alpha = 1.0 / (double)a.avg_n;
+  bool mxv = a.flags[kFlagMaxValid] != 0, mnv = a.flags[kFlagMinValid] != 0;
+  float mx = (a.max_hold && mxv) ? a.max_hold[k] : 0.f;
+  float mn = (a.min_hold && mnv) ? a.min_hold[k] : 0.f;
+  bool touched = false;
+  const bool has_tare = a.tare_buf != nullptr && a.tare_baseline != nullptr;
+  bool collecting = has_tare && a.flags[kFlagTareCollecting] != 0, tare_active = has_tare && a.flags[kFlagTareActive] != 0;
+  bool captured = false;
+  int tcount = collecting ? a.flags[kFlagTareCount] : 0;
+  double tbuf = (collecting && tcount > 0) ? a.tare_buf[k] : 0.0;
+  double base = tare_active ? a.tare_baseline[k] : 0.0;
+  for (int64_t r = 0; r < a.n_rows; ++r) {
+    double x = (double)a.rows[r * a.width + k];
+    if (a.cal != 0.0) x += a.cal;
+    if (!a.has_value[r]) {               // NaN-only frame: the reference returns before any state update (:211)
+      if (a.rows_out) a.rows_out[r * a.width + k] = (float)x;
+      continue;
+    }
+    if (collecting) {                    // accumulate the linear baseline, capture it after tare_target frames (:335-358)
+      const double lin = pow(10.0, x / 10.0);
+      if (tcount == 0) { tbuf = lin; tcount = 1; } else { tbuf += lin; ++tcount; }
+      if (tcount >= a.tare_target) {
+        base = 10.0 * log10(fmax(tbuf / (double)tcount, 1e-30));
+        tare_active = true; collecting = false; captured = true;
+      }
+    }
+    if (tare_active) x -= base;
+    if (averaging) {
+      const double lin = pow(10.0, x / 10.0);
+      if (count == 0) {
+        buf = lin;
+        count = 1;
+      } else if (a.avg_mode == 1) {
+        buf = __dmul_rn(buf, 1.0 - alpha);
+        buf = __dadd_rn(buf, __dmul_rn(alpha, lin));
+      } else {
+        if (count < a.avg_n) ++count;
+        buf = __dadd_rn(buf, __ddiv_rn(__dsub_rn(lin, buf), (double)count));
+      }
+      touched = true;
+      x = 10.0 * log10(fmax(buf, 1e-30));
+    }
+    const float db = (float)x;
+    if (a.rows_out) a.rows_out[r * a.width + k] = db;
+    if (a.max_hold) {
+      if (!mxv) { mx = isnan(db) ? -500.0f : db; mxv = true; }
+      else mx = fmaxf(mx, db);
+    }
+    if (a.min_hold) {
+      if (!mnv) { mn = isnan(db) ? 500.0f : db; mnv = true; }
+      else mn = fminf(mn, db);
+    }
+  }
+  if (averaging && touched) a.avg_state[k] = buf;
+  if (a.max_hold && mxv) a.max_hold[k] = mx;
+  if (a.min_hold && mnv) a.min_hold[k] = mn;
+  if (collecting) a.tare_buf[k] = tbuf;
+  if (captured) a.tare_baseline[k] = base;
+}
+
+__global__ void trace_flags_after_update_kernel(int32_t* __restrict__ flags, const int32_t* __restrict__ has_value,
+                                                int64_t n_rows, int avg_mode, int avg_n, int has_max, int has_min,
+                                                int has_tare, int tare_target) {
+  __shared__ int s_live;
+  if (threadIdx.x == 0) s_live = 0;
+  __syncthreads();
+  int live = 0;
+  for (int64_t r = threadIdx.x; r < n_rows; r += blockDim.x) live += has_value[r] != 0 ? 1 : 0;
+  atomicAdd(&s_live, live);
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  live = s_live;
+  flags[kFlagLive] = live;
+  if (live <= 0) return;
+  if (has_tare && flags[kFlagTareCollecting]) {          // TareState bookkeeping, display_data_processor.py:335-358
+    const int64_t c = (int64_t)flags[kFlagTareCount] + live;
+    if (c >= tare_target) { flags[kFlagTareCollecting] = 0; flags[kFlagTareActive] = 1; flags[kFlagTareCount] = 0; }
+    else flags[kFlagTareCount] = (int32_t)c;
+  }
+  if (avg_mode != 0 && avg_n > 1) {
+    const int64_t c = flags[kFlagCount];
+    flags[kFlagCount] = avg_mode == 2 ? (int32_t)((c + live) < avg_n ? (c + live) : avg_n) : (int32_t)(c > 1 ? c : 1);
+  }
+  if (has_max) flags[kFlagMaxValid] = 1;
+  if (has_min) flags[kFlagMinValid] = 1;
+}
+
+}  // namespace tdsa

@@ -7,7 +7,6 @@ in torch ops.
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
 from typing import Optional
 
 import numpy as np
@@ -46,62 +45,87 @@ def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-@dataclass
+# words of the device flag block (include/tdsa.h: TDSA_FLAG_*)
+FLAG_COUNT, FLAG_MAX_VALID, FLAG_MIN_VALID, FLAG_LIVE, FLAG_TARE_COLLECTING, FLAG_TARE_ACTIVE, FLAG_TARE_COUNT = range(7)
+FLAG_WORDS = 8
+
+
 class TraceState:
-    """Device-resident trace state: TraceAverager buffer + max/min hold rows.
+    """Device-resident trace state: TraceAverager buffer + max/min hold rows + the scalars that go with them.
 
-    Mirrors ``TraceAverager._buffer/_count`` (utils/signal_processing.py:15-17) and
-    ``mw.max_power_levels / mw.min_power_levels`` (core/display_data_processor.py:371-395).
+    Mirrors ``TraceAverager._buffer/_count`` (utils/signal_processing.py:15-17),
+    ``mw.max_power_levels / mw.min_power_levels`` (core/display_data_processor.py:371-395) and ``TareState``
+    (core/tare_state.py).  The scalars (count, "hold initialised", tare collecting / active / count) live in
+    ``flags``, an int32 block ON THE DEVICE, so no kernel call has to hand anything back to the host; the
+    controls below are stream-ordered device writes, the read-outs (``count``, ``valid``, ``tare_active``)
+    synchronise because the caller asked for a host value.
     """
-    width: int
-    device: torch.device
-    avg_mode: str = "off"
-    avg_n: int = 1
-    max_hold_enabled: bool = False
-    min_hold_enabled: bool = False
-    avg: torch.Tensor = field(init=False)
-    max_hold: torch.Tensor = field(init=False)
-    min_hold: torch.Tensor = field(init=False)
-    count: C.c_int32 = field(init=False)
-    valid: C.Array = field(init=False)
+    TARE_NUM_SAMPLES = 32                                 # utils/constants.py:141
 
-    def __post_init__(self):
+    def __init__(self, width: int, device, avg_mode: str = "off", avg_n: int = 1,
+                 max_hold_enabled: bool = False, min_hold_enabled: bool = False):
+        self.width, self.device = int(width), torch.device(device)
+        self.avg_mode, self.avg_n = avg_mode, int(avg_n)
+        self.max_hold_enabled, self.min_hold_enabled = max_hold_enabled, min_hold_enabled
         self.avg = torch.zeros(self.width, dtype=torch.float64, device=self.device)
         self.max_hold = torch.zeros(self.width, dtype=torch.float32, device=self.device)
         self.min_hold = torch.zeros(self.width, dtype=torch.float32, device=self.device)
-        self.count = C.c_int32(0)
-        self.valid = (C.c_int32 * 2)(0, 0)
+        self.flags = torch.zeros(FLAG_WORDS, dtype=torch.int32, device=self.device)
+        self.last_row = torch.zeros(self.width, dtype=torch.float32, device=self.device)   # last good dB row
         # tare / normalisation (core/tare_state.py; display_data_processor.py:329-369)
         self.tare_buf = torch.zeros(self.width, dtype=torch.float64, device=self.device)
         self.tare_baseline = torch.zeros(self.width, dtype=torch.float64, device=self.device)
-        self.tare_flags = (C.c_int32 * 2)(0, 0)          # {collecting, active}
-        self.tare_count = C.c_int32(0)
 
-    TARE_NUM_SAMPLES = 32                                 # utils/constants.py:141
-
+    # ---- controls: device writes, no synchronisation ------------------------------------------------
     def start_tare(self) -> None:
         """Begin collecting a baseline (TareState(collecting=True))."""
-        self.tare_flags[0], self.tare_flags[1] = 1, 0
-        self.tare_count.value = 0
+        self.flags[FLAG_TARE_COLLECTING:FLAG_TARE_COUNT + 1] = torch.tensor([1, 0, 0], dtype=torch.int32).to(
+            self.device, non_blocking=True)
 
     def clear_tare(self) -> None:
-        self.tare_flags[0], self.tare_flags[1] = 0, 0
-        self.tare_count.value = 0
-
-    @property
-    def tare_active(self) -> bool:
-        return bool(self.tare_flags[1])
+        self.flags[FLAG_TARE_COLLECTING:FLAG_TARE_COUNT + 1].zero_()
 
     def set_averaging(self, mode: str, n: int) -> None:       # TraceAverager.set_mode, :19-28
         self.avg_mode, self.avg_n = mode, max(1, int(n))
         self.reset_averaging()
 
     def reset_averaging(self) -> None:                        # TraceAverager.reset, :30-33
-        self.count.value = 0
+        self.flags[FLAG_COUNT:FLAG_COUNT + 1].zero_()
 
     def clear_holds(self) -> None:
-        self.valid[0] = 0
-        self.valid[1] = 0
+        self.flags[FLAG_MAX_VALID:FLAG_MIN_VALID + 1].zero_()
+
+    def clear_max_hold(self) -> None:
+        self.flags[FLAG_MAX_VALID:FLAG_MAX_VALID + 1].zero_()
+
+    def clear_min_hold(self) -> None:
+        self.flags[FLAG_MIN_VALID:FLAG_MIN_VALID + 1].zero_()
+
+    # ---- read-outs: host values, synchronise -----------------------------------------------------------
+    def host_flags(self) -> list:
+        return self.flags.cpu().tolist()
+
+    @property
+    def count(self) -> int:
+        return int(self.flags[FLAG_COUNT].item())
+
+    @property
+    def valid(self) -> tuple:
+        f = self.host_flags()
+        return (f[FLAG_MAX_VALID], f[FLAG_MIN_VALID])
+
+    @property
+    def live_frames(self) -> int:
+        """Frames of the last call that were not silent / all-NaN."""
+        return int(self.flags[FLAG_LIVE].item())
+
+    @property
+    def tare_active(self) -> bool:
+        return bool(self.flags[FLAG_TARE_ACTIVE].item())
+
+    @property
+    def tare_collecting(self) -> bool:
+        return bool(self.flags[FLAG_TARE_COLLECTING].item())
 
     @property
     def averaging(self) -> bool:                              # TraceAverager.is_active, :63-65
@@ -224,32 +248,28 @@ class SpectrumPlan:
 
     def psd_db_avg_hold(self, iq: torch.Tensor, state: TraceState, last_only: bool = False,
                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Frames folded into the running trace state (averager + holds) on the device."""
-        b, stride = self._frames(iq, None, None)
-        rows = 1 if last_only else b
-        if out is None:
-            out = torch.empty((rows, self.n_fft), dtype=torch.float32, device=iq.device)
-        self._bind()
-        L.check(self.lib.tdsa_psd_db_avg_hold(
-            self._h, iq.data_ptr(), b, stride, L.AVG_IDS[state.avg_mode], state.avg_n, state.avg.data_ptr(),
-            C.byref(state.count), state.max_hold.data_ptr() if state.max_hold_enabled else None,
-            state.min_hold.data_ptr() if state.min_hold_enabled else None, state.valid, int(last_only), out.data_ptr()))
-        return out
+        """Frames folded into the running trace state (averager + holds) on the device; nothing is read back."""
+        return self._avg_hold(iq, state, None, 1.0, last_only, out)[0]
 
     def psd_db_avg_hold_dc(self, iq: torch.Tensor, state: TraceState, dc_state: torch.Tensor, dc_alpha: float = 1.0,
                            last_only: bool = False, out: Optional[torch.Tensor] = None):
         """HackRF front end + trace state (hackrf_samples.py:351-381). Returns ``(db, silent_flags)``."""
+        return self._avg_hold(iq, state, dc_state, dc_alpha, last_only, out)
+
+    def _avg_hold(self, iq, state: TraceState, dc_state, dc_alpha, last_only, out):
         b, stride = self._frames(iq, None, None)
         rows = 1 if last_only else b
         if out is None:
             out = torch.empty((rows, self.n_fft), dtype=torch.float32, device=iq.device)
-        silent = torch.empty(b, dtype=torch.int32, device=iq.device)
+        silent = torch.empty(b, dtype=torch.int32, device=iq.device) if dc_state is not None else None
         self._bind()
-        L.check(self.lib.tdsa_psd_db_avg_hold_dc(
-            self._h, iq.data_ptr(), b, stride, float(dc_alpha), dc_state.data_ptr(), silent.data_ptr(),
-            L.AVG_IDS[state.avg_mode], state.avg_n, state.avg.data_ptr(), C.byref(state.count),
+        L.check(self.lib.tdsa_psd_db_avg_hold_dev(
+            self._h, iq.data_ptr(), b, stride, int(dc_state is not None), float(dc_alpha),
+            dc_state.data_ptr() if dc_state is not None else None, silent.data_ptr() if silent is not None else None,
+            L.AVG_IDS[state.avg_mode], state.avg_n, state.avg.data_ptr(),
             state.max_hold.data_ptr() if state.max_hold_enabled else None,
-            state.min_hold.data_ptr() if state.min_hold_enabled else None, state.valid, int(last_only), out.data_ptr()))
+            state.min_hold.data_ptr() if state.min_hold_enabled else None, state.flags.data_ptr(),
+            state.last_row.data_ptr(), int(last_only), out.data_ptr()))
         return out, silent
 
     def group_avg_db(self, iq: torch.Tensor) -> torch.Tensor:
@@ -301,14 +321,13 @@ def trace_update(rows: torch.Tensor, state: TraceState, cal_offset_db: float = 0
     r, w = rows.shape
     if out is None:
         out = torch.empty_like(rows)
-    flags = torch.empty(max(r, 1), dtype=torch.int32, device=rows.device)
-    L.check(lib.tdsa_trace_update_tare(rows.data_ptr(), r, w, float(cal_offset_db), L.AVG_IDS[state.avg_mode], state.avg_n,
-                                       state.avg.data_ptr(), C.byref(state.count),
-                                       state.max_hold.data_ptr() if state.max_hold_enabled else None,
-                                       state.min_hold.data_ptr() if state.min_hold_enabled else None, state.valid,
-                                       out.data_ptr(), _stream_ptr(), flags.data_ptr(), state.tare_flags,
-                                       C.byref(state.tare_count), state.TARE_NUM_SAMPLES, state.tare_buf.data_ptr(),
-                                       state.tare_baseline.data_ptr()))
+    scratch = torch.empty(max(r, 1), dtype=torch.int32, device=rows.device)
+    L.check(lib.tdsa_trace_update_dev(rows.data_ptr(), r, w, float(cal_offset_db), L.AVG_IDS[state.avg_mode], state.avg_n,
+                                      state.avg.data_ptr(),
+                                      state.max_hold.data_ptr() if state.max_hold_enabled else None,
+                                      state.min_hold.data_ptr() if state.min_hold_enabled else None,
+                                      state.flags.data_ptr(), out.data_ptr(), _stream_ptr(), scratch.data_ptr(),
+                                      state.TARE_NUM_SAMPLES, state.tare_buf.data_ptr(), state.tare_baseline.data_ptr()))
     return out
 
 
@@ -329,22 +348,59 @@ def stitch(rows: torch.Tensor, row_lo_hz: torch.Tensor, row_hz: float, start_hz:
 
 
 class WaterfallRing:
-    """Device history ring with the widget's semantics (displays/waterfall.py:163-180)."""
+    """Device history ring with the widget's semantics (displays/waterfall.py:163-180, 330-336).
 
-    def __init__(self, h: int, w: int, fill: float, device):
+    ``dedupe=True`` applies the widget's duplicate filter (a row identical to the previous one is not added); the
+    write pointer then lives on the device (``state``), because only the device knows how many rows were new.
+    ``image()`` hands out the colour-mapped RGBA picture of the display view (core/export_manager.py:67-84)."""
+
+    def __init__(self, h: int, w: int, fill: float, device, dedupe: bool = False):
         _require_cuda()
         self.lib = L.load()
-        self.h, self.w = int(h), int(w)
+        self.h, self.w, self.dedupe = int(h), int(w), bool(dedupe)
         self.buf = torch.full((2 * self.h, self.w), float(fill), dtype=torch.float32, device=device)
-        self.ptr = C.c_int64(0)
+        self.ptr = C.c_int64(0)                                        # host pointer of the plain push
+        self.state = torch.zeros(4, dtype=torch.int64, device=device)  # {ptr, has_last, rows added by the last push, -}
+        self.last_row = torch.zeros(self.w, dtype=torch.float32, device=device)
+        self._on_device = self.dedupe
 
     def push(self, rows: torch.Tensor) -> None:
         rows = rows.reshape(-1, self.w)
         if rows.dtype != torch.float32 or not rows.is_contiguous():
             raise ValueError("rows must be contiguous float32")
-        L.check(self.lib.tdsa_ring_push(rows.data_ptr(), rows.shape[0], self.buf.data_ptr(), self.h, self.w,
-                                        C.byref(self.ptr), _stream_ptr()))
+        if not self._on_device:
+            L.check(self.lib.tdsa_ring_push(rows.data_ptr(), rows.shape[0], self.buf.data_ptr(), self.h, self.w,
+                                            C.byref(self.ptr), _stream_ptr()))
+            return
+        r = rows.shape[0]
+        slot = torch.empty(max(r, 1), dtype=torch.int64, device=rows.device)
+        differs = torch.empty(max(r, 1), dtype=torch.int32, device=rows.device)
+        L.check(self.lib.tdsa_ring_push_dev(rows.data_ptr(), r, self.buf.data_ptr(), self.h, self.w, self.state.data_ptr(),
+                                            self.last_row.data_ptr(), int(self.dedupe), slot.data_ptr(), differs.data_ptr(),
+                                            _stream_ptr()))
+
+    def use_device_pointer(self) -> None:
+        """Move the write pointer to the device (needed by ``image()`` and by dedupe); keeps the current position."""
+        if not self._on_device:
+            self.state[0] = int(self.ptr.value)
+            self._on_device = True
+
+    @property
+    def rows_added(self) -> int:
+        """Rows the last device-side push really added (duplicates excluded). Synchronises."""
+        return int(self.state[2].item())
 
     def view(self) -> torch.Tensor:
-        p = int(self.ptr.value)
+        p = int(self.state[0].item()) if self._on_device else int(self.ptr.value)
         return self.buf[p:p + self.h]
+
+    def image(self, lo_db: float, hi_db: float, lut_rgba: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """uint8 [H, W, 4]: the display view through the widget's LUT, newest row first; no host round trip."""
+        if lut_rgba.dtype != torch.uint8 or tuple(lut_rgba.shape) != (256, 4) or not lut_rgba.is_cuda:
+            raise ValueError("lut_rgba must be a uint8 CUDA tensor [256, 4]")
+        self.use_device_pointer()
+        if out is None:
+            out = torch.empty((self.h, self.w, 4), dtype=torch.uint8, device=self.buf.device)
+        L.check(self.lib.tdsa_ring_image_rgba(self.buf.data_ptr(), self.h, self.w, self.state.data_ptr(), float(lo_db),
+                                              float(hi_db), lut_rgba.contiguous().data_ptr(), out.data_ptr(), _stream_ptr()))
+        return out

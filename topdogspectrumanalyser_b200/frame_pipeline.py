@@ -17,12 +17,13 @@ from .engine import TraceState, trace_update
 
 
 class B200FramePipeline:
-    def __init__(self, source, cal_offset_db: float = 0.0, peak_list: bool = False):
+    def __init__(self, source, cal_offset_db: float = 0.0, peak_list: bool = False, peak_excursion: float = 10.0):
         self.source = source
         self.cal_offset_db = float(cal_offset_db)
-        self.max_peak_search_enabled = False          # dm.max_peak_search_enabled
-        self.min_hold_enabled = False                 # mw.min_hold_enabled
+        self._max_on = False                          # dm.max_peak_search_enabled
+        self._min_on = False                          # mw.min_hold_enabled
         self.peak_list_enabled = peak_list
+        self.peak_excursion = float(peak_excursion)   # mw.peak_excursion (display_data_processor.py:418)
         self.frequency_bins: Optional[np.ndarray] = None
         self.peaks: List[Tuple[float, float]] = []
         self._state: Optional[TraceState] = None
@@ -32,13 +33,34 @@ class B200FramePipeline:
     def _ensure_state(self, width: int, device) -> TraceState:
         if self._state is None or self._state.width != width:        # shape change drops holds and tare (:375-377,361-364)
             self._state = TraceState(width, device)
-        self._state.max_hold_enabled = self.max_peak_search_enabled
-        self._state.min_hold_enabled = self.min_hold_enabled
-        if not self.max_peak_search_enabled:
-            self._state.valid[0] = 0
-        if not self.min_hold_enabled:
-            self._state.valid[1] = 0
+        # a disabled hold keeps its row until the shape changes (:374-378); enabling starts afresh (the setters below)
+        self._state.max_hold_enabled = self._max_on
+        self._state.min_hold_enabled = self._min_on
         return self._state
+
+    @property
+    def max_peak_search_enabled(self) -> bool:
+        return self._max_on
+
+    @max_peak_search_enabled.setter
+    def max_peak_search_enabled(self, on: bool) -> None:
+        """display_manager.py:139-157: every enable starts from an empty hold."""
+        on = bool(on)
+        if on and not self._max_on and self._state is not None:
+            self._state.clear_max_hold()
+        self._max_on = on
+
+    @property
+    def min_hold_enabled(self) -> bool:
+        return self._min_on
+
+    @min_hold_enabled.setter
+    def min_hold_enabled(self, on: bool) -> None:
+        """display_manager.py:166-176: the buffer is reset on every toggle."""
+        on = bool(on)
+        if on != self._min_on and self._state is not None:
+            self._state.clear_min_hold()
+        self._min_on = on
 
     def start_tare(self) -> None:
         if self._state is not None:
@@ -71,7 +93,9 @@ class B200FramePipeline:
         self.frequency_bins = bins
         self._live = trace_update(row, st, self.cal_offset_db)
         if self.peak_list_enabled:
-            self.peaks = top_peaks(bins, self._live[0])
+            # display_data_processor.py:417-418: separation scales with the trace width
+            self.peaks = top_peaks(bins, self._live[0], min_sep_bins=max(10, len(bins) // 50),
+                                   min_excursion_db=self.peak_excursion)
         return True
 
     # ---- what the widgets read ---------------------------------------------------------------------------
@@ -82,12 +106,12 @@ class B200FramePipeline:
     @property
     def max_power_levels(self) -> Optional[np.ndarray]:
         st = self._state
-        return st.max_hold.cpu().numpy() if st is not None and st.max_hold_enabled and st.valid[0] else None
+        return st.max_hold.cpu().numpy() if st is not None and st.valid[0] else None
 
     @property
     def min_power_levels(self) -> Optional[np.ndarray]:
         st = self._state
-        return st.min_hold.cpu().numpy() if st is not None and st.min_hold_enabled and st.valid[1] else None
+        return st.min_hold.cpu().numpy() if st is not None and st.valid[1] else None
 
     @property
     def baseline_power_levels(self) -> Optional[np.ndarray]:

@@ -45,12 +45,18 @@ _W_OUT = None
 _W_WIN = None
 
 
+FS_HZ, FC_HZ = 2.048e6, 98e6       # RTL defaults (core/source_manager.py:67): only the freq-bin rebuild uses them
+
+
 def _cpu_worker(span):
-    """Literal per-frame loop of datasources/rtl_samples.py:169-184 over frames [lo, hi)."""
+    """What one RtlSamplesDataSource.get_power_levels call does per frame (datasources/rtl_samples.py:167-188):
+    the raw-sample copy (:168), window * FFT * shift * |.|^2 * dB (:169-184) and the frequency-bin rebuild (:188)."""
     from oracle import oracle as O
     lo, hi = span
     for f in range(lo, hi):
-        _W_OUT[f] = O.power_db_frame(_W_IQ[f], _W_WIN, O.MODE_POWER)
+        raw = _W_IQ[f].copy()                                              # :168  self._store_raw(samples.copy())
+        _W_OUT[f] = O.power_db_frame(raw, _W_WIN, O.MODE_POWER)            # :169-184
+        O.freq_bins(N_FFT, FS_HZ, FC_HZ)                                   # :188  rebuilt on every call
     return hi - lo
 
 
@@ -115,7 +121,7 @@ def reference_arm(args):
     if rank != 0:
         return
     cores = host_cores()
-    sample_frames = 2048
+    sample_frames = BATCH                       # one step = the whole 8192-frame batch, like the GPU arm
     ref = CpuReference(sample_frames, cores)
     for _ in range(max(args.warmup, 1)):
         ref.step()
@@ -126,15 +132,25 @@ def reference_arm(args):
     ref.close()
     value = args.steps * sample_frames * N_FFT / dt
     import scipy
+    try:
+        affinity = sorted(os.sched_getaffinity(0))
+        aff = f"{affinity[0]}-{affinity[-1]}" if affinity == list(range(affinity[0], affinity[-1] + 1)) else str(affinity)
+    except AttributeError:
+        aff = "n/a"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.gpus), "n_fft": N_FFT, "window": "hanning", "mode": "power",
-                   "step_sample": f"{sample_frames} frames per step (bounded sample of the 8192-frame batch)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample_frames} frames/step, reference per-frame chain "
-                                   f"(scipy {scipy.__version__}, numpy {np.__version__}) over {cores} processes"},
+                   "batch_per_step": sample_frames,
+                   "per_frame_work": "raw-sample copy + window*FFT*shift*|.|^2*dB + freq-bin rebuild "
+                                     "(rtl_samples.py:168-188), one Python call per frame like the reference's tick",
+                   "note": "CPU arm: one host, all cores; the same 8192-frame batch per step whatever --gpus says"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "affinity": aff,
+                         "sample": f"{sample_frames} frames/step x {args.steps} steps, reference per-frame chain "
+                                   f"(scipy {scipy.__version__}, numpy {np.__version__}) over {cores} processes; "
+                                   "the reference is pure Python whose tree is absent on the GPU box, so the arm runs the "
+                                   "oracle's line-for-line restatement (oracle/oracle.py, pinned by tests/golden)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -231,6 +247,133 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
+# config 4 inside the same line: 300 sub-bands x 16 frames x 8192 points, sharded by rank, rows exchanged, grid stitched
+# ------------------------------------------------------------------------------------------
+CFG4 = {"bands": 300, "frames": 16, "n_fft": 8192, "band_hz": 20e6}
+_CFG4_KEEP = {}
+
+
+def measure_cfg4(dev, world, rank, precision, reps=20):
+    import torch
+    import torch.distributed as dist
+    from topdogspectrumanalyser_b200 import synth
+    from topdogspectrumanalyser_b200.sweep import WidebandSweep, shard_bands, shard_grid
+    nb, fr, n = CFG4["bands"], CFG4["frames"], CFG4["n_fft"]
+    mine = shard_bands(nb, world, rank)
+    iq = torch.from_numpy(synth.cfg4_subbands(nb, fr, n, seed=3, bands=mine)).to(dev)
+    out = {"workload": f"cfg4: {nb} sub-bands x {fr} frames x {n} points, {world} rank(s), "
+                       f"{len(shard_bands(nb, world, 0))} sub-bands on the largest shard",
+           "samples_per_sweep": nb * fr * n, "grid_bins": None}
+
+    def timed(sw, what):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        for _ in range(3):
+            sw.stitch(sw.all_rows(iq))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t_rows = t_st = 0.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            ev[0].record()
+            rows = sw.all_rows(iq)
+            ev[1].record()
+            grid = sw.stitch(rows)
+            ev[2].record()
+        e1.record()
+        torch.cuda.synchronize()
+        # phase split from the LAST repetition's events (device time), whole-loop time for the rate
+        t_rows, t_st = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+        ms = torch.tensor([e0.elapsed_time(e1) / reps, t_rows, t_st], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = ms.tolist()
+        return rows, grid, {"ms_per_sweep": ms[0], "rows_and_exchange_us": ms[1] * 1e3, "stitch_us": ms[2] * 1e3,
+                            "samples_per_s": nb * fr * n / (ms[0] * 1e-3), "exchange": sw.exchange, "grid": what}
+
+    modes = [("auto", "sharded")] if world > 1 else [("auto", "replicated")]
+    if world > 1:
+        modes.append(("nccl", "replicated"))               # round 1's path, for comparison
+    for exchange, grid_mode in modes:
+        sw = WidebandSweep(nb, CFG4["band_hz"], n, 0.0, precision=precision, device=dev, exchange=exchange, grid=grid_mode)
+        rows, grid, res = timed(sw, grid_mode)
+        key = "fused" if exchange == "auto" else "nccl_allgather"
+        out[key] = res
+        out["grid_bins"] = sw.m
+        if exchange == "auto":
+            if world > 1:
+                # every rank recomputes ALL sub-bands on its own GPU (single-GPU path) and compares bit for bit
+                full = torch.from_numpy(synth.cfg4_subbands(nb, fr, n, seed=3)).to(dev)
+                solo = WidebandSweep(nb, CFG4["band_hz"], n, 0.0, precision=precision, device=dev, exchange="none")
+                solo.world, solo.rank = 1, 0
+                want_rows = solo.local_rows(full)
+                g0, cnt = shard_grid(sw.m, world, rank)
+                want_grid = solo.stitch(want_rows, sharded=False)[g0:g0 + cnt]
+                ok = torch.tensor([int(torch.equal(rows, want_rows)), int(torch.equal(grid, want_grid))], device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                out["rows_equal_single_gpu"], out["grid_equal_single_gpu"] = bool(ok[0].item()), bool(ok[1].item())
+            else:
+                _CFG4_KEEP.update(rows_host=rows.cpu().numpy(), grid_host=grid.cpu().numpy(), m=sw.m)
+    return out
+
+
+def check_cfg4_against_oracle(keep):
+    """rows within 1e-4 dB of the float64 chain, grid bit-equal to the reference's stitch (hackrf_sweep.py:150-166)."""
+    from oracle import oracle as O
+    from topdogspectrumanalyser_b200 import synth
+    nb, fr, n = CFG4["bands"], CFG4["frames"], CFG4["n_fft"]
+    w = O.make_window("hanning", n)
+    worst = 0.0
+    for b0 in range(0, nb, 20):
+        blk = synth.cfg4_subbands(nb, fr, n, seed=3, bands=range(b0, min(b0 + 20, nb)))
+        for i, band in enumerate(blk):
+            want = 10 * np.log10(O.linear_power_batch(band, w).mean(axis=0) + 1e-10)
+            worst = max(worst, float(np.abs(keep["rows_host"][b0 + i] - want).max()))
+    los = [CFG4["band_hz"] * i for i in range(nb)]
+    g = O.stitch_rows(keep["rows_host"], los, [l + CFG4["band_hz"] for l in los],
+                      O.sweep_grid(0, int(nb * CFG4["band_hz"]), CFG4["band_hz"] / n))
+    return {"rows_max_err_db": worst, "grid_equal": bool(np.array_equal(g, keep["grid_host"]))}
+
+
+# ------------------------------------------------------------------------------------------
+# host placement: each rank on the cores (and therefore the DRAM) of its GPU's NUMA node
+# ------------------------------------------------------------------------------------------
+def _parse_cpulist(text):
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.extend(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(index: int) -> dict:
+    """Pin this process to the CPU cores of the NUMA node the GPU hangs off, BEFORE any pinned buffer is allocated, so
+    that cudaHostAlloc's pages (first touch) land in that node's DRAM.  Returns what was done, for the JSON line."""
+    info = {"gpu": index, "numa_node": None, "cpus": None}
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:                      # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        info["numa_node"] = node
+        if node >= 0:
+            cpus = _parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+            allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                info["cpus"] = f"{allowed[0]}-{allowed[-1]} ({len(allowed)})"
+    except Exception as e:                                   # noqa: BLE001 - placement is best effort
+        info["error"] = repr(e)[:120]
+    return info
+
+
+# ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
 def main():
@@ -243,6 +386,10 @@ def main():
                     help="f64 = the reference's float64 arithmetic (strict 1e-4 dB parity); f32 = fast path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--min-seconds", type=float, default=0.25,
+                    help="also run the headline launch back to back for at least this long (sustained clocks); 0 = skip")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the config-4 (wideband stitch) object")
+    ap.add_argument("--no-other-sizes", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -261,6 +408,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
+    placement = bind_to_gpu_numa(local_rank)                # before the first pinned allocation
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -294,6 +442,52 @@ def main():
     x = iq_host_t.to(dev)
     out = torch.empty((BATCH, N_FFT), dtype=torch.float32, device=dev)
     samples_per_step = BATCH * N_FFT
+
+    def measure_size(n_fft, batch, precision, steps=10, warmup=3):
+        """Device time of kernel 1 at another FFT size (same bytes per launch as the headline batch)."""
+        xs = x.view(batch, n_fft)
+        os_ = out.view(batch, n_fft)
+        plan = SpectrumPlan(n_fft, "hanning", mode="power", precision=precision, device=dev)
+        for _ in range(warmup):
+            plan.psd_db(xs, out=os_)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            plan.psd_db(xs, out=os_)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        info = plan.info()
+        plan.close()
+        return {"kernel_ms": ms, "roofline_frac": BYTES_PER_SAMPLE * samples_per_step / (ms * 1e-3) / 1e9 / peak,
+                "threads_per_cta": info["threads_per_cta"], "ctas_per_sm": info["ctas_per_sm"]}
+
+    def measure_sustained(precision, seconds):
+        """The headline launch back to back for >= `seconds` (power-capped clocks), CUDA events, max over ranks."""
+        plan = SpectrumPlan(N_FFT, "hanning", mode="power", precision=precision, device=dev)
+        for _ in range(3):
+            plan.psd_db(x, out=out)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps, t0 = 0, time.perf_counter()
+        e0.record()
+        while True:
+            for _ in range(100):
+                plan.psd_db(x, out=out)
+            steps += 100
+            if time.perf_counter() - t0 >= seconds:        # host time only decides when to stop queueing
+                break
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        plan.close()
+        total_ms = float(ms.item())
+        return {"seconds": total_ms * 1e-3, "steps": steps, "ms_per_step": total_ms / steps,
+                "value": world * samples_per_step * steps / (total_ms * 1e-3), "unit": UNIT,
+                "roofline_frac": BYTES_PER_SAMPLE * samples_per_step * steps / (total_ms * 1e-3) / 1e9 / peak}
 
     def measure(precision, steps, warmup, sample_clocks):
         plan = SpectrumPlan(N_FFT, "hanning", mode="power", precision=precision, device=dev)
@@ -336,15 +530,15 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        per_rank = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
         if world > 1:
+            dist.all_gather(per_rank, t.clone())
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        else:
+            per_rank = [t.clone()]
         plan.close()
-        return float(t.item()) / steps
-
-    main_run = measure(args.precision, args.steps, args.warmup, True)
-    other = "f32" if args.precision == "f64" else "f64"
-    other_run = measure(other, min(args.steps, 20), 3, False)
-    e2e_s = measure_e2e(args.precision, args.e2e_steps)
+        secs = [float(v.item()) / steps for v in per_rank]
+        return float(t.item()) / steps, secs
 
     peaks = {}
     try:
@@ -352,6 +546,23 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    main_run = measure(args.precision, args.steps, args.warmup, True)
+    other = "f32" if args.precision == "f64" else "f64"
+    other_run = measure(other, min(args.steps, 20), 3, False)
+    sustained = measure_sustained(args.precision, args.min_seconds) if args.min_seconds > 0 else None
+    e2e_s, e2e_per_rank = measure_e2e(args.precision, args.e2e_steps)
+    other_sizes = None
+    if not args.no_other_sizes:
+        other_sizes = {}
+        for n_fft in (1024, 8192):
+            other_sizes[str(n_fft)] = {pr: measure_size(n_fft, BATCH * N_FFT // n_fft, pr) for pr in ("f64", "f32")}
+    cfg4 = None
+    if not args.no_cfg4:
+        try:
+            cfg4 = measure_cfg4(dev, world, rank, args.precision)
+        except Exception as e:                              # noqa: BLE001 - the headline line must still be printed
+            cfg4 = {"error": repr(e)[:300]}
     peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     traffic = None
     try:
@@ -390,7 +601,7 @@ def main():
                        "kernel": main_run["info"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": (f"fft_wl_kernel<{'double' if args.precision == 'f64' else 'float'},EpiDb> "
+                         "kernel": (f"fft_wl_kernel<{'double' if args.precision == 'f64' else 'float'},EpiDb,NB=1,ACC=0> "
                                     "(warp-local 16x256 plan, swizzled TMA tensor staging, dynamic frame scheduling)"
                                     if os.environ.get("TDSA_WL", "1") != "0" else
                                     f"fft_fused_kernel<{'double' if args.precision == 'f64' else 'float'},12,EpiDb>"),
@@ -403,8 +614,15 @@ def main():
                          "sm_side": sm_side(args.precision, main_run["kernel_ms"])},
             "e2e": {"value": world * samples_per_step / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": samples_per_step * 8, "d2h_bytes_per_step": samples_per_step * 4,
-                    "api": "SpectrumPlan.psd_db_host -> tdsa_psd_db_batch_host (pinned host in, pinned host out)",
-                    "ms_per_step": e2e_s * 1e3},
+                    "api": "SpectrumPlan.psd_db_host -> tdsa_psd_db_batch_host (pinned host in, pinned host out; "
+                           "H2D, kernel and D2H on three streams)",
+                    "ms_per_step": e2e_s * 1e3,
+                    "per_rank_h2d_gbs": [round(samples_per_step * 8 / t / 1e9, 1) for t in e2e_per_rank],
+                    "per_rank_d2h_gbs": [round(samples_per_step * 4 / t / 1e9, 1) for t in e2e_per_rank],
+                    "host_placement": placement},
+            "sustained": sustained,
+            "other_sizes": other_sizes,
+            "cfg4": cfg4,
             "gpu_launches": main_run["launches"],
             "clocks": main_run["clocks"],
             "other_precision": {"precision": other, "value": world * samples_per_step / (other_run["kernel_ms"] * 1e-3),
@@ -413,9 +631,13 @@ def main():
                                 "note": "f32 = fast path (deep-null tail, see DESIGN.md); f64 = strict 1e-4 dB parity"},
         }
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1)) if hasattr(os, "sched_setaffinity") else None   # all cores again
             cores = host_cores()
             line["cpu_baseline"] = run_cpu_baseline(12.0, 2048, cores)
             line["cpu_baseline"]["single_core"] = run_cpu_baseline(4.0, 512, 1)["value"]
+            if cfg4 is not None and "rows_host" in _CFG4_KEEP:
+                cfg4.update(check_cfg4_against_oracle(_CFG4_KEEP))      # the checker, in the CPU leg only
+        _CFG4_KEEP.clear()
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -167,6 +167,14 @@ int tdsa_psd_db_avg_hold_dev(tdsa_handle_t h, const void* iq, int64_t n_frames, 
 int tdsa_group_avg_db(tdsa_handle_t h, const void* iq, int64_t n_groups, int64_t frames_per_group,
                       float* db_rows);
 
+/* tdsa_group_avg_db fused with the all-gather of config 4: the dB row of local group g is stored by the FFT kernel
+ * itself into every rank's gathered row table, at row row_offset + g (peer_rows_host: HOST array of n_peers <= 8
+ * device pointers to float32 [n_bands][n_fft] buffers, one per rank of the node, e.g. torch symmetric memory;
+ * the caller's buffer is one of them).  The caller synchronises the ranks afterwards (a barrier, not a collective).
+ * N = 4096 / 8192 only (TDSA_ERR_UNSUPPORTED otherwise: use tdsa_group_avg_db + an all-gather). */
+int tdsa_group_avg_db_peers(tdsa_handle_t h, const void* iq, int64_t n_groups, int64_t frames_per_group,
+                            int64_t row_offset, const uint64_t* peer_rows_host, int n_peers);
+
 /* Config 3: Welch average + peak hold over a flat IQ stream:
  * segments s = 0 .. floor((n_samples - n_fft)/hop), each transformed as kernel 1;
  * avg_db = 10*log10(mean_s |X_s|^2 + floor) (TraceAverager 'lin' with n >= nseg,
@@ -246,6 +254,12 @@ int tdsa_parse_sweep_binary_host(const uint8_t* buf, int64_t len, int64_t max_ro
 int tdsa_stitch(const float* rows, const double* row_lo_hz, double row_hz, int64_t n_rows,
                 int64_t bins_per_row, double start_hz, double stop_hz, int64_t m, double* grid_out,
                 void* cuda_stream, int32_t* order_scratch);
+
+/* tdsa_stitch for a slice of the grid (sharded stitch): computes grid points g0 .. g0+count-1 of the m-point grid
+ * into grid_out[0 .. count); bit-identical to the same elements of tdsa_stitch's output. */
+int tdsa_stitch_range(const float* rows, const double* row_lo_hz, double row_hz, int64_t n_rows,
+                      int64_t bins_per_row, double start_hz, double stop_hz, int64_t m, int64_t g0, int64_t count,
+                      double* grid_out, void* cuda_stream, int32_t* order_scratch);
 
 /* Waterfall history ring, displays/waterfall.py:163-180: ring is float32 [2*H][W];
  * for each pushed row: ptr = (ptr-1) mod H; ring[ptr] = ring[ptr+H] = row.

@@ -50,6 +50,7 @@ SIGNATURES = {
                                         _vp]),
     "tdsa_trace_update_dev": (_i32, [_vp, _i64, _i64, _f64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "tdsa_group_avg_db": (_i32, [_vp, _vp, _i64, _i64, _vp]),
+    "tdsa_group_avg_db_peers": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i32]),
     "tdsa_welch": (_i32, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "tdsa_trace_update": (_i32, [_vp, _i64, _i64, _f64, _i32, _i32, _vp, _pi32, _vp, _vp, _pi32, _vp, _vp, _vp]),
     "tdsa_trace_update_tare": (_i32, [_vp, _i64, _i64, _f64, _i32, _i32, _vp, _pi32, _vp, _vp, _pi32, _vp, _vp, _vp,
@@ -63,6 +64,7 @@ SIGNATURES = {
     "tdsa_parse_sweep_binary_host": (_i32, [C.c_char_p, _i64, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(C.c_int64),
                                             C.POINTER(C.c_int64)]),
     "tdsa_stitch": (_i32, [_vp, _vp, _f64, _i64, _i64, _f64, _f64, _i64, _vp, _vp, _vp]),
+    "tdsa_stitch_range": (_i32, [_vp, _vp, _f64, _i64, _i64, _f64, _f64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "tdsa_ring_push": (_i32, [_vp, _i64, _vp, _i64, _i64, C.POINTER(C.c_int64), _vp]),
     "tdsa_ring_push_dev": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _i32, _vp, _vp, _vp]),
     "tdsa_ring_image_rgba": (_i32, [_vp, _i64, _i64, _vp, C.c_float, C.c_float, _vp, _vp, _vp]),

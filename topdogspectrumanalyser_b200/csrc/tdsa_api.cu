@@ -82,9 +82,9 @@ struct tdsa_plan {
   // scratch (grown on demand)
   void* scratch = nullptr; size_t scratch_bytes = 0;
   void* scratch2 = nullptr; size_t scratch2_bytes = 0;
-  // host pipeline
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr};
+  // host pipeline: H2D on `side`, kernels on the plan's stream, D2H on `back`
+  cudaStream_t side = nullptr, back = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   void* d_in[2] = {nullptr, nullptr}; void* d_out[2] = {nullptr, nullptr};
   size_t d_in_bytes = 0, d_out_bytes = 0;
 };
@@ -525,8 +525,10 @@ int tdsa_destroy(tdsa_handle_t p) {
     cudaFree(p->d_in[i]); cudaFree(p->d_out[i]);
     if (p->ev_h2d[i]) cudaEventDestroy(p->ev_h2d[i]);
     if (p->ev_k[i]) cudaEventDestroy(p->ev_k[i]);
+    if (p->ev_d2h[i]) cudaEventDestroy(p->ev_d2h[i]);
   }
   if (p->side) cudaStreamDestroy(p->side);
+  if (p->back) cudaStreamDestroy(p->back);
   delete p;
   return TDSA_OK;
 }
@@ -830,6 +832,25 @@ int tdsa_group_avg_db(tdsa_handle_t p, const void* iq, int64_t n_groups, int64_t
     CK(cudaGetLastError());
   }
   return TDSA_OK;
+}
+
+int tdsa_group_avg_db_peers(tdsa_handle_t p, const void* iq, int64_t n_groups, int64_t frames_per_group, int64_t row_offset,
+                            const uint64_t* peer_rows_host, int n_peers) {
+  if (!p) return fail(TDSA_ERR_INVALID, "null plan");
+  if (n_groups < 0 || frames_per_group < 1 || row_offset < 0) return fail(TDSA_ERR_INVALID, "bad group geometry");
+  if (!peer_rows_host || n_peers < 1 || n_peers > kMaxPeers) return fail(TDSA_ERR_INVALID, "1..%d peer buffers", kMaxPeers);
+  if (p->mode == TDSA_MODE_MAG20) return fail(TDSA_ERR_INVALID, "group average works on power; use power or psd mode");
+  if (n_groups == 0) return TDSA_OK;
+  if (!iq) return fail(TDSA_ERR_INVALID, "null buffer");
+  DeviceGuard guard(p->device);
+  if (p->win_dirty) { int rcw = upload_window(p); if (rcw) return rcw; }
+  if (frames_per_group >= (1 << 20) || n_groups * frames_per_group >= (1 << 30) ||
+      !wl_prepare(p, iq, n_groups * frames_per_group, p->n, kEpiDb, kAccGroupMean, false))
+    return fail(TDSA_ERR_UNSUPPORTED, "peer-store group mean needs N = 4096 or 8192 and 16-byte aligned frames");
+  WlAcc acc;
+  acc.group = (int)frames_per_group; acc.group_db = nullptr; acc.n_peers = n_peers; acc.peer_row0 = row_offset;
+  for (int i = 0; i < n_peers; ++i) acc.peer_rows[i] = (float*)(uintptr_t)peer_rows_host[i];
+  return run_wl(p, iq, n_groups * frames_per_group, p->n, nullptr, kEpiDb, nullptr, nullptr, kAccGroupMean, acc, nullptr, false);
 }
 
 int tdsa_welch(tdsa_handle_t p, const void* iq_stream, int64_t n_samples, int64_t hop, float* avg_db, float* peak_db) {
@@ -1158,6 +1179,24 @@ int tdsa_stitch(const float* rows, const double* row_lo_hz, double row_hz, int64
   return TDSA_OK;
 }
 
+int tdsa_stitch_range(const float* rows, const double* row_lo_hz, double row_hz, int64_t n_rows, int64_t bins_per_row,
+                      double start_hz, double stop_hz, int64_t m, int64_t g0, int64_t count, double* grid_out,
+                      void* cuda_stream, int32_t* order_scratch) {
+  if (!rows || !row_lo_hz || !grid_out || !order_scratch) return fail(TDSA_ERR_INVALID, "null argument");
+  if (n_rows < 1 || bins_per_row < 1 || m < 1 || g0 < 0 || count < 0 || g0 + count > m) return fail(TDSA_ERR_INVALID, "bad sizes");
+  if (count == 0) return TDSA_OK;
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  stitch_rank_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, s>>>(row_lo_hz, n_rows, order_scratch);
+  count_launch();
+  StitchArgs a;
+  a.rows = rows; a.lo = row_lo_hz; a.order = order_scratch; a.row_hz = row_hz; a.n_rows = n_rows; a.k = bins_per_row;
+  a.start = start_hz; a.stop = stop_hz; a.m = m; a.g0 = g0; a.count = count; a.out = grid_out;
+  stitch_interp_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(a);
+  count_launch();
+  CK(cudaGetLastError());
+  return TDSA_OK;
+}
+
 int tdsa_ring_push(const float* rows, int64_t n_rows, float* ring, int64_t H, int64_t W, int64_t* ptr_host,
                    void* cuda_stream) {
   if (!rows || !ring || !ptr_host || H < 1 || W < 1 || n_rows < 0) return fail(TDSA_ERR_INVALID, "bad argument");
@@ -1240,9 +1279,11 @@ int tdsa_psd_db_batch_host(tdsa_handle_t p, const void* iq_host, int64_t n_frame
   const size_t out_bytes = (size_t)chunk_frames * n * sizeof(float);
   if (!p->side) {
     CK(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&p->back, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
       CK(cudaEventCreateWithFlags(&p->ev_h2d[i], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&p->ev_k[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&p->ev_d2h[i], cudaEventDisableTiming));
     }
   }
   if (p->d_in_bytes < in_bytes) {
@@ -1261,16 +1302,21 @@ int tdsa_psd_db_batch_host(tdsa_handle_t p, const void* iq_host, int64_t n_frame
     const int b = (int)(c & 1);
     const int64_t nf = std::min(chunk_frames, n_frames - f0);
     const size_t bytes = (size_t)((nf - 1) * stride + n) * sizeof(float2);
-    // buffer b is free once the kernel + D2H of chunk c-2 are done
+    // three streams, two buffers: the input buffer b is free once the kernel of chunk c-2 has run, the output buffer b
+    // once the D2H of chunk c-2 has drained it; H2D, kernel and D2H of neighbouring chunks overlap (PCIe is full duplex)
     if (c >= 2) CK(cudaStreamWaitEvent(p->side, p->ev_k[b], 0));
     CK(cudaMemcpyAsync(p->d_in[b], (const float2*)iq_host + f0 * stride, bytes, cudaMemcpyHostToDevice, p->side));
     CK(cudaEventRecord(p->ev_h2d[b], p->side));
     CK(cudaStreamWaitEvent(user, p->ev_h2d[b], 0));
+    if (c >= 2) CK(cudaStreamWaitEvent(user, p->ev_d2h[b], 0));
     rc = run_fused(p, p->d_in[b], nf, stride, nullptr, kEpiDb, (float*)p->d_out[b], nullptr, nullptr, false);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(db_out_host + f0 * n, p->d_out[b], (size_t)nf * n * sizeof(float), cudaMemcpyDeviceToHost, user));
     CK(cudaEventRecord(p->ev_k[b], user));
+    CK(cudaStreamWaitEvent(p->back, p->ev_k[b], 0));
+    CK(cudaMemcpyAsync(db_out_host + f0 * n, p->d_out[b], (size_t)nf * n * sizeof(float), cudaMemcpyDeviceToHost, p->back));
+    CK(cudaEventRecord(p->ev_d2h[b], p->back));
   }
+  CK(cudaStreamSynchronize(p->back));
   CK(cudaStreamSynchronize(user));
   return TDSA_OK;
 }

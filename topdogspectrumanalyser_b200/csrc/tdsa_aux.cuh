@@ -395,8 +395,10 @@ struct StitchArgs {
   double row_hz;           // hz_high - hz_low of every row
   int64_t n_rows, k;
   double start, stop;
-  int64_t m;
-  double* out;             // [m]
+  int64_t m;               // points of the whole grid
+  int64_t g0 = 0;          // first grid point this launch computes (sharded stitch: each rank a slice)
+  int64_t count = -1;      // how many (-1: all m)
+  double* out;             // [count]: out[i] = grid point g0 + i
 };
 
 // x of sample i of row r, exactly as np.arange(lo + bw/2, hi, bw) produces it (start + i*bw).
@@ -411,8 +413,10 @@ __device__ __forceinline__ double stitch_y(const StitchArgs& a, int64_t sorted_i
 }
 
 __global__ void __launch_bounds__(256) stitch_interp_kernel(const StitchArgs a) {
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= a.m) return;
+  const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t cnt = a.count < 0 ? a.m : a.count;
+  if (gi >= cnt) return;
+  const int64_t g = a.g0 + gi;
   // np.linspace(start, stop, m): arange(m)*step + start, last element forced to stop
   const double step = __ddiv_rn(__dsub_rn(a.stop, a.start), (double)(a.m - 1));
   double xv = __dadd_rn(__dmul_rn((double)g, step), a.start);
@@ -421,8 +425,8 @@ __global__ void __launch_bounds__(256) stitch_interp_kernel(const StitchArgs a) 
   const int64_t total = a.n_rows * a.k;
   // np.interp: left/right clamp, then j = largest index with xp[j] <= x
   const double x_first = stitch_x(a, 0, bw), x_last = stitch_x(a, total - 1, bw);
-  if (xv < x_first) { a.out[g] = stitch_y(a, 0); return; }        // default left = fp[0]
-  if (xv > x_last) { a.out[g] = stitch_y(a, total - 1); return; } // default right = fp[-1]
+  if (xv < x_first) { a.out[gi] = stitch_y(a, 0); return; }        // default left = fp[0]
+  if (xv > x_last) { a.out[gi] = stitch_y(a, total - 1); return; } // default right = fp[-1]
   // j = largest index with x[j] <= xv.  Two levels: the row whose first sample is the last one <= xv (binary search
   // over rows), then the sample inside it from the spacing, corrected with the exact comparisons np.interp makes.
   int64_t j;
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(256) stitch_interp_kernel(const StitchArgs a) 
     if (stitch_x(a, hi_i, bw) <= xv) j = hi_i;
   }
   const double xj = stitch_x(a, j, bw), yj = stitch_y(a, j);
-  if (j == total - 1 || xj == xv) { a.out[g] = yj; return; }
+  if (j == total - 1 || xj == xv) { a.out[gi] = yj; return; }
   const double xj1 = stitch_x(a, j + 1, bw), yj1 = stitch_y(a, j + 1);
   const double slope = __ddiv_rn(__dsub_rn(yj1, yj), __dsub_rn(xj1, xj));
   double res = __dadd_rn(__dmul_rn(slope, __dsub_rn(xv, xj)), yj);
@@ -458,7 +462,7 @@ __global__ void __launch_bounds__(256) stitch_interp_kernel(const StitchArgs a) 
     res = __dadd_rn(__dmul_rn(slope, __dsub_rn(xv, xj1)), yj1);
     if (isnan(res) && yj == yj1) res = yj;
   }
-  a.out[g] = res;
+  a.out[gi] = res;
 }
 
 // ---------------------------------------------------------------------------------------

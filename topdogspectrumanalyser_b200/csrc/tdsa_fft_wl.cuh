@@ -41,6 +41,7 @@
 namespace tdsa {
 
 enum : int { kAccSum = 1, kAccMax = 2, kAccMin = 4, kAccGroup = 8, kAccRows = 16 };
+constexpr int kMaxPeers = 8;
 
 // arguments of the accumulating epilogue
 struct WlAcc {
@@ -50,6 +51,11 @@ struct WlAcc {
   float* part_max = nullptr;        // [grid][N] per-CTA running max of |X|^2 (-inf = no live frame)
   float* part_min = nullptr;        // [grid][N] per-CTA running min of |X|^2 (+inf = no live frame)
   float* group_db = nullptr;        // kAccGroup: [n_frames / group][N] dB of each group's mean
+  // kAccGroup, multi-GPU (config 4): instead of group_db the row of group g is stored straight into EVERY rank's copy of
+  // the gathered row table (peer memory over NVLink), at row peer_row0 + g: compute and all-gather in one kernel
+  float* peer_rows[kMaxPeers] = {};
+  int n_peers = 0;
+  int64_t peer_row0 = 0;
   int group = 1;                    // frames per claimed unit (kAccGroup: frames per group)
   int64_t only_row = -1;            // kAccRows: >= 0 stores the dB row of this frame only (at row 0), -1 stores every row
 };
@@ -343,6 +349,9 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     TDSA_STAMP(5);
     engine_sync();                                           // all sixteen Y_r complete; every warp has left this stage
     TDSA_STAMP(6);
+    // Measured (round 2): letting the LAST warp to finish its staged reads refill the stage (shared-memory counter, frame
+    // claimed at the top of the iteration) instead of thread 0 after this barrier was slower: 78.0 -> 83.9 us (f32),
+    // 135.2 -> 139.4 us (f64) at N = 4096, 206.8 -> 219.1 us (f64) at N = 8192.
     if (tid == 0) {
       if constexpr (NB > 1) mbar_wait(ctrl_u32 + 32 + 8 * stg, (uint32_t)((it / NSTAGE) & 1));   // the other engine too
       fence_proxy_async();
@@ -427,7 +436,7 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       if constexpr ((ACC & kAccGroup) != 0) {
         if ((f + 1) % group == 0) {                          // last frame of its group: emit the mean as one dB row, clear
           tmem_wait_st();
-          float* row = acc.group_db + (int64_t)(f / group) * N;
+          const int64_t g = (int64_t)(f / group);
           const double inv = 1.0 / (double)group;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -436,7 +445,14 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const double s = __hiloint2double((int)u[2 * i + 1], (int)u[2 * i]);
-              row[bin_of(8 * half + i)] = to_db_m<double, false>(s * inv, a.ep);
+              const float db = to_db_m<double, false>(s * inv, a.ep);
+              const int64_t at = bin_of(8 * half + i);
+              if (acc.n_peers == 0) {
+                acc.group_db[g * N + at] = db;
+              } else {
+#pragma unroll 1
+                for (int pr = 0; pr < acc.n_peers; ++pr) acc.peer_rows[pr][(acc.peer_row0 + g) * N + at] = db;
+              }
               u[2 * i] = 0u; u[2 * i + 1] = 0u;
             }
             tmem_st16(tacc + 16 * half, u);

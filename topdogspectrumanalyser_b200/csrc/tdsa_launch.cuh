@@ -346,14 +346,10 @@ cudaError_t launch_wl_impl(int epi, const FftArgs<T>& a, const WlLaunch& L, cuda
       default: break;
     }
   } else if (L.nb == 2 && !dc) {
-    switch (L.acc_flags) {
-      case 0:
-        if (epi == kEpiDb) TDSA_WL_GO(EpiDb, false, 2, 0);
-        if (epi == kEpiLinear) TDSA_WL_GO(EpiLinear, false, 2, 0);
-        break;
-      case kAccGroupMean: TDSA_WL_GO(EpiDb, false, 2, kAccGroupMean);
-      default: break;
-    }
+    // Two engines (N = 8192): only the group-mean epilogue.  For plain dB rows the two-engine kernel measured no better
+    // than the four-pass classic kernel (f32 0.55 vs 0.58, f64 0.30 vs 0.31 of HBM: the engines share one stage and
+    // run in lock step), so those stay on fft_fused_kernel; frames_per_group = 1 gives its dB rows when wanted.
+    if (L.acc_flags == kAccGroupMean) TDSA_WL_GO(EpiDb, false, 2, kAccGroupMean);
   }
 #undef TDSA_WL_GO
   return cudaErrorInvalidValue;
@@ -364,7 +360,7 @@ inline bool wl_supported(int nb, int epi, int acc_flags, bool dc) {
     if (acc_flags == 0) return epi == kEpiDb || epi == kEpiLinear;
     return !dc && (acc_flags == kAccAvg || acc_flags == kAccHold || acc_flags == kAccWelch || acc_flags == kAccGroupMean);
   }
-  if (nb == 2 && !dc) return acc_flags == 0 ? (epi == kEpiDb || epi == kEpiLinear) : acc_flags == kAccGroupMean;
+  if (nb == 2 && !dc) return acc_flags == kAccGroupMean;
   return false;
 }
 cudaError_t launch_wl_f32(int epi, const FftArgs<float>& a, const WlLaunch& L, cudaStream_t s, LaunchInfo* info, bool dry);

@@ -332,18 +332,22 @@ def trace_update(rows: torch.Tensor, state: TraceState, cal_offset_db: float = 0
 
 
 def stitch(rows: torch.Tensor, row_lo_hz: torch.Tensor, row_hz: float, start_hz: float, stop_hz: float,
-           m: int) -> torch.Tensor:
-    """hackrf_sweep stitch on the device (datasources/hackrf_sweep.py:150-166)."""
+           m: int, g0: int = 0, count: Optional[int] = None) -> torch.Tensor:
+    """hackrf_sweep stitch on the device (datasources/hackrf_sweep.py:150-166).
+
+    ``g0`` / ``count`` select a slice of the m-point grid (sharded stitch across ranks); the slice is bit-identical
+    to the same elements of the full grid."""
     _require_cuda()
     lib = L.load()
     if rows.dtype != torch.float32 or row_lo_hz.dtype != torch.float64:
         raise ValueError("rows float32 [R, K], row_lo_hz float64 [R]")
     rows, row_lo_hz = rows.contiguous(), row_lo_hz.contiguous()
     r, k = rows.shape
-    out = torch.empty(m, dtype=torch.float64, device=rows.device)
+    count = int(m) - int(g0) if count is None else int(count)
+    out = torch.empty(count, dtype=torch.float64, device=rows.device)
     order = torch.empty(r, dtype=torch.int32, device=rows.device)
-    L.check(lib.tdsa_stitch(rows.data_ptr(), row_lo_hz.data_ptr(), float(row_hz), r, k, float(start_hz),
-                            float(stop_hz), int(m), out.data_ptr(), _stream_ptr(), order.data_ptr()))
+    L.check(lib.tdsa_stitch_range(rows.data_ptr(), row_lo_hz.data_ptr(), float(row_hz), r, k, float(start_hz),
+                                  float(stop_hz), int(m), int(g0), count, out.data_ptr(), _stream_ptr(), order.data_ptr()))
     return out
 
 

@@ -47,11 +47,27 @@ def gather_rows(local_rows: torch.Tensor, n_bands: int, group=None) -> torch.Ten
     return torch.cat(parts, dim=0)
 
 
+def shard_grid(m: int, world: int, rank: int) -> Tuple[int, int]:
+    """(first grid point, count) of the slice of the stitched grid that ``rank`` interpolates."""
+    base, extra = divmod(m, world)
+    g0 = rank * base + min(rank, extra)
+    return g0, base + (1 if rank < extra else 0)
+
+
 class WidebandSweep:
-    """6 GHz span as ``n_bands`` x ``band_hz`` sub-bands, ``n_fft`` points each."""
+    """6 GHz span as ``n_bands`` x ``band_hz`` sub-bands, ``n_fft`` points each.
+
+    Multi-GPU (one process per GPU, ``torch.distributed`` initialised): sub-bands are sharded by rank.
+    ``exchange="peer"`` (default when symmetric memory is available) fuses the per-band mean with the gather: the FFT
+    kernel's epilogue stores every finished dB row straight into ALL ranks' row tables over NVLink
+    (``tdsa_group_avg_db_peers``), followed by one cross-rank barrier; ``exchange="nccl"`` computes local rows and
+    all-gathers them.  ``grid="sharded"`` lets each rank interpolate only its slice of the stitched grid
+    (``shard_grid``); ``"replicated"`` computes the whole grid on every rank like round 1.
+    """
 
     def __init__(self, n_bands: int = 300, band_hz: float = 20e6, n_fft: int = 8192, start_hz: float = 0.0,
-                 precision: str = "f64", device: Optional[torch.device] = None):
+                 precision: str = "f64", device: Optional[torch.device] = None, exchange: str = "auto",
+                 grid: str = "replicated", group=None):
         from .engine import SpectrumPlan
         self.n_bands, self.band_hz, self.n_fft = n_bands, float(band_hz), n_fft
         self.start_hz = float(start_hz)
@@ -61,6 +77,31 @@ class WidebandSweep:
         self.m = int((self.stop_hz - self.start_hz) / self.bin_hz)
         self.plan = SpectrumPlan(n_fft, "hanning", mode="power", precision=precision, fs=band_hz, device=device)
         self.device = self.plan.device
+        self.group, self.grid_mode = group, grid
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self._lo_all = self.band_lo_hz(range(n_bands))
+        self._symm = None
+        self.exchange = "none" if self.world == 1 else exchange
+        if self.world > 1 and exchange in ("auto", "peer"):
+            try:
+                self._setup_peer_rows()
+                self.exchange = "peer"
+            except Exception as e:                         # noqa: BLE001 - no symmetric memory on this system
+                if exchange == "peer":
+                    raise
+                self.exchange, self.peer_error = "nccl", repr(e)
+
+    def _setup_peer_rows(self) -> None:
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        if self.n_fft not in (4096, 8192) or self.world > 8:
+            raise RuntimeError("peer exchange needs N = 4096 / 8192 and at most 8 ranks")
+        self.rows_all = symm_mem.empty((self.n_bands, self.n_fft), dtype=torch.float32, device=self.device)
+        self.rows_all.fill_(float("nan"))
+        self._symm = symm_mem.rendezvous(self.rows_all, self.group if self.group is not None else dist.group.WORLD)
+        self._peer_ptrs = (C.c_uint64 * self.world)(*[int(p) for p in self._symm.buffer_ptrs])
+        self._symm.barrier()
 
     def band_lo_hz(self, bands) -> torch.Tensor:
         return torch.tensor([self.start_hz + b * self.band_hz for b in bands], dtype=torch.float64, device=self.device)
@@ -69,13 +110,29 @@ class WidebandSweep:
         """``iq_local[n_local, F, N]`` -> dB rows ``[n_local, N]`` (kernel 1 + linear mean over F)."""
         return self.plan.group_avg_db(iq_local)
 
-    def stitch(self, rows: torch.Tensor, arrival_order: Optional[List[int]] = None) -> torch.Tensor:
-        """Stitch all sub-band rows onto the fixed grid (float64 ``[M]``), reference geometry."""
+    def all_rows(self, iq_local: torch.Tensor) -> torch.Tensor:
+        """Rank-local IQ -> every sub-band's dB row ``[n_bands, N]`` on every rank."""
+        if self.exchange == "peer":
+            from . import _lib as L
+            mine = shard_bands(self.n_bands, self.world, self.rank)
+            n_local, frames = int(iq_local.shape[0]), int(iq_local.shape[1])
+            self.plan._bind()
+            if n_local:
+                L.check(self.plan.lib.tdsa_group_avg_db_peers(self.plan._h, iq_local.data_ptr(), n_local, frames, mine.start,
+                                                              self._peer_ptrs, self.world))
+            self._symm.barrier()                           # every rank's rows have landed in every table
+            return self.rows_all
+        return gather_rows(self.local_rows(iq_local), self.n_bands, self.group)
+
+    def stitch(self, rows: torch.Tensor, arrival_order: Optional[List[int]] = None, sharded: Optional[bool] = None) -> torch.Tensor:
+        """Stitch all sub-band rows onto the fixed grid (float64), reference geometry; ``sharded``: this rank's slice."""
         from .engine import stitch
-        bands = list(range(self.n_bands)) if arrival_order is None else arrival_order
-        return stitch(rows, self.band_lo_hz(bands), self.band_hz, self.start_hz, self.stop_hz, self.m)
+        lo = self._lo_all if arrival_order is None else self.band_lo_hz(arrival_order)
+        sharded = (self.grid_mode == "sharded" and self.world > 1) if sharded is None else sharded
+        g0, count = shard_grid(self.m, self.world, self.rank) if sharded else (0, self.m)
+        return stitch(rows, lo, self.band_hz, self.start_hz, self.stop_hz, self.m, g0, count)
 
     def run(self, iq_local: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Rank-local IQ -> (all dB rows ``[n_bands, N]``, stitched grid ``[M]``) on every rank."""
-        rows = gather_rows(self.local_rows(iq_local), self.n_bands, group)
+        """Rank-local IQ -> (all dB rows ``[n_bands, N]``, stitched grid: whole ``[M]`` or this rank's slice)."""
+        rows = self.all_rows(iq_local)
         return rows, self.stitch(rows)

@@ -265,47 +265,121 @@ def gen_stitch():
                         binary=np.frombuffer(binary, dtype=np.uint8))
 
 
+class _QtStub(types.ModuleType):
+    """A module whose every attribute is a do-nothing class: lets Qt-bound reference modules be IMPORTED here (PyQt6,
+    pyqtgraph are not installed) so that their numpy arithmetic can be executed; nothing Qt does is relied upon."""
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        cls = type(name, (), {"__init__": lambda self, *a, **k: None,
+                              "__getattr__": lambda self, n: (lambda *a, **k: None)})
+        setattr(self, name, cls)
+        return cls
+
+
+def _install_qt_stubs():
+    for m in ("PyQt6", "PyQt6.QtCore", "PyQt6.QtWidgets", "PyQt6.QtGui", "pyqtgraph", "pyqtgraph.exporters"):
+        if m not in sys.modules:
+            sys.modules[m] = _QtStub(m)
+    sys.modules["PyQt6"].QtCore = sys.modules["PyQt6.QtCore"]
+    sys.modules["PyQt6"].QtWidgets = sys.modules["PyQt6.QtWidgets"]
+    sys.modules["PyQt6"].QtGui = sys.modules["PyQt6.QtGui"]
+    sys.modules["pyqtgraph"].exporters = sys.modules["pyqtgraph.exporters"]
+
+
 def gen_analytics():
-    """Colour map (export_manager.py:72-79), density histogram (density_display.py:306-319) and band power
-    (marker_manager.py:308-318): the three formulas are executed here with numpy exactly as written there
-    (those modules import Qt at module level, so their classes cannot be instantiated in this container)."""
+    """Colour map (core/export_manager.py:67-84), density histogram (displays/density_display.py:306-319), band power
+    (core/marker_manager.py:308-318) and marker snap (:74-99), all by EXECUTING the reference's own methods: the
+    Qt-bound modules are imported against stub Qt modules (see _QtStub) and driven with stand-in widgets."""
+    _install_qt_stubs()
+    from core.export_manager import ExportManager                  # noqa: E402  (reference)
+    from core.marker_manager import MarkerManager                  # noqa: E402  (reference)
+    from displays.density_display import DensityDisplay            # noqa: E402  (reference)
+    from utils.constants import DisplayMode                        # noqa: E402  (reference)
     rng = np.random.default_rng(81)
+    # ---- waterfall export colour map: run export_display('png') and capture the bytes handed to QImage -------------
     arr = rng.normal(-70.0, 25.0, (6, 64)).astype(np.float32)
     arr[0, 0] = np.float32(-100.0); arr[0, 1] = np.float32(-20.0)
     wf_min_db, wf_max_db = -100.0, -20.0
     lut = rng.integers(0, 256, (256, 4), dtype=np.uint8)
-    norm = np.clip((arr - wf_min_db) / max(wf_max_db - wf_min_db, 1e-9), 0.0, 1.0)
-    rgba = np.ascontiguousarray(lut[(norm * 255).astype(np.uint8)], dtype=np.uint8)
-    # density histogram, three frames, decay "medium"
-    _AMP_BINS, _AMP_MIN, _AMP_RNG, decay = 512, -200.0, 300.0, 0.96
+    captured = {}
+
+    class _QImage:
+        class Format:
+            Format_RGBA8888 = 0
+
+        def __init__(self, data, w, h, stride, fmt):
+            captured["rgba"] = np.frombuffer(data, dtype=np.uint8).reshape(h, w, 4).copy()
+
+        def isNull(self):
+            return False
+
+    class _QPixmap:
+        @staticmethod
+        def fromImage(qi):
+            return _QPixmap()
+
+        def save(self, filename, fmt):
+            return True
+
+    class _QFileDialog:
+        @staticmethod
+        def getSaveFileName(*a, **k):
+            return "/tmp/tdsa_golden_export.png", ""
+
+    sys.modules["PyQt6.QtGui"].QImage, sys.modules["PyQt6.QtGui"].QPixmap = _QImage, _QPixmap
+    sys.modules["PyQt6.QtWidgets"].QFileDialog = _QFileDialog
+    wf = types.SimpleNamespace(waterfall_array=arr, wf_min_db=wf_min_db, wf_max_db=wf_max_db, _lut_rgba=lut)
+    mw = types.SimpleNamespace(current_stacked_index=DisplayMode.WATERFALL, paused=False, waterfall_widget=wf,
+                               status_label=types.SimpleNamespace(setText=lambda t: captured.setdefault("status", t)))
+    ExportManager(mw).export_display("png")
+    rgba = captured["rgba"]
+    # ---- density histogram: DensityDisplay._update_hist on a stand-in object, three frames, decay "medium" ----------
     frames = rng.normal(-80.0, 30.0, (3, 48)).astype(np.float32)
     frames[1, 3] = np.nan; frames[2, 5] = np.float32(-200.2); frames[2, 6] = np.float32(120.0)
-    hist = np.zeros((48, _AMP_BINS), dtype=np.float32)
+    sink = types.SimpleNamespace(setImage=lambda *a, **k: None, setRect=lambda *a, **k: None)
+    dd = types.SimpleNamespace(_hist=None, _hist_n_freq=None, _decay=0.96, _img=sink, _last_freq_rect=None,
+                               plot_widget=types.SimpleNamespace(setXRange=lambda *a, **k: None))
+    dd._ensure_hist = types.MethodType(DensityDisplay._ensure_hist, dd)
+    fb = np.linspace(88e6, 108e6, 48)
     hists = []
     for live in frames:
-        live_db = live.astype(np.float64)
-        n = len(live_db)
-        if decay < 1.0:
-            hist *= decay
-        valid = ~np.isnan(live_db)
-        raw_idx = np.full(n, -1, dtype=np.int32)
-        raw_idx[valid] = ((live_db[valid] - _AMP_MIN) / _AMP_RNG * _AMP_BINS).astype(np.int32)
-        in_range = (raw_idx >= 0) & (raw_idx < _AMP_BINS)
-        fi = np.where(in_range)[0]
-        if len(fi):
-            hist[fi, raw_idx[fi]] += 1.0
-        hists.append(hist.copy())
-    # band power
+        DensityDisplay._update_hist(dd, live.astype(np.float64), fb)
+        hists.append(dd._hist.copy())
+    # ---- band power and marker snap: MarkerManager on a stand-in main window -------------------------------------------
     bins = np.linspace(88e6, 108e6, 2048)
     levels = rng.normal(-90.0, 6.0, 2048).astype(np.float32)
     lo, hi = 95e6, 99.5e6
-    mask = (bins >= lo) & (bins <= hi)
-    bin_width = (bins[-1] - bins[0]) / max(len(bins) - 1, 1)
-    total = np.sum(10.0 ** (levels[mask].astype(np.float64) / 10.0)) * bin_width
-    bp = 10.0 * np.log10(max(total, 1e-30))
+    mm_mw = types.SimpleNamespace(frequency_bins=bins, live_power_levels=levels,
+                                  status_label=types.SimpleNamespace(setText=lambda t: None))
+    mm = MarkerManager(mm_mw)
+    bp = mm._band_power(lo, hi)
+    mm._sync_display = lambda name: None
+    mm._refresh_status = lambda: None
+    snaps_levels, snaps_thr, snaps_exc, snaps_idx = [], [], [], []
+    for case in range(8):
+        lv = rng.normal(-90.0, 4.0, 1024).astype(np.float32)
+        for _ in range(case % 4):
+            k = int(rng.integers(3, 1020))
+            lv[k] += np.float32(rng.uniform(8, 40))
+        if case == 5:
+            lv[300:304] = lv.max() + np.float32(5.0)            # flat-topped peak
+        if case == 6:
+            lv = np.sort(lv)                                     # no peak: argmax fallback
+        thr, exc = (-200.0, 6.0) if case % 2 == 0 else (-80.0, 10.0)
+        b = np.linspace(88e6, 108e6, 1024)
+        mm_mw.frequency_bins, mm_mw.live_power_levels = b, lv
+        mm_mw.peak_threshold, mm_mw.peak_excursion = thr, exc
+        mm.active_marker = "F1"
+        mm.snap_to_peak()
+        snaps_levels.append(lv); snaps_thr.append(thr); snaps_exc.append(exc)
+        snaps_idx.append(int(np.argmin(np.abs(b - mm.markers["F1"].position))))
     np.savez_compressed(os.path.join(OUT, "analytics.npz"), meta=META, cm_rows=arr, cm_lo=wf_min_db, cm_hi=wf_max_db,
                         cm_lut=lut, cm_rgba=rgba, dens_frames=frames, dens_hists=np.stack(hists),
-                        bp_bins=bins, bp_levels=levels, bp_lo=lo, bp_hi=hi, bp_value=bp)
+                        bp_bins=bins, bp_levels=levels, bp_lo=lo, bp_hi=hi, bp_value=bp,
+                        snap_levels=np.stack(snaps_levels), snap_thr=np.array(snaps_thr), snap_exc=np.array(snaps_exc),
+                        snap_idx=np.array(snaps_idx), executed_reference=True)
 
 
 def gen_waterfall():

@@ -133,7 +133,7 @@ def test_two_engine_8192_kernel(dev, parity_log, prec, tol):
     plan.close()
 
 
-@pytest.mark.parametrize("n,groups,frames", [(4096, 37, 16), (8192, 21, 16), (8192, 5, 3)])
+@pytest.mark.parametrize("n,groups,frames", [(4096, 37, 16), (8192, 21, 16), (8192, 5, 3), (8192, 300, 16), (4096, 700, 4)])
 def test_group_mean_in_the_epilogue(dev, parity_log, n, groups, frames):
     """Config-4 rows: the linear mean of each group of frames, formed in TMEM inside the FFT kernel, as one dB row."""
     import torch

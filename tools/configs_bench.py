@@ -45,6 +45,26 @@ for prec in ("f64", "f32"):
     torch.cuda.synchronize(); lat = []
     for c in range(50):
         t0 = time.perf_counter(); st.push_chunk(chunks[c]); torch.cuda.synchronize(); lat.append(time.perf_counter() - t0)
+    # timeline of a burst: the producer has filled every pinned slot in place (acquire), then the slots are committed
+    # back to back, so the host loop is out of the way and the copy of chunk k+1 can be seen under the compute of chunk k
+    torch.cuda.synchronize()
+    for i in range(st.depth):
+        st.pinned[(st.chunks_in + i) % st.depth].numpy()[:] = chunks[i]
+    st.record_timeline(True)
+    for _ in range(6):
+        for i in range(st.depth):
+            st.commit()
+    tl = st.timeline()
+    st.record_timeline(False)
+    # copy of chunk k+1 under the compute of chunk k: overlap of the two intervals, summed over the recorded chunks
+    ov = sum(max(0.0, min(tl[k + 1]["h2d_us"][1], tl[k]["compute_us"][1]) - max(tl[k + 1]["h2d_us"][0], tl[k]["compute_us"][0]))
+             for k in range(len(tl) - 1))
+    h2d = sum(t["h2d_us"][1] - t["h2d_us"][0] for t in tl[1:])
+    if prec == "f64":
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump(tl, open("gpurun_out/cfg5_timeline.json", "w"))
     print(json.dumps({"config": "cfg5 streaming waterfall 20 Msps x 10 s, 65536-sample pinned chunks", "precision": prec,
                       "seconds_for_10s_of_signal": stats["seconds"], "real_time_factor": stats["real_time_factor"],
-                      "samples_per_s": stats["samples_per_s"], "chunk_latency_ms_median": float(np.median(lat)) * 1e3}))
+                      "samples_per_s": stats["samples_per_s"], "chunk_latency_ms_median": float(np.median(lat)) * 1e3,
+                      "graphs": st.use_graphs, "h2d_under_previous_compute_frac": ov / h2d if h2d else None,
+                      "timeline_first_chunks": tl[:4]}))

@@ -209,9 +209,9 @@ static bool dyn_enabled() {
   return on;
 }
 
-static bool welch_cluster_enabled() {
-  static const bool on = [] { const char* e = getenv("TDSA_WELCH_CLUSTER"); return !(e && e[0] == '0'); }();
-  return on;
+static bool welch_cluster_enabled() {   // read at every call so that tests can compare both paths in one process
+  const char* e = getenv("TDSA_WELCH_CLUSTER");
+  return !(e && e[0] == '0');
 }
 
 static bool wl_enabled() {
@@ -794,6 +794,41 @@ int tdsa_psd_db_avg_hold_dc(tdsa_handle_t p, const void* iq, int64_t n_frames, i
                                count_state_host, max_hold, min_hold, hold_valid_host, last_only, db_out);
 }
 
+// Group means in the FFT kernel's accumulating epilogue.  A group is the unit CTAs claim; when there are too few groups
+// to fill the GPU (config 4 sharded over 8 ranks: 38 groups for 148 SMs) every group is split into `split` units whose
+// float64 sums are combined by group_finish_kernel.  Rows go to db_rows or, with peers, into every rank's table.
+static int run_group_mean(tdsa_plan* p, const void* iq, int64_t n_groups, int64_t frames, float* db_rows,
+                          const uint64_t* peers, int n_peers, int64_t row0) {
+  const int64_t n = p->n;
+  int split = 1;
+  static const int force_split = [] { const char* e = getenv("TDSA_GROUP_SPLIT"); return e ? atoi(e) : 0; }();
+  const int64_t want_units = 2 * (int64_t)p->sm_count * (p->wl_nb == 1 ? 2 : 1);
+  while (split * 2 <= frames && frames % (split * 2) == 0 && n_groups * split < want_units) split *= 2;
+  if (force_split > 0 && frames % force_split == 0) split = force_split;
+  WlAcc acc;
+  acc.group = (int)(frames / split);
+  if (split == 1) {
+    acc.group_db = db_rows; acc.n_peers = n_peers; acc.peer_row0 = row0;
+    for (int i = 0; i < n_peers; ++i) acc.peer_rows[i] = (float*)(uintptr_t)peers[i];
+    return run_wl(p, iq, n_groups * frames, n, nullptr, kEpiDb, nullptr, nullptr, kAccGroupMean, acc, nullptr, false);
+  }
+  int rc = ensure_scratch(&p->scratch, &p->scratch_bytes, (size_t)(n_groups * split * n) * sizeof(double));
+  if (rc) return rc;
+  acc.unit_sum = (double*)p->scratch;
+  rc = run_wl(p, iq, n_groups * frames, n, nullptr, kEpiDb, nullptr, nullptr, kAccGroupMean, acc, nullptr, false);
+  if (rc) return rc;
+  GroupFinishArgs g;
+  g.unit_sum = acc.unit_sum; g.n_groups = n_groups; g.width = n; g.split = split; g.frames = (int)frames;
+  g.scale = (p->mode == TDSA_MODE_PSD) ? 1.0 / (p->fs * (double)n) : 1.0; g.floor = p->floor; g.mode = p->mode;
+  g.group_db = db_rows; g.n_peers = n_peers; g.peer_row0 = row0;
+  for (int i = 0; i < 8; ++i) g.peer_rows[i] = i < n_peers ? (float*)(uintptr_t)peers[i] : nullptr;
+  const int64_t total = n_groups * n;
+  group_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, p->stream>>>(g);
+  count_launch();
+  CK(cudaGetLastError());
+  return TDSA_OK;
+}
+
 int tdsa_group_avg_db(tdsa_handle_t p, const void* iq, int64_t n_groups, int64_t frames_per_group, float* db_rows) {
   if (!p) return fail(TDSA_ERR_INVALID, "null plan");
   if (n_groups < 0 || frames_per_group < 1) return fail(TDSA_ERR_INVALID, "bad group geometry");
@@ -806,11 +841,8 @@ int tdsa_group_avg_db(tdsa_handle_t p, const void* iq, int64_t n_groups, int64_t
   // per group out; no linear rows at all)
   if (frames_per_group < (1 << 20) && n_groups * frames_per_group < (1 << 30)) {
     if (p->win_dirty) { int rcw = upload_window(p); if (rcw) return rcw; }
-    if (wl_prepare(p, iq, n_groups * frames_per_group, n, kEpiDb, kAccGroupMean, false)) {
-      WlAcc acc;
-      acc.group = (int)frames_per_group; acc.group_db = db_rows;
-      return run_wl(p, iq, n_groups * frames_per_group, n, nullptr, kEpiDb, nullptr, nullptr, kAccGroupMean, acc, nullptr, false);
-    }
+    if (wl_prepare(p, iq, n_groups * frames_per_group, n, kEpiDb, kAccGroupMean, false))
+      return run_group_mean(p, iq, n_groups, frames_per_group, db_rows, nullptr, 0, 0);
   }
   const int64_t per_group = frames_per_group * n * (int64_t)sizeof(double);
   // groups per launch: the float64 rows of a chunk are written by the FFT kernel and read straight back by the
@@ -847,10 +879,7 @@ int tdsa_group_avg_db_peers(tdsa_handle_t p, const void* iq, int64_t n_groups, i
   if (frames_per_group >= (1 << 20) || n_groups * frames_per_group >= (1 << 30) ||
       !wl_prepare(p, iq, n_groups * frames_per_group, p->n, kEpiDb, kAccGroupMean, false))
     return fail(TDSA_ERR_UNSUPPORTED, "peer-store group mean needs N = 4096 or 8192 and 16-byte aligned frames");
-  WlAcc acc;
-  acc.group = (int)frames_per_group; acc.group_db = nullptr; acc.n_peers = n_peers; acc.peer_row0 = row_offset;
-  for (int i = 0; i < n_peers; ++i) acc.peer_rows[i] = (float*)(uintptr_t)peer_rows_host[i];
-  return run_wl(p, iq, n_groups * frames_per_group, p->n, nullptr, kEpiDb, nullptr, nullptr, kAccGroupMean, acc, nullptr, false);
+  return run_group_mean(p, iq, n_groups, frames_per_group, nullptr, peer_rows_host, n_peers, row_offset);
 }
 
 int tdsa_welch(tdsa_handle_t p, const void* iq_stream, int64_t n_samples, int64_t hop, float* avg_db, float* peak_db) {

@@ -51,6 +51,8 @@ struct WlAcc {
   float* part_max = nullptr;        // [grid][N] per-CTA running max of |X|^2 (-inf = no live frame)
   float* part_min = nullptr;        // [grid][N] per-CTA running min of |X|^2 (+inf = no live frame)
   float* group_db = nullptr;        // kAccGroup: [n_frames / group][N] dB of each group's mean
+  double* unit_sum = nullptr;       // kAccGroup, split groups: [n_frames / group][N] float64 SUM of each unit's frames
+                                    // (a unit is a part of a group; group_finish_kernel adds the parts and takes the dB)
   // kAccGroup, multi-GPU (config 4): instead of group_db the row of group g is stored straight into EVERY rank's copy of
   // the gathered row table (peer memory over NVLink), at row peer_row0 + g: compute and all-gather in one kernel
   float* peer_rows[kMaxPeers] = {};
@@ -445,15 +447,16 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const double s = __hiloint2double((int)u[2 * i + 1], (int)u[2 * i]);
-              const float db = to_db_m<double, false>(s * inv, a.ep);
               const int64_t at = bin_of(8 * half + i);
+              u[2 * i] = 0u; u[2 * i + 1] = 0u;
+              if (acc.unit_sum != nullptr) { acc.unit_sum[g * N + at] = s; continue; }
+              const float db = to_db_m<double, false>(s * inv, a.ep);
               if (acc.n_peers == 0) {
                 acc.group_db[g * N + at] = db;
               } else {
 #pragma unroll 1
                 for (int pr = 0; pr < acc.n_peers; ++pr) acc.peer_rows[pr][(acc.peer_row0 + g) * N + at] = db;
               }
-              u[2 * i] = 0u; u[2 * i + 1] = 0u;
             }
             tmem_st16(tacc + 16 * half, u);
           }

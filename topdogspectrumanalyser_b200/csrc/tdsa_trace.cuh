@@ -140,6 +140,33 @@ __global__ void __launch_bounds__(256) welch_acc_finish_kernel(const double* __r
   peak_db[k] = to_db<float>(m, ep);
 }
 
+// Config-4 rows from split groups: each group's `split` unit sums are added, divided by the frames of the group and
+// converted to one dB row, stored locally (group_db) or straight into every rank's row table (peers, NVLink stores).
+struct GroupFinishArgs {
+  const double* unit_sum;   // [n_groups * split][W]
+  int64_t n_groups, width;
+  int split, frames;
+  double scale, floor;
+  int mode;
+  float* group_db;          // [n_groups][W] or null
+  float* peer_rows[8];
+  int n_peers;
+  int64_t peer_row0;
+};
+__global__ void __launch_bounds__(256) group_finish_kernel(const GroupFinishArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n_groups * a.width) return;
+  const int64_t g = i / a.width, k = i - g * a.width;
+  double s = 0.0;
+  for (int u = 0; u < a.split; ++u) s += a.unit_sum[(g * a.split + u) * a.width + k];
+  EpiParams ep;
+  ep.db_out = nullptr; ep.lin_out = nullptr; ep.scale = a.scale; ep.floor = a.floor; ep.mode = a.mode;
+  const float db = to_db_m<double, false>(s / (double)a.frames, ep);
+  if (a.n_peers == 0) a.group_db[i] = db;
+  else
+    for (int pr = 0; pr < a.n_peers; ++pr) a.peer_rows[pr][(a.peer_row0 + g) * a.width + k] = db;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // General path: frame-ordered scan over float64 linear rows (one thread per bin), flags read from the device.
 // The rows of a chunk are written by the FFT kernel and consumed here while still in L2 (the caller sizes chunks).

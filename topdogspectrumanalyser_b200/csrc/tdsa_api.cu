@@ -800,10 +800,21 @@ int tdsa_psd_db_avg_hold_dc(tdsa_handle_t p, const void* iq, int64_t n_frames, i
 static int run_group_mean(tdsa_plan* p, const void* iq, int64_t n_groups, int64_t frames, float* db_rows,
                           const uint64_t* peers, int n_peers, int64_t row0) {
   const int64_t n = p->n;
-  int split = 1;
+  // split = units per group.  Cost model (microseconds): the slowest CTA runs ceil(units / CTAs) units of frames/split
+  // frames each (measured ~0.92 ns per point and frame in float64, ~0.52 ns in float32 on one CTA slot), and split > 1
+  // adds a float64 partial row per unit that is written and read once (~4 TB/s through L2).
   static const int force_split = [] { const char* e = getenv("TDSA_GROUP_SPLIT"); return e ? atoi(e) : 0; }();
-  const int64_t want_units = 2 * (int64_t)p->sm_count * (p->wl_nb == 1 ? 2 : 1);
-  while (split * 2 <= frames && frames % (split * 2) == 0 && n_groups * split < want_units) split *= 2;
+  const int64_t ctas = (int64_t)p->sm_count * (p->wl_nb == 1 ? 2 : 1);
+  const double t_frame = (double)n * (p->precision == TDSA_PREC_F64 ? 0.92e-3 : 0.52e-3);
+  int split = 1;
+  double best = 0.0;
+  for (int sp = 1; sp <= frames && sp <= 64; sp *= 2) {
+    if (frames % sp) break;
+    const int64_t rounds = (n_groups * sp + ctas - 1) / ctas;
+    const double cost = (double)rounds * (double)(frames / sp) * t_frame +
+                        (sp > 1 ? (double)(n_groups * sp) * (double)n * 16.0 / 4.0e6 : 0.0);
+    if (sp == 1 || cost < best) { best = cost; split = sp; }
+  }
   if (force_split > 0 && frames % force_split == 0) split = force_split;
   WlAcc acc;
   acc.group = (int)(frames / split);

@@ -431,10 +431,20 @@ __global__ void __launch_bounds__(256) stitch_interp_kernel(const StitchArgs a) 
   // over rows), then the sample inside it from the spacing, corrected with the exact comparisons np.interp makes.
   int64_t j;
   {
-    int64_t rlo = 0, rhi = a.n_rows - 1;             // x_first(rlo) <= xv (checked above)
-    while (rlo < rhi) {
-      const int64_t mid = (rlo + rhi + 1) >> 1;
-      if (stitch_x(a, mid * a.k, bw) <= xv) rlo = mid; else rhi = mid - 1;
+    // hackrf_sweep's rows tile the span uniformly, so the row follows from the spacing; a few exact comparisons settle
+    // it, and anything irregular falls back to the binary search over rows
+    int64_t rlo = (int64_t)floor((xv - x_first) / a.row_hz);
+    rlo = rlo < 0 ? 0 : (rlo > a.n_rows - 1 ? a.n_rows - 1 : rlo);
+    int steps = 0;
+    while (steps < 4 && rlo < a.n_rows - 1 && stitch_x(a, (rlo + 1) * a.k, bw) <= xv) { ++rlo; ++steps; }
+    while (steps < 4 && rlo > 0 && stitch_x(a, rlo * a.k, bw) > xv) { --rlo; ++steps; }
+    if (steps >= 4) {
+      rlo = 0;
+      int64_t rhi = a.n_rows - 1;                    // x_first(0) <= xv (checked above)
+      while (rlo < rhi) {
+        const int64_t mid = (rlo + rhi + 1) >> 1;
+        if (stitch_x(a, mid * a.k, bw) <= xv) rlo = mid; else rhi = mid - 1;
+      }
     }
     const double x0 = stitch_x(a, rlo * a.k, bw);
     int64_t i = (int64_t)floor((xv - x0) / bw);

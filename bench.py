@@ -547,11 +547,40 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
 
+    def measure_host_link():
+        """What the host <-> device links give when every rank copies at once and nothing else runs: plain pinned
+        cudaMemcpyAsync of the e2e step's buffers, H2D and D2H concurrently on two streams (the ceiling of `e2e`)."""
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        reps = 3
+        for timed in (False, True):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps if timed else 1):
+                with torch.cuda.stream(s_in):
+                    x.copy_(iq_host_t, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    db_host_t.copy_(out, non_blocking=True)
+            s_in.synchronize()
+            s_out.synchronize()
+            dt = (time.perf_counter() - t0) / reps
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        per_rank = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(per_rank, t)
+        else:
+            per_rank = [t]
+        secs = [float(v.item()) for v in per_rank]
+        return {"what": "all ranks at once: 268 MB pinned H2D + 134 MB pinned D2H on two streams, no kernel",
+                "per_rank_h2d_gbs": [round(samples_per_step * 8 / v / 1e9, 1) for v in secs],
+                "aggregate_h2d_plus_d2h_gbs": round(sum(samples_per_step * 12 / v for v in secs) / 1e9, 1),
+                "samples_per_s_if_copy_bound": sum(samples_per_step / v for v in secs)}
+
     main_run = measure(args.precision, args.steps, args.warmup, True)
     other = "f32" if args.precision == "f64" else "f64"
     other_run = measure(other, min(args.steps, 20), 3, False)
     sustained = measure_sustained(args.precision, args.min_seconds) if args.min_seconds > 0 else None
     e2e_s, e2e_per_rank = measure_e2e(args.precision, args.e2e_steps)
+    host_link = measure_host_link()
     other_sizes = None
     if not args.no_other_sizes:
         other_sizes = {}
@@ -619,7 +648,7 @@ def main():
                     "ms_per_step": e2e_s * 1e3,
                     "per_rank_h2d_gbs": [round(samples_per_step * 8 / t / 1e9, 1) for t in e2e_per_rank],
                     "per_rank_d2h_gbs": [round(samples_per_step * 4 / t / 1e9, 1) for t in e2e_per_rank],
-                    "host_placement": placement},
+                    "host_placement": placement, "host_link_ceiling": host_link},
             "sustained": sustained,
             "other_sizes": other_sizes,
             "cfg4": cfg4,

@@ -675,7 +675,7 @@ static int avg_hold_dev_impl(tdsa_handle_t p, const void* iq, int64_t n_frames, 
     acc.weight = wts; acc.part_sum = ps;
     rc = run_wl(p, iq, n_frames, stride, nullptr, kEpiDb, nullptr, nullptr, kAccAvg, acc, nullptr, false);
     if (rc) return rc;
-    avg_finish_kernel<<<fin_grid, 256, 0, p->stream>>>(ps, grid, p->n, p->d_meta, scale, p->floor, p->mode, avg_state, flags,
+    avg_finish_kernel<<<partial_grid(p->n), 256, 0, p->stream>>>(ps, grid, p->n, p->d_meta, scale, p->floor, p->mode, avg_state, flags,
                                                       n_frames, db_out, last_row);
     count_launch();
     CK(cudaGetLastError());
@@ -693,7 +693,7 @@ static int avg_hold_dev_impl(tdsa_handle_t p, const void* iq, int64_t n_frames, 
     acc.part_max = pmx; acc.part_min = pmn; acc.only_row = last_only ? n_frames - 1 : -1;
     rc = run_wl(p, iq, n_frames, stride, nullptr, kEpiDb, db_out, nullptr, kAccHold, acc, nullptr, false);
     if (rc) return rc;
-    hold_finish_kernel<<<fin_grid, 256, 0, p->stream>>>(pmx, pmn, grid, p->n, p->d_meta, scale, p->floor, p->mode, max_hold, min_hold);
+    hold_finish_kernel<<<partial_grid(p->n), 256, 0, p->stream>>>(pmx, pmn, grid, p->n, p->d_meta, scale, p->floor, p->mode, max_hold, min_hold);
     count_launch();
     if (last_row) {
       CK(cudaMemcpyAsync(last_row, last_only ? db_out : db_out + (n_frames - 1) * p->n, sizeof(float) * p->n,
@@ -913,7 +913,7 @@ int tdsa_welch(tdsa_handle_t p, const void* iq_stream, int64_t n_samples, int64_
       rca = run_wl(p, iq_stream, nseg, hop, nullptr, kEpiDb, nullptr, nullptr, kAccWelch, acc, nullptr, false);
       if (rca) return rca;
       const double scale = (p->mode == TDSA_MODE_PSD) ? 1.0 / (p->fs * (double)n) : 1.0;
-      welch_acc_finish_kernel<<<(int)((n + 255) / 256), 256, 0, p->stream>>>(ps, pmx, grid, n, nseg, scale, p->floor, p->mode,
+      welch_acc_finish_kernel<<<partial_grid(n), 256, 0, p->stream>>>(ps, pmx, grid, n, nseg, scale, p->floor, p->mode,
                                                                            avg_db, peak_db);
       count_launch();
       CK(cudaGetLastError());

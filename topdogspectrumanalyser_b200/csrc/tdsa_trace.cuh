@@ -74,15 +74,39 @@ __global__ void flags_prepare_kernel(int32_t* __restrict__ flags, double* __rest
   }
 }
 
+// Per-CTA partial rows [n_parts][width] are combined by blocks of 256 threads = 32 neighbouring bins x 8 slices of the
+// partial rows (coalesced 32-bin reads, 8-way parallel walk down the rows, shared-memory combine in slice order, so
+// the float64 sums are deterministic).  Launch with partial_grid(width) blocks; thread (slice 0, bin) finishes the bin.
+constexpr int kPartBins = 32, kPartSlices = 8;
+inline int partial_grid(int64_t width) { return (int)((width + kPartBins - 1) / kPartBins); }
+
+template <typename V, typename Op>
+__device__ __forceinline__ V reduce_partials(const V* __restrict__ part, int n_parts, int64_t width, V init, Op op, bool* owner,
+                                             int64_t* bin) {
+  __shared__ double s_buf[kPartSlices][kPartBins];
+  const int kb = threadIdx.x & (kPartBins - 1), sl = threadIdx.x / kPartBins;
+  const int64_t k = (int64_t)blockIdx.x * kPartBins + kb;
+  V v = init;
+  if (k < width)
+    for (int c = sl; c < n_parts; c += kPartSlices) v = op(v, part[(int64_t)c * width + k]);
+  __syncthreads();                                    // the buffer may still be read by a previous call's owner threads
+  s_buf[sl][kb] = (double)v;
+  __syncthreads();
+  *owner = sl == 0 && k < width;
+  *bin = k;
+  if (sl == 0)
+    for (int i = 1; i < kPartSlices; ++i) v = op(v, (V)s_buf[i][kb]);
+  return v;
+}
+
 // fused running average, last step: state <- carry * state + scale * sum over CTAs; one dB row out
 __global__ void __launch_bounds__(256) avg_finish_kernel(const double* __restrict__ part_sum, int n_parts, int64_t width,
                                                         const double* __restrict__ meta, double scale, double floor, int mode,
                                                         double* __restrict__ avg_state, int32_t* __restrict__ flags,
                                                         int64_t live, float* __restrict__ db_out, float* __restrict__ last_row) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= width) return;
-  double s = 0.0;
-  for (int c = 0; c < n_parts; ++c) s += part_sum[(int64_t)c * width + k];
+  bool owner; int64_t k;
+  double s = reduce_partials<double>(part_sum, n_parts, width, 0.0, [](double a, double b) { return a + b; }, &owner, &k);
+  if (!owner) return;
   s *= scale;
   const double carry = meta[0];
   const double v = carry != 0.0 ? __fma_rn(carry, avg_state[k], s) : s;
@@ -100,26 +124,27 @@ __global__ void __launch_bounds__(256) hold_finish_kernel(const float* __restric
                                                          int n_parts, int64_t width, const double* __restrict__ meta,
                                                          double scale, double floor, int mode, float* __restrict__ max_hold,
                                                          float* __restrict__ min_hold) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= width) return;
   EpiParams ep;
   ep.db_out = nullptr; ep.lin_out = nullptr; ep.scale = scale; ep.floor = floor; ep.mode = mode;
   if (max_hold) {
-    float m = -INFINITY;
-    bool nan_only = true;                                 // every live frame had NaN in this bin
-    for (int c = 0; c < n_parts; ++c) m = fmaxf(m, part_max[(int64_t)c * width + k]);
-    nan_only = (m == -INFINITY);
-    const float db = nan_only ? -500.0f : to_db<float>(m, ep);     // _nan_safe: NaN -> -500 on the initialising frame
-    if (meta[3] != 0.0) { if (!nan_only) max_hold[k] = fmaxf(max_hold[k], db); }
-    else max_hold[k] = db;
+    bool owner; int64_t k;
+    const float m = reduce_partials<float>(part_max, n_parts, width, -INFINITY, [](float a, float b) { return fmaxf(a, b); }, &owner, &k);
+    if (owner) {
+      const bool nan_only = (m == -INFINITY);                        // every live frame had NaN in this bin
+      const float db = nan_only ? -500.0f : to_db<float>(m, ep);     // _nan_safe: NaN -> -500 on the initialising frame
+      if (meta[3] != 0.0) { if (!nan_only) max_hold[k] = fmaxf(max_hold[k], db); }
+      else max_hold[k] = db;
+    }
   }
   if (min_hold) {
-    float m = INFINITY;
-    for (int c = 0; c < n_parts; ++c) m = fminf(m, part_min[(int64_t)c * width + k]);
-    const bool nan_only = (m == INFINITY);
-    const float db = nan_only ? 500.0f : to_db<float>(m, ep);
-    if (meta[4] != 0.0) { if (!nan_only) min_hold[k] = fminf(min_hold[k], db); }
-    else min_hold[k] = db;
+    bool owner; int64_t k;
+    const float m = reduce_partials<float>(part_min, n_parts, width, INFINITY, [](float a, float b) { return fminf(a, b); }, &owner, &k);
+    if (owner) {
+      const bool nan_only = (m == INFINITY);
+      const float db = nan_only ? 500.0f : to_db<float>(m, ep);
+      if (meta[4] != 0.0) { if (!nan_only) min_hold[k] = fminf(min_hold[k], db); }
+      else min_hold[k] = db;
+    }
   }
 }
 
@@ -128,11 +153,10 @@ __global__ void __launch_bounds__(256) welch_acc_finish_kernel(const double* __r
                                                               int n_parts, int64_t width, int64_t n_seg, double scale,
                                                               double floor, int mode, float* __restrict__ avg_db,
                                                               float* __restrict__ peak_db) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= width) return;
-  double s = 0.0;
-  float m = -INFINITY;
-  for (int c = 0; c < n_parts; ++c) { s += part_sum[(int64_t)c * width + k]; m = fmaxf(m, part_max[(int64_t)c * width + k]); }
+  bool owner, owner2; int64_t k, k2;
+  const double s = reduce_partials<double>(part_sum, n_parts, width, 0.0, [](double a, double b) { return a + b; }, &owner, &k);
+  const float m = reduce_partials<float>(part_max, n_parts, width, -INFINITY, [](float a, float b) { return fmaxf(a, b); }, &owner2, &k2);
+  if (!owner) return;
   EpiParams ep;
   ep.db_out = nullptr; ep.lin_out = nullptr; ep.scale = 1.0; ep.floor = floor; ep.mode = mode;
   avg_db[k] = to_db<double>(s * scale / (double)n_seg, ep);
@@ -201,7 +225,8 @@ __global__ void __launch_bounds__(256) trace_scan_dev_kernel(const TraceScanDevA
   ep.db_out = nullptr; ep.lin_out = nullptr; ep.scale = 1.0; ep.floor = a.floor; ep.mode = a.mode;
   float last_db = a.last_row ? a.last_row[k] : 0.0f;     // what a skipped frame repeats (hackrf_samples.py:351-355)
   bool any = false;
-  constexpr int kAhead = 8;                              // rows fetched ahead of the recurrence (they come from L2)
+  constexpr int kAhead = 32;                             // rows fetched ahead of the recurrence (they come from L2; one
+                                                         // warp per SM runs this kernel, so latency is hidden by depth only)
   for (int64_t f0 = 0; f0 < a.n_frames; f0 += kAhead) {
     double pre[kAhead];
 #pragma unroll

@@ -1203,6 +1203,17 @@ int tdsa_parse_sweep_binary_host(const uint8_t* buf, int64_t len, int64_t max_ro
   return TDSA_OK;
 }
 
+static void fill_stitch_invariants(StitchArgs& a) {
+  volatile double num = a.stop - a.start, den = (double)(a.m - 1);      // volatile: no contraction / reassociation
+  a.step = a.m > 1 ? num / den : 0.0;
+  volatile double rh = a.row_hz, kk = (double)a.k;
+  a.bw = rh / kk;
+  volatile double b = a.bw;
+  a.half_bw = b / 2.0;
+  a.inv_bw = 1.0 / a.bw;
+  a.inv_row = 1.0 / a.row_hz;
+}
+
 int tdsa_stitch(const float* rows, const double* row_lo_hz, double row_hz, int64_t n_rows, int64_t bins_per_row,
                 double start_hz, double stop_hz, int64_t m, double* grid_out, void* cuda_stream, int32_t* order_scratch) {
   if (!rows || !row_lo_hz || !grid_out || !order_scratch) return fail(TDSA_ERR_INVALID, "null argument");
@@ -1213,6 +1224,7 @@ int tdsa_stitch(const float* rows, const double* row_lo_hz, double row_hz, int64
   StitchArgs a;
   a.rows = rows; a.lo = row_lo_hz; a.order = order_scratch; a.row_hz = row_hz; a.n_rows = n_rows; a.k = bins_per_row;
   a.start = start_hz; a.stop = stop_hz; a.m = m; a.out = grid_out;
+  fill_stitch_invariants(a);
   stitch_interp_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(a);
   count_launch();
   CK(cudaGetLastError());
@@ -1231,6 +1243,7 @@ int tdsa_stitch_range(const float* rows, const double* row_lo_hz, double row_hz,
   StitchArgs a;
   a.rows = rows; a.lo = row_lo_hz; a.order = order_scratch; a.row_hz = row_hz; a.n_rows = n_rows; a.k = bins_per_row;
   a.start = start_hz; a.stop = stop_hz; a.m = m; a.g0 = g0; a.count = count; a.out = grid_out;
+  fill_stitch_invariants(a);
   stitch_interp_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(a);
   count_launch();
   CK(cudaGetLastError());

@@ -399,12 +399,18 @@ struct StitchArgs {
   int64_t g0 = 0;          // first grid point this launch computes (sharded stitch: each rank a slice)
   int64_t count = -1;      // how many (-1: all m)
   double* out;             // [count]: out[i] = grid point g0 + i
+  // loop invariants, computed once on the host with the same IEEE operations numpy uses (a float64 division costs
+  // ~40 FP64-pipe instructions on the device; ten of them per grid point were most of this kernel's 75 us)
+  double step;             // (stop - start) / (m - 1)          np.linspace
+  double bw;               // row_hz / k                        hackrf_sweep.py:159
+  double half_bw;          // bw / 2
+  double inv_bw, inv_row;  // reciprocals, used for index GUESSES only (every guess is verified by exact comparisons)
 };
 
 // x of sample i of row r, exactly as np.arange(lo + bw/2, hi, bw) produces it (start + i*bw).
 __device__ __forceinline__ double stitch_x(const StitchArgs& a, int64_t sorted_idx, double bw) {
   const int64_t rr = sorted_idx / a.k, i = sorted_idx - rr * a.k;
-  const double x0 = __dadd_rn(a.lo[a.order[rr]], __ddiv_rn(bw, 2.0));
+  const double x0 = __dadd_rn(a.lo[a.order[rr]], a.half_bw);
   return __dadd_rn(x0, __dmul_rn((double)i, bw));
 }
 __device__ __forceinline__ double stitch_y(const StitchArgs& a, int64_t sorted_idx) {
@@ -418,10 +424,10 @@ __global__ void __launch_bounds__(256) stitch_interp_kernel(const StitchArgs a) 
   if (gi >= cnt) return;
   const int64_t g = a.g0 + gi;
   // np.linspace(start, stop, m): arange(m)*step + start, last element forced to stop
-  const double step = __ddiv_rn(__dsub_rn(a.stop, a.start), (double)(a.m - 1));
+  const double step = a.step;
   double xv = __dadd_rn(__dmul_rn((double)g, step), a.start);
   if (g == a.m - 1 && a.m > 1) xv = a.stop;
-  const double bw = __ddiv_rn(a.row_hz, (double)a.k);
+  const double bw = a.bw;
   const int64_t total = a.n_rows * a.k;
   // np.interp: left/right clamp, then j = largest index with xp[j] <= x
   const double x_first = stitch_x(a, 0, bw), x_last = stitch_x(a, total - 1, bw);
@@ -433,7 +439,7 @@ __global__ void __launch_bounds__(256) stitch_interp_kernel(const StitchArgs a) 
   {
     // hackrf_sweep's rows tile the span uniformly, so the row follows from the spacing; a few exact comparisons settle
     // it, and anything irregular falls back to the binary search over rows
-    int64_t rlo = (int64_t)floor((xv - x_first) / a.row_hz);
+    int64_t rlo = (int64_t)floor((xv - x_first) * a.inv_row);
     rlo = rlo < 0 ? 0 : (rlo > a.n_rows - 1 ? a.n_rows - 1 : rlo);
     int steps = 0;
     while (steps < 4 && rlo < a.n_rows - 1 && stitch_x(a, (rlo + 1) * a.k, bw) <= xv) { ++rlo; ++steps; }
@@ -447,7 +453,7 @@ __global__ void __launch_bounds__(256) stitch_interp_kernel(const StitchArgs a) 
       }
     }
     const double x0 = stitch_x(a, rlo * a.k, bw);
-    int64_t i = (int64_t)floor((xv - x0) / bw);
+    int64_t i = (int64_t)floor((xv - x0) * a.inv_bw);
     i = i < 0 ? 0 : (i > a.k - 1 ? a.k - 1 : i);
     while (i < a.k - 1 && stitch_x(a, rlo * a.k + i + 1, bw) <= xv) ++i;
     while (i > 0 && stitch_x(a, rlo * a.k + i, bw) > xv) --i;

@@ -84,24 +84,35 @@ def test_fused_holds_without_averaging(dev, parity_log, last_only):
     plan.close()
 
 
-def test_general_scan_in_l2_sized_chunks(dev, parity_log):
-    """Averaging AND holds AND every row out: the frame-ordered scan, run over more frames than one 32 MB chunk of
-    float64 rows holds (1024 frames at N = 4096), so the state is carried across chunk boundaries."""
+@pytest.mark.parametrize("mode,navg", [("exp", 16), ("lin", 700), ("lin", 5000)])
+def test_general_scan_in_l2_sized_chunks(dev, parity_log, mode, navg):
+    """Averaging AND holds AND every row out: the frame-ordered scan (parallel over 32-frame blocks through the affine
+    form of the recurrence), run over more frames than one 32 MB chunk of float64 rows holds (1024 frames at N = 4096),
+    so the state is carried across block and chunk boundaries; 'lin' capped inside the run and never capped."""
     import torch
     from topdogspectrumanalyser_b200.engine import SpectrumPlan, TraceState
     n, b = 4096, 2300
     iq = synth.cfg2_frames(b=b, n=n, seed=503)
-    rows, a, mx, mn = _oracle_avg_sequence(iq, n, "exp", 16)
+    rows, a, mx, mn = _oracle_avg_sequence(iq, n, mode, navg)
     plan = SpectrumPlan(n, device=dev)
     st = TraceState(n, dev, max_hold_enabled=True, min_hold_enabled=True)
-    st.set_averaging("exp", 16)
-    got = plan.psd_db_avg_hold(torch.from_numpy(iq).to(dev), st).cpu().numpy()
+    st.set_averaging(mode, navg)
+    x = torch.from_numpy(iq).to(dev)
+    got = torch.cat([plan.psd_db_avg_hold(x[:1500], st), plan.psd_db_avg_hold(x[1500:], st)]).cpu().numpy()
     err = np.abs(got - rows).max()
     eh = max(np.abs(st.max_hold.cpu().numpy() - mx).max(), np.abs(st.min_hold.cpu().numpy() - mn).max())
-    parity_log("general_scan_chunked_exp16_rows_holds", max(err, eh), tol=TOL_DB, frames=b)
+    rel = np.abs(st.avg.cpu().numpy() - a._buffer).max() / np.abs(a._buffer).max()
+    parity_log(f"general_scan_chunked_{mode}{navg}_rows_holds", max(err, eh), tol=TOL_DB, frames=b, state_rel=float(rel))
     assert err <= TOL_DB and eh <= TOL_DB
-    assert np.abs(st.avg.cpu().numpy() - a._buffer).max() / np.abs(a._buffer).max() <= 1e-12
-    assert st.count == a._count and st.live_frames == b
+    assert rel <= 1e-12
+    assert st.count == a._count and st.live_frames == b - 1500
+    assert np.abs(st.last_row.cpu().numpy() - rows[-1]).max() <= TOL_DB
+    # last_only with a hold: same state, one row out
+    st2 = TraceState(n, dev, max_hold_enabled=True)
+    st2.set_averaging(mode, navg)
+    last = plan.psd_db_avg_hold(x, st2, last_only=True).cpu().numpy()
+    assert np.abs(last[0] - rows[-1]).max() <= TOL_DB
+    assert np.abs(st2.max_hold.cpu().numpy() - mx).max() <= TOL_DB
     plan.close()
 
 

@@ -76,6 +76,8 @@ struct tdsa_plan {
   int32_t* d_flags = nullptr; float* d_last_row = nullptr;
   // HackRF front end: per-frame mean / power / DC estimate (its own allocation: the large-FFT path uses scratch2)
   void* scratch_dc = nullptr; size_t scratch_dc_bytes = 0;
+  // blocked scan of the general trace path: per-block affine terms, start states and extrema
+  void* scan_scratch = nullptr; size_t scan_scratch_bytes = 0;
   // large-FFT (two-kernel) tables: inner plan size M = N/256
   double2* d_twin64 = nullptr; float2* d_twin32 = nullptr;    // twiddles of the M-point inner transform
   double2* d_twh64 = nullptr; float2* d_twh32 = nullptr;      // DIF tables of big_head_kernel (passes 0, 1)
@@ -518,7 +520,7 @@ int tdsa_destroy(tdsa_handle_t p) {
   cudaFree(p->d_win64); cudaFree(p->d_win32); cudaFree(p->d_tw64); cudaFree(p->d_tw32);
   cudaFree(p->d_wperm64); cudaFree(p->d_wperm32); cudaFree(p->d_sched); cudaFree(p->d_wltw64); cudaFree(p->d_wltw32);
   cudaFree(p->acc_parts); cudaFree(p->acc_weights); cudaFree(p->d_meta); cudaFree(p->d_flags); cudaFree(p->d_last_row);
-  cudaFree(p->scratch_dc);
+  cudaFree(p->scratch_dc); cudaFree(p->scan_scratch);
   cudaFree(p->d_twin64); cudaFree(p->d_twin32); cudaFree(p->d_twh64); cudaFree(p->d_twh32);
   cudaFree(p->scratch); cudaFree(p->scratch2);
   for (int i = 0; i < 2; ++i) {
@@ -717,6 +719,38 @@ static int avg_hold_dev_impl(tdsa_handle_t p, const void* iq, int64_t n_frames, 
     }
     rc = run_fused(p, src, nf, stride, dc, kEpiLinear, nullptr, lin, nullptr, false);
     if (rc) return rc;
+    if (!with_dc && nf >= 4 * kScanBlock) {        // every frame live: the scan runs parallel over frame blocks too
+      const int nblk = (int)((nf + kScanBlock - 1) / kScanBlock);
+      const size_t w = (size_t)p->n;
+      rc = ensure_scratch(&p->scan_scratch, &p->scan_scratch_bytes,
+                          (size_t)nblk * w * (2 * sizeof(double) + 2 * sizeof(float)) + (size_t)nblk * sizeof(double));
+      if (rc) return rc;
+      TraceBlockArgs b;
+      b.lin = lin; b.n_frames = nf; b.width = p->n; b.avg_mode = avg_mode; b.avg_n = avg_n; b.flags = flags;
+      b.avg_state = avg_state; b.max_hold = max_hold; b.min_hold = min_hold; b.last_row = last_row; b.last_only = last_only;
+      b.db_out = last_only ? db_out : db_out + f0 * p->n; b.floor = p->floor; b.mode = p->mode;
+      b.blk_b = (double*)p->scan_scratch; b.blk_start = b.blk_b + (size_t)nblk * w;
+      b.blk_a = b.blk_start + (size_t)nblk * w;
+      b.blk_max = (float*)(b.blk_a + nblk); b.blk_min = b.blk_max + (size_t)nblk * w;
+      const dim3 g2((unsigned)fin_grid, (unsigned)nblk);
+      if (averaging) {
+        scan_block_affine_kernel<<<g2, 256, 0, p->stream>>>(b);
+        count_launch();
+        scan_chain_kernel<<<fin_grid, 256, 0, p->stream>>>(b, nblk);
+        count_launch();
+      }
+      scan_block_emit_kernel<<<g2, 256, 0, p->stream>>>(b);
+      count_launch();
+      if (max_hold || min_hold) {
+        scan_holds_kernel<<<fin_grid, 256, 0, p->stream>>>(b, nblk);
+        count_launch();
+      }
+      trace_flags_after_scan_kernel<<<1, 256, 0, p->stream>>>(flags, nullptr, nf, avg_mode, avg_n, max_hold != nullptr,
+                                                            min_hold != nullptr, f0 == 0);
+      count_launch();
+      CK(cudaGetLastError());
+      continue;
+    }
     TraceScanDevArgs a;
     a.lin = lin; a.skip = with_dc ? silent_out + f0 : nullptr;
     a.n_frames = nf; a.width = p->n; a.avg_mode = avg_mode; a.avg_n = avg_n; a.flags = flags;

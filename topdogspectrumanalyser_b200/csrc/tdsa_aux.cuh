@@ -418,6 +418,14 @@ __device__ __forceinline__ double stitch_y(const StitchArgs& a, int64_t sorted_i
   return (double)a.rows[(int64_t)a.order[rr] * a.k + i];
 }
 
+// same values as stitch_x / stitch_y for sample i of sorted row rr, without the 64-bit division by k
+__device__ __forceinline__ double stitch_x_ri(const StitchArgs& a, int64_t rr, int64_t i, double bw) {
+  return __dadd_rn(__dadd_rn(a.lo[a.order[rr]], a.half_bw), __dmul_rn((double)i, bw));
+}
+__device__ __forceinline__ double stitch_y_ri(const StitchArgs& a, int64_t rr, int64_t i) {
+  return (double)a.rows[(int64_t)a.order[rr] * a.k + i];
+}
+
 __global__ void __launch_bounds__(256) stitch_interp_kernel(const StitchArgs a) {
   const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t cnt = a.count < 0 ? a.m : a.count;
@@ -430,48 +438,60 @@ __global__ void __launch_bounds__(256) stitch_interp_kernel(const StitchArgs a) 
   const double bw = a.bw;
   const int64_t total = a.n_rows * a.k;
   // np.interp: left/right clamp, then j = largest index with xp[j] <= x
-  const double x_first = stitch_x(a, 0, bw), x_last = stitch_x(a, total - 1, bw);
-  if (xv < x_first) { a.out[gi] = stitch_y(a, 0); return; }        // default left = fp[0]
-  if (xv > x_last) { a.out[gi] = stitch_y(a, total - 1); return; } // default right = fp[-1]
-  // j = largest index with x[j] <= xv.  Two levels: the row whose first sample is the last one <= xv (binary search
-  // over rows), then the sample inside it from the spacing, corrected with the exact comparisons np.interp makes.
-  int64_t j;
-  {
-    // hackrf_sweep's rows tile the span uniformly, so the row follows from the spacing; a few exact comparisons settle
-    // it, and anything irregular falls back to the binary search over rows
-    int64_t rlo = (int64_t)floor((xv - x_first) * a.inv_row);
-    rlo = rlo < 0 ? 0 : (rlo > a.n_rows - 1 ? a.n_rows - 1 : rlo);
-    int steps = 0;
-    while (steps < 4 && rlo < a.n_rows - 1 && stitch_x(a, (rlo + 1) * a.k, bw) <= xv) { ++rlo; ++steps; }
-    while (steps < 4 && rlo > 0 && stitch_x(a, rlo * a.k, bw) > xv) { --rlo; ++steps; }
-    if (steps >= 4) {
-      rlo = 0;
-      int64_t rhi = a.n_rows - 1;                    // x_first(0) <= xv (checked above)
-      while (rlo < rhi) {
-        const int64_t mid = (rlo + rhi + 1) >> 1;
-        if (stitch_x(a, mid * a.k, bw) <= xv) rlo = mid; else rhi = mid - 1;
-      }
+  const double x_first = stitch_x_ri(a, 0, 0, bw), x_last = stitch_x_ri(a, a.n_rows - 1, a.k - 1, bw);
+  if (xv < x_first) { a.out[gi] = stitch_y_ri(a, 0, 0); return; }                         // default left = fp[0]
+  if (xv > x_last) { a.out[gi] = stitch_y_ri(a, a.n_rows - 1, a.k - 1); return; }         // default right = fp[-1]
+  // j = (row rlo, sample i) = largest index with x[j] <= xv.  hackrf_sweep's rows tile the span uniformly, so the row
+  // and the sample follow from the spacing; exact comparisons (the ones np.interp's search makes) settle both, and
+  // anything irregular falls back to binary searches.  Indices stay (row, sample) pairs: a 64-bit division by k per
+  // coordinate evaluation used to be most of this kernel's time.
+  int64_t rlo = (int64_t)floor((xv - x_first) * a.inv_row);
+  rlo = rlo < 0 ? 0 : (rlo > a.n_rows - 1 ? a.n_rows - 1 : rlo);
+  int steps = 0;
+  while (steps < 4 && rlo < a.n_rows - 1 && stitch_x_ri(a, rlo + 1, 0, bw) <= xv) { ++rlo; ++steps; }
+  while (steps < 4 && rlo > 0 && stitch_x_ri(a, rlo, 0, bw) > xv) { --rlo; ++steps; }
+  if (steps >= 4) {
+    rlo = 0;
+    int64_t rhi = a.n_rows - 1;                      // x_first(0) <= xv (checked above)
+    while (rlo < rhi) {
+      const int64_t mid = (rlo + rhi + 1) >> 1;
+      if (stitch_x_ri(a, mid, 0, bw) <= xv) rlo = mid; else rhi = mid - 1;
     }
-    const double x0 = stitch_x(a, rlo * a.k, bw);
-    int64_t i = (int64_t)floor((xv - x0) * a.inv_bw);
-    i = i < 0 ? 0 : (i > a.k - 1 ? a.k - 1 : i);
-    while (i < a.k - 1 && stitch_x(a, rlo * a.k + i + 1, bw) <= xv) ++i;
-    while (i > 0 && stitch_x(a, rlo * a.k + i, bw) > xv) --i;
-    j = rlo * a.k + i;
   }
+  const double x0 = stitch_x_ri(a, rlo, 0, bw);
+  int64_t i = (int64_t)floor((xv - x0) * a.inv_bw);
+  i = i < 0 ? 0 : (i > a.k - 1 ? a.k - 1 : i);
+  while (i < a.k - 1 && stitch_x_ri(a, rlo, i + 1, bw) <= xv) ++i;
+  while (i > 0 && stitch_x_ri(a, rlo, i, bw) > xv) --i;
+  // successor of (rlo, i) in sorted order
+  int64_t r1 = rlo, i1 = i + 1;
+  if (i1 == a.k) { r1 = rlo + 1; i1 = 0; }
+  const bool is_last = r1 >= a.n_rows;
+  double xj = stitch_x_ri(a, rlo, i, bw);
   // overlapping rows break the ordering the shortcut relies on: verify, and fall back to the search over all samples
-  if (!(stitch_x(a, j, bw) <= xv) || (j < total - 1 && stitch_x(a, j + 1, bw) <= xv)) {
+  if (!(xj <= xv) || (!is_last && stitch_x_ri(a, r1, i1, bw) <= xv)) {
     int64_t lo_i = 0, hi_i = total - 1;     // invariant: x[lo_i] <= xv, and (hi_i == total-1 or x[hi_i] > xv)
     while (hi_i - lo_i > 1) {
       const int64_t mid = (lo_i + hi_i) >> 1;
       if (stitch_x(a, mid, bw) <= xv) lo_i = mid; else hi_i = mid;
     }
-    j = lo_i;
+    int64_t j = lo_i;
     if (stitch_x(a, hi_i, bw) <= xv) j = hi_i;
+    const double xs = stitch_x(a, j, bw), ys = stitch_y(a, j);
+    if (j == total - 1 || xs == xv) { a.out[gi] = ys; return; }
+    const double xs1 = stitch_x(a, j + 1, bw), ys1 = stitch_y(a, j + 1);
+    const double sl = __ddiv_rn(__dsub_rn(ys1, ys), __dsub_rn(xs1, xs));
+    double rs = __dadd_rn(__dmul_rn(sl, __dsub_rn(xv, xs)), ys);
+    if (isnan(rs)) {
+      rs = __dadd_rn(__dmul_rn(sl, __dsub_rn(xv, xs1)), ys1);
+      if (isnan(rs) && ys == ys1) rs = ys;
+    }
+    a.out[gi] = rs;
+    return;
   }
-  const double xj = stitch_x(a, j, bw), yj = stitch_y(a, j);
-  if (j == total - 1 || xj == xv) { a.out[gi] = yj; return; }
-  const double xj1 = stitch_x(a, j + 1, bw), yj1 = stitch_y(a, j + 1);
+  const double yj = stitch_y_ri(a, rlo, i);
+  if (is_last || xj == xv) { a.out[gi] = yj; return; }
+  const double xj1 = stitch_x_ri(a, r1, i1, bw), yj1 = stitch_y_ri(a, r1, i1);
   const double slope = __ddiv_rn(__dsub_rn(yj1, yj), __dsub_rn(xj1, xj));
   double res = __dadd_rn(__dmul_rn(slope, __dsub_rn(xv, xj)), yj);
   if (isnan(res)) {

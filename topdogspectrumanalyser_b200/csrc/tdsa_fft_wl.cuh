@@ -137,6 +137,13 @@ template <typename T> __device__ __forceinline__ T w32_msin(int j) {   // imagin
   return (T)s[j];
 }
 
+// TDSA_WL_EARLY = 1: the stage is refilled as soon as every warp has reported its staged reads done (one
+// mbarrier.arrive per warp; thread 0 polls without blocking after its own pass A and pass B, and waits after the Y
+// barrier at the latest) instead of always after the Y barrier; the frame is claimed at the top of the iteration.
+#ifndef TDSA_WL_EARLY
+#define TDSA_WL_EARLY 0
+#endif
+
 template <typename T, typename Epi, int TWMODE, int NSTAGE, bool HAS_DC, int MIN_CTAS, bool TWB_BASE, int NB, int ACC>
 __global__ void __launch_bounds__(256 * NB, MIN_CTAS)
 fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, const T* __restrict__ wperm, WlSched sched,
@@ -170,7 +177,7 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
 #pragma unroll
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(ctrl_u32 + 8 * s, 1);
-      if constexpr (NB > 1) mbar_init(ctrl_u32 + 32 + 8 * s, 8 * NB);     // one arrival per warp
+      if constexpr (NB > 1 || TDSA_WL_EARLY) mbar_init(ctrl_u32 + 32 + 8 * s, 8 * NB);     // one arrival per warp
     }
     fence_mbar_init();
   }
@@ -266,6 +273,17 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
 #pragma unroll
       for (int j = 0; j < NWIN; ++j) win[j] = wperm[j * TH + tid];
     }
+    int fnext = 0;
+    bool refilled = false;
+    auto try_refill = [&](bool must) {                       // thread 0 only
+      if (refilled) return;
+      const uint32_t bar = ctrl_u32 + 32 + 8 * stg, par = (uint32_t)((it / NSTAGE) & 1);
+      if (must) mbar_wait(bar, par); else if (!mbar_try_wait(bar, par)) return;
+      fence_proxy_async();
+      issue_stage(stg, fnext);
+      refilled = true;
+    };
+    if constexpr (TDSA_WL_EARLY && NB == 1) { if (tid == 0) fnext = next_frame(); }
     TDSA_STAMP(0);
     mbar_wait(ctrl_u32 + 8 * stg, (uint32_t)((it / NSTAGE) & 1));
     const int f = slot[stg];                                 // written by thread 0 before it armed / completed the barrier
@@ -319,11 +337,11 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
 #pragma unroll
     for (int q = 0; q < 16; ++q) reg[c + 17 * q] = mk<T>(re[q], im[q]);
     __syncwarp();
-    if constexpr (NB > 1) {                                  // this warp's samples of the stage are consumed
+    if constexpr (NB > 1 || TDSA_WL_EARLY) {                 // this warp's samples of the stage are consumed
       if (l == 0) mbar_arrive(ctrl_u32 + 32 + 8 * stg);
     }
-    int fnext = 0;
-    if (tid == 0) fnext = next_frame();                      // consumed after the barrier below
+    if constexpr (TDSA_WL_EARLY && NB == 1) { if (tid == 0) try_refill(false); }
+    else { if (tid == 0) fnext = next_frame(); }             // consumed after the barrier below
     TDSA_STAMP(3);
     // ---- pass B: thread ka = c reads A_j[ka] (j = 0..15), pre-twiddle [j][ka], radix 16 over j --------------
     {
@@ -345,6 +363,7 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       dft16_pretw<T>(re, im, wr, wi);
     }
     TDSA_STAMP(4);
+    if constexpr (TDSA_WL_EARLY && NB == 1) { if (tid == 0) try_refill(false); }
     // Y_r[kk], kk = c + 16 kb, at position kk + (kk >> 4) = c + 17 kb of the team region
 #pragma unroll
     for (int q = 0; q < 16; ++q) reg[c + 17 * q] = mk<T>(re[q], im[q]);
@@ -355,9 +374,13 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     // claimed at the top of the iteration) instead of thread 0 after this barrier was slower: 78.0 -> 83.9 us (f32),
     // 135.2 -> 139.4 us (f64) at N = 4096, 206.8 -> 219.1 us (f64) at N = 8192.
     if (tid == 0) {
-      if constexpr (NB > 1) mbar_wait(ctrl_u32 + 32 + 8 * stg, (uint32_t)((it / NSTAGE) & 1));   // the other engine too
-      fence_proxy_async();
-      issue_stage(stg, fnext);
+      if constexpr (TDSA_WL_EARLY && NB == 1) {
+        try_refill(true);
+      } else {
+        if constexpr (NB > 1) mbar_wait(ctrl_u32 + 32 + 8 * stg, (uint32_t)((it / NSTAGE) & 1));   // the other engine too
+        fence_proxy_async();
+        issue_stage(stg, fnext);
+      }
     }
     // ---- last pass: thread kk = te reads Y_j[kk], pre-twiddle [j][kk], radix 16 over j ----------------------
     {

@@ -276,6 +276,136 @@ __global__ void __launch_bounds__(256) trace_scan_dev_kernel(const TraceScanDevA
   if (a.last_row && any) a.last_row[k] = last_db;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same scan, parallel over frames as well (no skip flags): the averager's recurrence is affine in the buffer, so a
+// block of kScanBlock frames maps its start state s to A s + B with A common to all bins.
+//   1. scan_block_affine_kernel: (bin, block) -> B (and A once per block)            [reads the rows]
+//   2. scan_chain_kernel:        bin -> state at the start of every block, final state
+//   3. scan_block_emit_kernel:   (bin, block) -> the block's dB rows in the reference's operation order from the
+//                                known start state, block max / min of the dB values   [reads the rows again, from L2]
+//   4. scan_holds_kernel:        bin -> max / min hold from the block extrema
+// One thread per bin walking 1024 frames is latency bound (175 us per 32 MB chunk on 16 SMs); this is ~6 x faster.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kScanBlock = 32;
+
+struct TraceBlockArgs {
+  const double* lin;       // [F][W]
+  int64_t n_frames, width;
+  int avg_mode, avg_n;
+  const int32_t* flags;
+  double* avg_state;
+  float* max_hold;
+  float* min_hold;
+  float* last_row;
+  int last_only;
+  float* db_out;
+  double floor;
+  int mode;
+  double* blk_b;           // [nblk][W]
+  double* blk_a;           // [nblk]
+  double* blk_start;       // [nblk][W]
+  float* blk_max;          // [nblk][W]  (-inf: no value)
+  float* blk_min;          // [nblk][W]  (+inf: no value)
+};
+
+// averager count BEFORE frame t of the call (every frame live): 0 means "the buffer is empty, this frame sets it"
+__device__ __forceinline__ int count_before(int avg_mode, int avg_n, int count0, int64_t t) {
+  if (avg_mode == 2) { const int64_t c = (int64_t)count0 + t; return (int)(c < avg_n ? c : avg_n); }
+  return (count0 > 0 || t > 0) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) scan_block_affine_kernel(const TraceBlockArgs a) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.width) return;
+  const int64_t t0 = (int64_t)blockIdx.y * kScanBlock, t1 = min(t0 + kScanBlock, a.n_frames);
+  const int count0 = a.flags[kFlagCount];
+  const double alpha = 1.0 / (double)a.avg_n;
+  double A = 1.0, B = 0.0;
+  double pre[kScanBlock];
+#pragma unroll
+  for (int u = 0; u < kScanBlock; ++u) pre[u] = (t0 + u < t1) ? a.lin[(t0 + u) * a.width + k] : 0.0;
+#pragma unroll
+  for (int u = 0; u < kScanBlock; ++u) {
+    const int64_t t = t0 + u;
+    if (t >= t1) break;
+    const int c = count_before(a.avg_mode, a.avg_n, count0, t);
+    if (c == 0) { A = 0.0; B = pre[u]; }
+    else if (a.avg_mode == 1) { A *= (1.0 - alpha); B = __dadd_rn(__dmul_rn(B, 1.0 - alpha), __dmul_rn(alpha, pre[u])); }
+    else {
+      const double inv = 1.0 / (double)(c < a.avg_n ? c + 1 : a.avg_n);
+      A *= (1.0 - inv); B = __fma_rn(B, 1.0 - inv, pre[u] * inv);
+    }
+  }
+  a.blk_b[(int64_t)blockIdx.y * a.width + k] = B;
+  if (k == 0) a.blk_a[blockIdx.y] = A;
+}
+
+__global__ void __launch_bounds__(256) scan_chain_kernel(const TraceBlockArgs a, int nblk) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.width) return;
+  double s = a.flags[kFlagCount] > 0 ? a.avg_state[k] : 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    a.blk_start[(int64_t)b * a.width + k] = s;
+    s = __fma_rn(a.blk_a[b], s, a.blk_b[(int64_t)b * a.width + k]);
+  }
+  a.avg_state[k] = s;
+}
+
+__global__ void __launch_bounds__(256) scan_block_emit_kernel(const TraceBlockArgs a) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.width) return;
+  const int64_t t0 = (int64_t)blockIdx.y * kScanBlock, t1 = min(t0 + kScanBlock, a.n_frames);
+  const bool averaging = a.avg_mode != 0 && a.avg_n > 1;
+  const int count0 = averaging ? a.flags[kFlagCount] : 0;
+  const double alpha = 1.0 / (double)a.avg_n;
+  double buf = averaging ? a.blk_start[(int64_t)blockIdx.y * a.width + k] : 0.0;
+  EpiParams ep;
+  ep.db_out = nullptr; ep.lin_out = nullptr; ep.scale = 1.0; ep.floor = a.floor; ep.mode = a.mode;
+  float mx = -INFINITY, mn = INFINITY, db = 0.0f;
+  double pre[kScanBlock];
+#pragma unroll
+  for (int u = 0; u < kScanBlock; ++u) pre[u] = (t0 + u < t1) ? a.lin[(t0 + u) * a.width + k] : 0.0;
+#pragma unroll
+  for (int u = 0; u < kScanBlock; ++u) {
+    const int64_t t = t0 + u;
+    if (t >= t1) break;
+    double v = pre[u];
+    if (averaging) {
+      const int c = count_before(a.avg_mode, a.avg_n, count0, t);
+      if (c == 0) buf = v;
+      else if (a.avg_mode == 1) { buf = __dmul_rn(buf, 1.0 - alpha); buf = __dadd_rn(buf, __dmul_rn(alpha, v)); }
+      else buf = __dadd_rn(buf, __ddiv_rn(__dsub_rn(v, buf), (double)(c < a.avg_n ? c + 1 : a.avg_n)));
+      v = buf;
+    }
+    db = to_db<double>(v, ep);
+    if (!a.last_only) a.db_out[t * a.width + k] = db;
+    mx = fmaxf(mx, db); mn = fminf(mn, db);              // NaN-ignoring, like np.fmax / np.fmin
+  }
+  if (t1 == a.n_frames) {                                // the block that holds the call's last frame
+    if (a.last_only) a.db_out[k] = db;
+    if (a.last_row) a.last_row[k] = db;
+  }
+  if (a.max_hold) a.blk_max[(int64_t)blockIdx.y * a.width + k] = mx;
+  if (a.min_hold) a.blk_min[(int64_t)blockIdx.y * a.width + k] = mn;
+}
+
+__global__ void __launch_bounds__(256) scan_holds_kernel(const TraceBlockArgs a, int nblk) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.width) return;
+  if (a.max_hold) {
+    float m = -INFINITY;
+    for (int b = 0; b < nblk; ++b) m = fmaxf(m, a.blk_max[(int64_t)b * a.width + k]);
+    if (a.flags[kFlagMaxValid] != 0) { if (m != -INFINITY) a.max_hold[k] = fmaxf(a.max_hold[k], m); }
+    else a.max_hold[k] = m == -INFINITY ? -500.0f : m;   // _nan_safe on the initialising frame
+  }
+  if (a.min_hold) {
+    float m = INFINITY;
+    for (int b = 0; b < nblk; ++b) m = fminf(m, a.blk_min[(int64_t)b * a.width + k]);
+    if (a.flags[kFlagMinValid] != 0) { if (m != INFINITY) a.min_hold[k] = fminf(a.min_hold[k], m); }
+    else a.min_hold[k] = m == INFINITY ? 500.0f : m;
+  }
+}
+
 // after a scan: fold the number of live (not skipped) frames into the flag block
 __global__ void trace_flags_after_scan_kernel(int32_t* __restrict__ flags, const int32_t* __restrict__ skip, int64_t n_frames,
                                               int avg_mode, int avg_n, int has_max, int has_min, int first_chunk) {

@@ -171,6 +171,31 @@ out["rtl_resumed_same_object"] = mw.current_source is src and src.running
 out["hackrf_closed"] = ("hackrf_close",) in LOG
 mgr._stop_current_source("rtl_sweep")
 out["rtl_closed_for_sweep"] = ("close",) in LOG
+# optional third replacement: the HackRF sweep source computed from raw IQ (no external hackrf_sweep binary)
+from topdogspectrumanalyser_b200.datasources import b200_sweep
+if no_gpu:
+    b200_sweep.B200SweepDataSource._ensure_sweep = lambda self: None
+    b200_sweep.B200SweepDataSource.process_sweep = lambda self, iq: None
+b200_samples.install_backend(sweep=True)
+del LOG[:]
+mgr.set_source("hackrf_sweep")
+sw = mw.current_source
+out["sweep_class"] = type(sw).__name__
+out["sweep_status"] = mw.status_label.text
+out["sweep_running"] = bool(sw is not None and sw.is_running)
+out["sweep_gains"] = [sw.lna_gain, sw.vga_gain] if sw is not None else None
+out["sweep_grid_len"] = len(sw.frequency_grid) if sw is not None else None
+out["sweep_isinstance_ref"] = isinstance(sw, sm_mod.SweepDataSource)
+import time as _t
+_t.sleep(0.3)
+if not no_gpu and sw is not None:
+    t0 = _t.time()
+    while sw.sweep_rate is None and _t.time() - t0 < 20:
+        _t.sleep(0.05)
+    d = sw.get_data()
+    out["sweep_data_finite"] = bool(len(d) == len(sw.frequency_grid) and np.isfinite(d).all())
+mgr._stop_current_source("rtl_samples")
+out["sweep_stopped"] = bool(sw is not None and not sw.is_running) and ("hackrf_close",) in LOG
 b200_samples.uninstall_backend()
 out["uninstalled"] = SM.SOURCE_CLASSES["rtl_samples"].__name__
 print("RESULT " + json.dumps(out))

@@ -354,3 +354,40 @@ def test_snap_to_peak_matches_scipy_find_peaks(dev):
         bins = np.linspace(88e6, 108e6, n)
         f, idx, fb = snap_to_peak(bins, torch.from_numpy(x).to(dev), thr, exc, 3)
         assert idx == want and f == bins[want] and fb == (len(peaks) == 0), (trial, n, idx, want)
+
+
+def test_iq_in_sweep_source(dev, parity_log):
+    """B200SweepDataSource: the job of the external hackrf_sweep binary done from raw IQ. Rows = kernel 1 per frame +
+    linear mean (float64 oracle, 1e-4 dB); the stitched grid is what HackRFSweepDataSource._parse builds from those rows
+    (argsort + np.interp onto linspace(start, stop, int(span / bin_size))), bit for bit."""
+    from topdogspectrumanalyser_b200.datasources import B200SweepDataSource, SweepDataSource, SyntheticTunerFeed
+    start, stop, bin_size = 2400e6, 2500e6, 30000
+    feed = SyntheticTunerFeed(20e6, carriers_hz=[2.412e9, 2.437e9, 2.4835e9], amp=0.7, seed=21)
+    src = B200SweepDataSource(start, stop, bin_size, feed=feed, frames=4)
+    assert isinstance(src, SweepDataSource) and src.n_fft == 1024 and src.n_bands == 5
+    assert np.isnan(src.get_data()).all() and src.get_number_of_points() == 3333       # nothing swept yet
+    iq = src.acquire_sweep()
+    grid = src.process_sweep(iq)
+    w = O.make_window("hanning", src.n_fft)
+    rows = np.stack([10 * np.log10(O.linear_power_batch(b, w).mean(axis=0) + O.POWER_LOG_FLOOR) for b in iq])
+    got_rows = src._plan.group_avg_db(src._dev_iq).cpu().numpy()
+    err = float(np.abs(got_rows - rows).max())
+    parity_log("iq_sweep_rows", err, tol=TOL_DB)
+    assert err <= TOL_DB
+    los = [start + 20e6 * i for i in range(5)]
+    want = O.stitch_rows(got_rows, los, [lo + 20e6 for lo in los], O.sweep_grid(int(start), int(stop), bin_size))
+    np.testing.assert_array_equal(grid, want)
+    np.testing.assert_array_equal(src.get_data(), want)
+    assert src.get_data() is not src.get_data()                                         # a copy per call, like the reference
+    # the three carriers stand out where they should
+    for f in (2.412e9, 2.437e9, 2.4835e9):
+        k = int(np.argmin(np.abs(src.frequency_grid - f)))
+        assert grid[max(k - 3, 0):k + 4].max() > np.nanmedian(grid) + 20
+    # background thread: start / a few sweeps / stop
+    src.start()
+    import time
+    t0 = time.time()
+    while src.sweep_rate is None and time.time() - t0 < 20:
+        time.sleep(0.05)
+    src.stop()
+    assert src.sweep_rate is not None and not src.is_running and not np.isnan(src.get_data()).any()

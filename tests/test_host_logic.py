@@ -143,3 +143,23 @@ def test_hackrf_chunk_feed_consume_policy(golden):
         feed.put(np.full(8, k, dtype=np.complex64))
     assert feed.stats["queue_overflows"] == 2 and feed.stats["samples_dropped"] == 16
     assert feed.read_samples(4)[0].real == 5.0
+
+
+def test_sweep_source_interface_without_gpu():
+    """The IQ-in sweep source builds the reference's grid (hackrf_sweep.py:32-40) and answers get_data without a device."""
+    from topdogspectrumanalyser_b200.datasources import B200SweepDataSource, SweepDataSource, SyntheticTunerFeed
+    src = B200SweepDataSource(88e6, 108e6, 30000, feed=SyntheticTunerFeed(20e6))
+    assert isinstance(src, SweepDataSource)
+    n = int((108e6 - 88e6) / 30000)
+    np.testing.assert_array_equal(src.frequency_grid, np.linspace(88e6, 108e6, n))
+    d = src.get_data()
+    assert d.shape == (n,) and np.isnan(d).all() and src.get_number_of_points() == n
+    assert src.n_bands == 1 and src.n_fft == 1024 and (src.lna_gain, src.vga_gain, src.amp_enabled) == (20, 20, True)
+    src.set_gains(lna_gain=24)
+    assert src.lna_gain == 24
+    for name in ("start", "stop", "get_data", "get_number_of_points", "set_gains", "set_amplifier"):
+        assert callable(getattr(src, name))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            src.start()
+        assert not src.is_running

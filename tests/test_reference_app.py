@@ -44,6 +44,10 @@ def _check_common(o):
     assert o["hackrf_thread_alive"] and o["hackrf_raw_len"] == 1024
     assert o["rtl_resumed_same_object"] and o["hackrf_closed"] and o["rtl_closed_for_sweep"]
     assert o["uninstalled"] == "RtlSamplesDataSource"
+    # the IQ-in sweep source behind "hackrf_sweep": constructed by _initialise_hackrf_sweep(start, stop, bin_size=30000)
+    assert o["sweep_class"] == "B200SweepDataSource", o["sweep_status"]
+    assert o["sweep_running"] and o["sweep_isinstance_ref"] and o["sweep_gains"] == [24, 30]
+    assert o["sweep_grid_len"] > 0 and o["sweep_stopped"]
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU variant (plan stubbed); the gpu variant runs the real thing")
@@ -56,3 +60,4 @@ def test_set_source_constructs_b200_backend_gpu():
     o = _drive()
     _check_common(o)
     assert o["frame_shape"] == [1024] and o["frame_finite"] and o["hackrf_frame_dtype"] == "float32"
+    assert o["sweep_data_finite"]

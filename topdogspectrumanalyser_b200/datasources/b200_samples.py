@@ -465,7 +465,7 @@ class B200HackrfSamples(B200SampleDataSource):
 BACKEND_ENV = "TDSA_BACKEND"
 
 
-def install_backend(force: bool = False):
+def install_backend(force: bool = False, sweep: Optional[bool] = None):
     """Make the reference application use the B200 backend for its two IQ sample sources.
 
     ``SourceManager.set_source`` validates the id against ``SOURCE_CLASSES`` and then constructs through a fixed
@@ -490,6 +490,13 @@ def install_backend(force: bool = False):
         RefBase.register(B200SampleDataSource)
     SourceManager.SOURCE_CLASSES["rtl_samples"] = B200RtlSamples
     SourceManager.SOURCE_CLASSES["hackrf_samples"] = B200HackrfSamples
+    # optional: the HackRF sweep source computed from raw IQ instead of the external hackrf_sweep binary
+    # (TDSA_BACKEND_SWEEP=b200 or sweep=True); _initialise_hackrf_sweep constructs cls(start, stop, bin_size=...)
+    if sweep or (sweep is None and os.environ.get("TDSA_BACKEND_SWEEP", "").lower() == "b200"):
+        from datasources.hackrf_sweep import HackRFSweepDataSource            # type: ignore
+        from .b200_sweep import B200SweepDataSource
+        HackRFSweepDataSource.register(B200SweepDataSource) if hasattr(HackRFSweepDataSource, "register") else None
+        SourceManager.SOURCE_CLASSES["hackrf_sweep"] = B200SweepDataSource
     return SourceManager
 
 
@@ -498,6 +505,8 @@ def uninstall_backend():
     from core.source_manager import SourceManager              # type: ignore
     from datasources.hackrf_samples import HackrfSamplesDataSource   # type: ignore
     from datasources.rtl_samples import RtlSamplesDataSource   # type: ignore
+    from datasources.hackrf_sweep import HackRFSweepDataSource   # type: ignore
     SourceManager.SOURCE_CLASSES["rtl_samples"] = RtlSamplesDataSource
     SourceManager.SOURCE_CLASSES["hackrf_samples"] = HackrfSamplesDataSource
+    SourceManager.SOURCE_CLASSES["hackrf_sweep"] = HackRFSweepDataSource
     return SourceManager

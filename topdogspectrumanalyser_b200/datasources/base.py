@@ -15,10 +15,31 @@ import numpy as np
 
 try:                                     # running inside the reference app
     from datasources.base import SampleDataSource as _RefSampleDataSource   # type: ignore
+    from datasources.base import SweepDataSource as _RefSweepDataSource     # type: ignore
     IN_REFERENCE_APP = True
 except Exception:                        # stand-alone
     _RefSampleDataSource = None
+    _RefSweepDataSource = None
     IN_REFERENCE_APP = False
+
+
+if _RefSweepDataSource is not None:
+    SweepDataSource = _RefSweepDataSource
+else:
+    class SweepDataSource(ABC):
+        """Mirror of datasources/base.py:15-39."""
+
+        @abstractmethod
+        def start(self, frequency=None):
+            ...
+
+        @abstractmethod
+        def stop(self):
+            ...
+
+        @abstractmethod
+        def get_data(self):
+            ...
 
 
 class AveragerSettings:

@@ -143,6 +143,14 @@ template <typename T> __device__ __forceinline__ T w32_msin(int j) {   // imagin
 #ifndef TDSA_WL_EARLY
 #define TDSA_WL_EARLY 0
 #endif
+// TDSA_WL_SPLIT_B2 = 1 (one engine only): the second engine-wide barrier of a frame ("every warp has read its Y values,
+// the regions may be overwritten") becomes a split barrier: one mbarrier.arrive per warp right after the loads, the wait
+// right before the next frame's team stores, i.e. a whole last pass + epilogue + staged read + pass A later.
+// Measured (round 2, 8192 frames): 135.2 -> 131.1 us in float64, 77.8 -> 77.8 us (best 77.6 -> 75.8) in float32; on.
+// (Together with TDSA_WL_EARLY it is pathological: 184 us.)
+#ifndef TDSA_WL_SPLIT_B2
+#define TDSA_WL_SPLIT_B2 1
+#endif
 
 template <typename T, typename Epi, int TWMODE, int NSTAGE, bool HAS_DC, int MIN_CTAS, bool TWB_BASE, int NB, int ACC>
 __global__ void __launch_bounds__(256 * NB, MIN_CTAS)
@@ -179,6 +187,7 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       mbar_init(ctrl_u32 + 8 * s, 1);
       if constexpr (NB > 1 || TDSA_WL_EARLY) mbar_init(ctrl_u32 + 32 + 8 * s, 8 * NB);     // one arrival per warp
     }
+    if constexpr (TDSA_WL_SPLIT_B2 && NB == 1) mbar_init(ctrl_u32 + 24, 8);     // "regions free": one arrival per warp
     fence_mbar_init();
   }
   for (int i = te; i < W::TW_SMEM; i += 256) tws[i] = twe[i];
@@ -334,6 +343,9 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     }
     TDSA_STAMP(2);
     // ---- team-local 16x16 transpose: A_c[ka] at position c + 16 ka, row pitch 17 ---------------------------
+    if constexpr (TDSA_WL_SPLIT_B2 && NB == 1) {
+      if (it > 0) mbar_wait(ctrl_u32 + 24, (uint32_t)((it - 1) & 1));        // every warp has read the previous frame's Y
+    }
 #pragma unroll
     for (int q = 0; q < 16; ++q) reg[c + 17 * q] = mk<T>(re[q], im[q]);
     __syncwarp();
@@ -388,7 +400,12 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
 #pragma unroll
       for (int j = 0; j < 16; ++j) { const CT x = col[j * REGION]; re[j] = x.x; im[j] = x.y; }
     }
-    engine_sync();                                           // regions may be overwritten by the next frame's pass A
+    if constexpr (TDSA_WL_SPLIT_B2 && NB == 1) {
+      __syncwarp();                                          // the warp's loads are ordered before its one arrival
+      if (l == 0) mbar_arrive(ctrl_u32 + 24);
+    } else {
+      engine_sync();                                         // regions may be overwritten by the next frame's pass A
+    }
     TDSA_STAMP(7);
     {
       T wr[16], wi[16];

@@ -90,15 +90,22 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 
 // ---- tensor memory as per-thread scratch: 32x32b shape = lane <-> thread, consecutive columns <-> registers ------
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, int cols) {
-  if (cols == 128) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_dst) : "memory");
-  else asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_dst) : "memory");
+template <int COLS> __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
+  static_assert(COLS == 32 || COLS == 64 || COLS == 128 || COLS == 256 || COLS == 512, "power of two >= 32");
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, int cols) {
-  if (cols == 128) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(taddr) : "memory");
-  else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(taddr) : "memory");
+template <int COLS> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -140,6 +147,31 @@ template <typename T> __device__ __forceinline__ T w32_msin(int j) {   // imagin
 // TDSA_WL_EARLY = 1: the stage is refilled as soon as every warp has reported its staged reads done (one
 // mbarrier.arrive per warp; thread 0 polls without blocking after its own pass A and pass B, and waits after the Y
 // barrier at the latest) instead of always after the Y barrier; the frame is claimed at the top of the iteration.
+// TDSA_WL_WIN_TMEM = 1 (float64, one engine): the thread's sixteen window values live in tensor memory (32 columns of
+// its lane) instead of being re-read from global memory through L1 for every frame (the register budget has no room
+// for them): 16 LDG.64 per thread and frame leave the LSU / L1 path, which is the tighter side of this kernel.
+#ifndef TDSA_WL_EPI_F32SQ
+#define TDSA_WL_EPI_F32SQ 0
+#endif
+// last-pass base twiddles held in registers: 6 (w^1..w^3, w^4, w^8, w^12; 24 registers in float64) or 2 (w^1, w^4; the
+// other four bases by multiplication every frame: 16 registers fewer, 16 DFMA more)
+#ifndef TDSA_WL_TWL_BASE2
+#define TDSA_WL_TWL_BASE2 0
+#endif
+#ifndef TDSA_WL_WIN_TMEM
+#define TDSA_WL_WIN_TMEM 0
+#endif
+// TDSA_WL_TWB_SMEM_BASE (float64): pass-B twiddles W256^(j c) from a few base values of the shared table plus complex
+// multiplies instead of fifteen LDS.128 per thread and frame.  Measured (8192 frames, on top of the split barrier):
+// 0: 132.1 us; 1 (six bases, nine multiplies): 129.0 us; 2 (w^1 and w^4 only, thirteen multiplies): 128.0 us.  The same
+// idea for the last pass' register-held bases (TDSA_WL_TWL_BASE2: 16 registers fewer) changes nothing (129.0 us), nor do
+// squaring in float32 after narrowing re / im (TDSA_WL_EPI_F32SQ: 130.5 us) or integer-pipe narrowing (129.1 us).
+// Tensor memory for the per-frame window values
+// (TDSA_WL_WIN_TMEM) measured slower (135.2 / 131.1 us without / with this option): the blocking tcgen05.wait::ld costs
+// more than sixteen L1-cached loads.
+#ifndef TDSA_WL_TWB_SMEM_BASE
+#define TDSA_WL_TWB_SMEM_BASE 2
+#endif
 #ifndef TDSA_WL_EARLY
 #define TDSA_WL_EARLY 0
 #endif
@@ -159,7 +191,13 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
   using W = WlPlan<T, NB>;
   using CT = typename CplxOf<T>::type;
   constexpr int N = W::N, TH = W::TH, REGION = W::REGION;
-  constexpr int kTmemCols = 64 * 2 * NB;                                   // 64 columns per warp, NB * 2 warps per lane quarter
+  // tensor memory per warp (one lane per thread): 64 accumulator columns (ACC) and / or 32 window columns (WIN_TMEM);
+  // 2 * NB warps share a lane quarter, each with its own column range
+  constexpr bool kWinTmem = TDSA_WL_WIN_TMEM && sizeof(T) == 8 && NB == 1 && TWMODE != 1;
+  constexpr int kTmemPerWarp = (ACC != 0 ? 64 : 0) + (kWinTmem ? 32 : 0);
+  constexpr int kTmemNeed = kTmemPerWarp * 2 * NB;
+  constexpr int kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
+  constexpr bool kUseTmem = kTmemPerWarp != 0;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t base_u32 = smem_u32(smem_raw);
   const uint32_t ctrl_u32 = base_u32 + (uint32_t)W::EX_BYTES;              // full[4] at +0, empty[4] at +32
@@ -192,8 +230,9 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
   }
   for (int i = te; i < W::TW_SMEM; i += 256) tws[i] = twe[i];
   uint32_t tacc = 0;                                        // TMEM address of this thread's 64 accumulator columns
-  if constexpr (ACC != 0) {
-    if ((tid >> 5) == 0) tmem_alloc(base_u32 + (uint32_t)W::EX_BYTES + 96, kTmemCols);
+  uint32_t twin = 0;                                        // TMEM address of this thread's 32 window columns
+  if constexpr (kUseTmem) {
+    if ((tid >> 5) == 0) tmem_alloc<kTmemCols>(base_u32 + (uint32_t)W::EX_BYTES + 96);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
 
@@ -210,6 +249,7 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
   } else {
 #pragma unroll
     for (int j = 1; j < 16; ++j) {
+      if (TDSA_WL_TWL_BASE2 && sizeof(T) == 8 && j != 1 && j != 4) continue;
       if (j < 4 || (j & 3) == 0) { const CT x = tw_last[j * 256 + te]; twlr[j] = x.x; twli[j] = x.y; }
     }
   }
@@ -251,9 +291,25 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     for (int s = 0; s < NSTAGE; ++s) issue_stage(s, next_frame());
   }
   __syncthreads();
-  if constexpr (ACC != 0) {
+  if constexpr (kUseTmem) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    tacc = *tmem_slot + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)((tid >> 7) * 64);
+    tacc = *tmem_slot + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)((tid >> 7) * kTmemPerWarp);
+    twin = tacc + (ACC != 0 ? 64 : 0);
+  }
+  if constexpr (kWinTmem) {                                  // park the window values of pass A in tensor memory
+    uint32_t u[16];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const double wv = (double)wperm[(8 * half + i) * TH + tid];
+        u[2 * i] = (uint32_t)__double2loint(wv); u[2 * i + 1] = (uint32_t)__double2hiint(wv);
+      }
+      tmem_st16(twin + 16 * half, u);
+    }
+    tmem_wait_st();
+  }
+  if constexpr (ACC != 0) {
     // state: columns [0, 32) sixteen float64 sums, [32, 48) sixteen float32 maxima, [48, 64) sixteen float32 minima
     uint32_t z[16];
 #pragma unroll
@@ -278,7 +334,13 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
 
   for (int it = 0;; ++it) {
     const int stg = it % NSTAGE;
-    if constexpr (TWMODE != 1) {                             // window values for pass A, re-read every frame (register budget)
+    uint32_t wraw[kWinTmem ? 32 : 1];
+    if constexpr (kWinTmem) {                                // issued here, waited for after the stage barrier
+      uint32_t (&lo16)[16] = *reinterpret_cast<uint32_t (*)[16]>(&wraw[0]);
+      uint32_t (&hi16)[16] = *reinterpret_cast<uint32_t (*)[16]>(&wraw[16]);
+      tmem_ld16_nowait(twin, lo16);
+      tmem_ld16_nowait(twin + 16, hi16);
+    } else if constexpr (TWMODE != 1) {                      // window values for pass A, re-read every frame (register budget)
 #pragma unroll
       for (int j = 0; j < NWIN; ++j) win[j] = wperm[j * TH + tid];
     }
@@ -304,6 +366,11 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     }
 #endif
     T re[16], im[16];
+    if constexpr (kWinTmem) {
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) win[j] = (T)__hiloint2double((int)wraw[2 * j + 1], (int)wraw[2 * j]);
+    }
     // ---- pass A: staged samples -> registers, window, radix 16 over j (samples r + 16 c + 256 j) ----------
     {
       T dcr = T(0), dci = T(0);
@@ -365,6 +432,25 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
           if (j < 4 || (j & 3) == 0) { wr[j] = twbr[j]; wi[j] = twbi[j]; }
           else { wr[j] = twbr[j & 3]; wi[j] = twbi[j & 3]; cmul<T>(wr[j], wi[j], twbr[j & ~3], twbi[j & ~3]); }
         }
+      } else if constexpr (TDSA_WL_TWB_SMEM_BASE && sizeof(T) == 8) {
+        // six base twiddles from the shared table, the other nine by one complex multiply each (9 LDS.128 fewer, 36 DFMA more)
+        if constexpr (TDSA_WL_TWB_SMEM_BASE == 2) {          // only w^1 and w^4 from the table, the other bases by squaring
+          { const CT x = tws[1 * 16 + c]; wr[1] = x.x; wi[1] = x.y; }
+          { const CT x = tws[4 * 16 + c]; wr[4] = x.x; wi[4] = x.y; }
+          wr[2] = wr[1]; wi[2] = wi[1]; cmul<T>(wr[2], wi[2], wr[1], wi[1]);
+          wr[3] = wr[2]; wi[3] = wi[2]; cmul<T>(wr[3], wi[3], wr[1], wi[1]);
+          wr[8] = wr[4]; wi[8] = wi[4]; cmul<T>(wr[8], wi[8], wr[4], wi[4]);
+          wr[12] = wr[8]; wi[12] = wi[8]; cmul<T>(wr[12], wi[12], wr[4], wi[4]);
+        } else {
+#pragma unroll
+          for (int j = 1; j < 16; ++j) {
+            if (j < 4 || (j & 3) == 0) { const CT x = tws[j * 16 + c]; wr[j] = x.x; wi[j] = x.y; }
+          }
+        }
+#pragma unroll
+        for (int j = 1; j < 16; ++j) {
+          if (!(j < 4 || (j & 3) == 0)) { wr[j] = wr[j & 3]; wi[j] = wi[j & 3]; cmul<T>(wr[j], wi[j], wr[j & ~3], wi[j & ~3]); }
+        }
       } else {
 #pragma unroll
         for (int j = 1; j < 16; ++j) { const CT x = tws[j * 16 + c]; wr[j] = x.x; wi[j] = x.y; }
@@ -411,11 +497,24 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       T wr[16], wi[16];
       wr[0] = T(1); wi[0] = T(0);
 #pragma unroll
-      for (int j = 1; j < 16; ++j) {
-        if constexpr (TWMODE == 1) { wr[j] = twlr[j]; wi[j] = twli[j]; }
-        else {
-          if (j < 4 || (j & 3) == 0) { wr[j] = twlr[j]; wi[j] = twli[j]; }
-          else { wr[j] = twlr[j & 3]; wi[j] = twli[j & 3]; cmul<T>(wr[j], wi[j], twlr[j & ~3], twli[j & ~3]); }
+      if constexpr (TWMODE != 1 && TDSA_WL_TWL_BASE2 && sizeof(T) == 8) {
+        wr[1] = twlr[1]; wi[1] = twli[1]; wr[4] = twlr[4]; wi[4] = twli[4];
+        wr[2] = wr[1]; wi[2] = wi[1]; cmul<T>(wr[2], wi[2], wr[1], wi[1]);
+        wr[3] = wr[2]; wi[3] = wi[2]; cmul<T>(wr[3], wi[3], wr[1], wi[1]);
+        wr[8] = wr[4]; wi[8] = wi[4]; cmul<T>(wr[8], wi[8], wr[4], wi[4]);
+        wr[12] = wr[8]; wi[12] = wi[8]; cmul<T>(wr[12], wi[12], wr[4], wi[4]);
+#pragma unroll
+        for (int j = 5; j < 16; ++j) {
+          if ((j & 3) != 0) { wr[j] = wr[j & 3]; wi[j] = wi[j & 3]; cmul<T>(wr[j], wi[j], wr[j & ~3], wi[j & ~3]); }
+        }
+      } else {
+#pragma unroll
+        for (int j = 1; j < 16; ++j) {
+          if constexpr (TWMODE == 1) { wr[j] = twlr[j]; wi[j] = twli[j]; }
+          else {
+            if (j < 4 || (j & 3) == 0) { wr[j] = twlr[j]; wi[j] = twli[j]; }
+            else { wr[j] = twlr[j & 3]; wi[j] = twli[j & 3]; cmul<T>(wr[j], wi[j], twlr[j & ~3], twli[j & ~3]); }
+          }
         }
       }
       dft16_pretw<T>(re, im, wr, wi);
@@ -430,9 +529,16 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
         constexpr bool MAG = decltype(mag_tag)::value;
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-          const T pw = re[q] * re[q] + im[q] * im[q];
-          if constexpr (ACC != 0) re[q] = pw;                // keep the power for the accumulators
-          if (store_row) Epi::template store<T, MAG>(a.ep, row, N, bin_of(q), pw);
+          if constexpr (TDSA_WL_EPI_F32SQ && ACC == 0 && sizeof(T) == 8 && !MAG && std::is_same<Epi, EpiDb>::value) {
+            // narrow re and im first and square in float32: two conversions instead of DMUL + DFMA + one conversion on
+            // the FP64 pipe; |X|^2 has no cancellation, so the result is within 2 ulp(float32) = 5e-7 dB
+            const float fr = (float)re[q], fi = (float)im[q];
+            Epi::template store<float, MAG>(a.ep, row, N, bin_of(q), __fmaf_rn(fr, fr, fi * fi));
+          } else {
+            const T pw = re[q] * re[q] + im[q] * im[q];
+            if constexpr (ACC != 0) re[q] = pw;              // keep the power for the accumulators
+            if (store_row) Epi::template store<T, MAG>(a.ep, row, N, bin_of(q), pw);
+          }
         }
       };
       if (mag20) emit(std::true_type{}); else emit(std::false_type{});
@@ -534,7 +640,10 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if ((tid >> 5) == 0) tmem_dealloc(*tmem_slot, kTmemCols);
+  }
+  if constexpr (kUseTmem) {
+    if constexpr (ACC == 0) { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); __syncthreads(); }
+    if ((tid >> 5) == 0) tmem_dealloc<kTmemCols>(*tmem_slot);
   }
   // leave: the last CTA out re-arms the scheduler for the next launch
   if (tid == 0) {

@@ -277,8 +277,9 @@ cudaError_t launch_wl_final(const FftArgs<T>& a, const CUtensorMap& tmap, const 
     if (e != cudaSuccess) return e;
     // Kernels that allocate tensor memory are reported as one CTA per SM by the occupancy calculator (ncu capture of
     // round 2: grid 148, limits by registers and shared memory both 2).  The accumulating epilogue allocates 128 of
-    // the 512 TMEM columns per CTA, so two CTAs do fit; registers (launch bounds) and shared memory allow exactly two.
-    if (ACC != 0 && NB == 1 && o < 2 && 2 * kSmem <= 227 * 1024) o = 2;
+    // the 512 TMEM columns per CTA (at most 256 with the window values parked there too), so two CTAs do fit; registers (launch bounds) and shared memory allow exactly two.
+    constexpr bool kTmemUser = ACC != 0 || (TDSA_WL_WIN_TMEM && sizeof(T) == 8 && NB == 1);
+    if (kTmemUser && NB == 1 && o < 2 && 2 * kSmem <= 227 * 1024) o = 2;
     occ_of[device] = std::max(o, 1);
   }
   const int occ = occ_of[device];

@@ -38,9 +38,17 @@ def _welch_oracle(stream, n, hop, block=64):
     return 10 * np.log10(total / nseg + O.POWER_LOG_FLOOR), 10 * np.log10(peak + O.POWER_LOG_FLOOR), nseg
 
 
-def test_cfg3_full_size_welch_both_paths(dev, parity_log):
-    """2^26 samples, N = 65536, hop 32768 -> 2047 segments: the 16-CTA cluster kernel (7 co-resident clusters) and the
-    two-kernel path against the oracle: the float64 plan at north_star's 1e-4 dB, the float32 plan at 1e-3 dB."""
+CFG3_PATHS = {   # name -> environment switches of tdsa_welch (read at every call)
+    "head_wl_tail": {"TDSA_WELCH_SUB": "1"},                              # default: radix-16 head + warp-local tails, state in TMEM
+    "cluster": {"TDSA_WELCH_SUB": "0", "TDSA_WELCH_CLUSTER": "1"},        # round-1 16-CTA cluster kernel
+    "two_kernel": {"TDSA_WELCH_SUB": "0", "TDSA_WELCH_CLUSTER": "0"},     # round-1 head + classic tail + linear rows
+}
+
+
+def test_cfg3_full_size_welch_all_paths(dev, parity_log):
+    """2^26 samples, N = 65536, hop 32768 -> 2047 segments: the default path (one radix-16 head pass, 4096-point tails in
+    fft_wl_kernel with the Welch state in tensor memory), the 16-CTA cluster kernel and the two-kernel path against the
+    oracle: the float64 plan at north_star's 1e-4 dB, the float32 plan at 1e-3 dB."""
     import torch
     from topdogspectrumanalyser_b200.engine import SpectrumPlan
     n, hop, total = 65536, 32768, 1 << 26
@@ -48,25 +56,46 @@ def test_cfg3_full_size_welch_both_paths(dev, parity_log):
     want_avg, want_peak, nseg = _welch_oracle(stream, n, hop)
     assert nseg == 2047
     x = torch.from_numpy(stream).to(dev)
-    old = os.environ.get("TDSA_WELCH_CLUSTER")
+    keys = ("TDSA_WELCH_SUB", "TDSA_WELCH_CLUSTER")
+    old = {k: os.environ.get(k) for k in keys}
     try:
-        for cluster in ("1", "0"):
-            os.environ["TDSA_WELCH_CLUSTER"] = cluster
+        for name, env in CFG3_PATHS.items():
+            for k in keys:
+                os.environ.pop(k, None)
+            os.environ.update(env)
             for prec in ("f64", "f32"):
                 plan = SpectrumPlan(n, precision=prec, device=dev)
                 avg, peak = plan.welch(x, hop)
+                avg2, peak2 = plan.welch(x, hop)              # a second call re-uses the re-armed claim counters
+                assert torch.equal(avg, avg2) and torch.equal(peak, peak2)
                 ea = float(np.abs(avg.cpu().numpy() - want_avg).max())
                 ep = float(np.abs(peak.cpu().numpy() - want_peak).max())
                 tol = TOL_DB if prec == "f64" else 1e-3       # float32 plan: measured 1.05e-4 dB on the peak row
-                parity_log(f"cfg3_full_{'cluster' if cluster == '1' else 'two_kernel'}_{prec}", max(ea, ep), tol=tol,
-                           avg_err=ea, peak_err=ep, segments=nseg)
-                assert ea <= tol and ep <= tol, (cluster, prec, ea, ep)
+                parity_log(f"cfg3_full_{name}_{prec}", max(ea, ep), tol=tol, avg_err=ea, peak_err=ep, segments=nseg)
+                assert ea <= tol and ep <= tol, (name, prec, ea, ep)
                 plan.close()
     finally:
-        if old is None:
-            os.environ.pop("TDSA_WELCH_CLUSTER", None)
-        else:
-            os.environ["TDSA_WELCH_CLUSTER"] = old
+        for k in keys:
+            if old[k] is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = old[k]
+
+
+@pytest.mark.parametrize("nseg", [1, 3, 17, 40])
+def test_welch_65536_few_segments(dev, nseg):
+    """Fewer segments than CTAs / classes with no work / odd counts: the head + warp-local-tail path at 1e-4 dB."""
+    import torch
+    from topdogspectrumanalyser_b200.engine import SpectrumPlan
+    n, hop = 65536, 16384
+    stream = synth.cfg3_stream(n_samples=n + hop * (nseg - 1) + 5, seed=11 + nseg)
+    want_avg, want_peak, got_nseg = _welch_oracle(stream, n, hop)
+    assert got_nseg == nseg
+    plan = SpectrumPlan(n, device=dev)
+    avg, peak = plan.welch(torch.from_numpy(stream).to(dev), hop)
+    assert np.abs(avg.cpu().numpy() - want_avg).max() <= TOL_DB
+    assert np.abs(peak.cpu().numpy() - want_peak).max() <= TOL_DB
+    plan.close()
 
 
 def test_cfg4_full_size_rows_and_grid(dev, parity_log):

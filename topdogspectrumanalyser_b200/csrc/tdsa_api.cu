@@ -216,6 +216,11 @@ static bool welch_cluster_enabled() {   // read at every call so that tests can 
   return !(e && e[0] == '0');
 }
 
+static bool welch_sub_enabled() {       // TDSA_WELCH_SUB=0: the older cluster / two-kernel paths (kept for comparison)
+  const char* e = getenv("TDSA_WELCH_SUB");
+  return !(e && e[0] == '0');
+}
+
 static bool wl_enabled() {
   static const bool on = [] { const char* e = getenv("TDSA_WL"); return !(e && e[0] == '0'); }();
   return on;
@@ -482,8 +487,8 @@ int tdsa_create(int n_fft, int window_id, int window_norm, int mode, double log_
         cudaMalloc(&p->d_win32, sizeof(float) * n_fft) != cudaSuccess) { rc = fail(TDSA_ERR_NOMEM, "window alloc failed"); break; }
     rc = upload_twiddles(p->log2n, effective_logr_f64(p->log2n), effective_logr_f32(p->log2n), &p->d_tw64, &p->d_tw32);
     if (rc) break;
-    if (cudaMalloc(&p->d_sched, 2 * sizeof(int)) != cudaSuccess ||
-        cudaMemset(p->d_sched, 0, 2 * sizeof(int)) != cudaSuccess) { rc = fail(TDSA_ERR_NOMEM, "scheduler alloc failed"); break; }
+    if (cudaMalloc(&p->d_sched, kWlSchedWords * sizeof(int)) != cudaSuccess ||
+        cudaMemset(p->d_sched, 0, kWlSchedWords * sizeof(int)) != cudaSuccess) { rc = fail(TDSA_ERR_NOMEM, "scheduler alloc failed"); break; }
     if ((p->log2n == 12 && effective_logr_f64(12) == 4 && effective_logr_f32(12) == 4) || p->log2n == 13) {   // warp-local kernels
       p->wl_nb = p->log2n == 12 ? 1 : 2;
       if (cudaMalloc(&p->d_wperm64, sizeof(double) * n_fft * p->wl_nb) != cudaSuccess ||
@@ -953,6 +958,77 @@ int tdsa_welch(tdsa_handle_t p, const void* iq_stream, int64_t n_samples, int64_
       CK(cudaGetLastError());
       return TDSA_OK;
     }
+  }
+  // 65536-point segments, default: one radix-16 head pass over every segment (big_head_wl_kernel: windowed samples ->
+  // sixteen 4096-point sub-transform inputs per segment, complex T, in the tail's thread order), then ONE launch of the
+  // warp-local kernel over all 16 * nseg sub-transforms with the Welch sum and peak in tensor memory (kAccSub).  The
+  // intermediate goes through HBM once each way (16 B/point in float64) under the tail's arithmetic; no linear rows.
+  if (p->log2n == 16 && welch_sub_enabled() && nseg < (1 << 26)) {
+    if (p->win_dirty) { int rcw = upload_window(p); if (rcw) return rcw; }
+    const bool f32 = p->precision == TDSA_PREC_F32;
+    const size_t csz = f32 ? sizeof(float2) : sizeof(double2);
+    const int64_t chunk = std::min<int64_t>(nseg, 2048);                 // segments per head + tail pair (2 GiB of float64)
+    const int64_t n_chunks = (nseg + chunk - 1) / chunk;
+    int rcs = ensure_scratch(&p->scratch2, &p->scratch2_bytes, (size_t)chunk * n * csz);
+    if (rcs) return rcs;
+    WlLaunch L;
+    L.tmap = &p->tmap; L.sched = WlSched{p->d_sched, p->d_sched + 1}; L.nb = 1; L.acc_flags = kAccWelchSub;
+    L.device = p->device; L.sm_count = p->sm_count; L.wperm = nullptr;
+    // grid of the tail = partial rows per chunk
+    LaunchInfo info;
+    {
+      cudaError_t eq;
+      if (f32) { FftArgs<float> t{}; t.n_frames = chunk * 16; eq = launch_wl_f32(kEpiDb, t, L, p->stream, &info, true); }
+      else { FftArgs<double> t{}; t.n_frames = chunk * 16; eq = launch_wl_f64(kEpiDb, t, L, p->stream, &info, true); }
+      if (eq != cudaSuccess) return fail(TDSA_ERR_CUDA, "welch tail query failed: %s", cudaGetErrorString(eq));
+    }
+    const int grid = info.grid;
+    const size_t per = (size_t)4096 * (sizeof(double) + sizeof(float));
+    rcs = ensure_scratch(&p->acc_parts, &p->acc_parts_bytes, per * (size_t)grid * (size_t)n_chunks);
+    if (rcs) return rcs;
+    double* ps = (double*)p->acc_parts;
+    float* pmx = (float*)(ps + (size_t)grid * n_chunks * 4096);
+    for (int64_t ci = 0; ci < n_chunks; ++ci) {
+      const int64_t s0 = ci * chunk, ns = std::min(chunk, nseg - s0);
+      cudaError_t e;
+      WlAcc acc;
+      acc.part_sum = ps + (size_t)ci * grid * 4096; acc.part_max = pmx + (size_t)ci * grid * 4096;
+      L.acc = acc;
+      if (ns < chunk) {      // a shorter last chunk may use a smaller grid: its unused partial rows must read as empty
+        welch_sub_clear_kernel<<<(grid * 4096 + 255) / 256, 256, 0, p->stream>>>(acc.part_sum, acc.part_max, (int64_t)grid * 4096);
+        count_launch();
+      }
+      if (f32) {
+        BigArgs<float> a;
+        a.iq = (const float2*)iq_stream + s0 * hop; a.n_frames = ns; a.frame_stride = hop; a.window = p->d_win32;
+        a.tw = p->d_twh32; a.dc = nullptr; a.y = (float2*)p->scratch2; a.log2n = p->log2n;
+        e = launch_big_head_f32(a, p->sm_count, p->stream, 0);
+        if (e == cudaSuccess) {
+          FftArgs<float> t;
+          t.iq = nullptr; t.n_frames = ns * 16; t.frame_stride = 0; t.window = nullptr; t.tw = p->d_twin32; t.dc = nullptr;
+          t.in_ct = (const float2*)p->scratch2; t.ep = make_epi(p, nullptr, nullptr);
+          e = launch_wl_f32(kEpiDb, t, L, p->stream, nullptr, false);
+        }
+      } else {
+        BigArgs<double> a;
+        a.iq = (const float2*)iq_stream + s0 * hop; a.n_frames = ns; a.frame_stride = hop; a.window = p->d_win64;
+        a.tw = p->d_twh64; a.dc = nullptr; a.y = (double2*)p->scratch2; a.log2n = p->log2n;
+        e = launch_big_head_f64(a, p->sm_count, p->stream, 0);
+        if (e == cudaSuccess) {
+          FftArgs<double> t;
+          t.iq = nullptr; t.n_frames = ns * 16; t.frame_stride = 0; t.window = nullptr; t.tw = p->d_twin64; t.dc = nullptr;
+          t.in_ct = (const double2*)p->scratch2; t.ep = make_epi(p, nullptr, nullptr);
+          e = launch_wl_f64(kEpiDb, t, L, p->stream, nullptr, false);
+        }
+      }
+      if (e != cudaSuccess) return fail(TDSA_ERR_CUDA, "welch head/tail launch failed: %s", cudaGetErrorString(e));
+    }
+    const double scale = (p->mode == TDSA_MODE_PSD) ? 1.0 / (p->fs * (double)n) : 1.0;
+    welch_sub_finish_kernel<<<65536 / 256, 256, 0, p->stream>>>(ps, pmx, grid * (int)n_chunks, nseg, scale, p->floor, p->mode,
+                                                                avg_db, peak_db);
+    count_launch();
+    CK(cudaGetLastError());
+    return TDSA_OK;
   }
   // 65536-point segments: one cluster kernel keeps everything but the IQ samples on the SMs (tdsa_welch_cluster.cuh)
   if (p->log2n == kWcLog2N && welch_cluster_enabled()) {

@@ -107,4 +107,102 @@ __global__ void __launch_bounds__(256) big_head1_kernel(const BigArgs<T> a) {
   }
 }
 
+// 8-byte asynchronous copy global -> shared (LDGSTS): the prefetch of the next segment needs no registers
+__device__ __forceinline__ void cp_async_8(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// shared memory of big_head_wl_kernel: two sample buffers [16 j][272 float2] (256 columns at pitch 17 per 16) and the
+// CTA's window slice [16 j][256] in T
+template <typename T> constexpr int head_wl_smem() { return 2 * 16 * 272 * 8 + 16 * 256 * (int)sizeof(T); }
+
+// Head of the 65536-point Welch path whose tails run through fft_wl_kernel (kAccSub): like big_head1_kernel, one radix-16
+// over the samples c + 4096 j of a windowed segment and the post-twiddle W_N^(c q), but
+//   * a CTA keeps one block of 256 columns (b = blockIdx.x % 16) for all the segments it processes: its window slice
+//     lives in shared memory and its base twiddles W_N^(c q) in registers (the other twiddles are products), so per
+//     segment only the samples are read;
+//   * sub-transform q of segment f is written in the order fft_wl_kernel's threads consume it: y[((f*16 + q)*16 + j)*256
+//     + tid] is sample n0 = r + 16 c' + 256 j of the 4096-point input, (r, c') = wl_thread_identity(tid).  The 256
+//     values of one (q, j) are exactly one CTA's columns (j = b), so head thread tid computes the column the tail's
+//     thread tid will want and stores are fully coalesced (dst[tid]);
+//   * the samples of the NEXT segment travel global -> shared by cp.async in natural column order (coalesced, no
+//     registers) while this segment is transformed; the permutation to the tail's order happens on the shared-memory
+//     read (pitch 17: at most two wavefronts per 8-byte warp read).
+// Measured (round 2, 2047 segments): storing in permuted order cost 1.07 GB of DRAM fill reads in float32 (half
+// sectors); permuted global loads of samples and window doubled the L2 read traffic (7.4 GB, the L2 limit) at 704 us
+// (float64); see profiles/r02_experiments.md.
+template <typename T>
+__global__ void __launch_bounds__(256, 2) big_head_wl_kernel(const BigArgs<T> a) {
+  using CT = typename CplxOf<T>::type;
+  constexpr int64_t s0 = 4096;                              // columns per segment
+  const int tid = threadIdx.x;
+  const int b = (int)(blockIdx.x & 15);
+  // the tail's thread identity (wl_thread_identity): warp w, lane l -> r = 2 w + ((l >> 3) & 1), c' = (l & 7) + 8 (l >> 4)
+  const int wl_w = tid >> 5, wl_l = tid & 31;
+  const int r = 2 * wl_w + ((wl_l >> 3) & 1), cp = (wl_l & 7) + 8 * (wl_l >> 4);
+  const int c = 256 * b + r + 16 * cp;                      // this thread's column of the segment
+  extern __shared__ __align__(16) unsigned char head_smem[];
+  float2* sbuf = reinterpret_cast<float2*>(head_smem);       // [2][16][272]
+  T* swin = reinterpret_cast<T*>(head_smem + 2 * 16 * 272 * 8);   // [16][256], thread order
+#pragma unroll
+  for (int j = 0; j < 16; ++j) swin[j * 256 + tid] = a.window[c + j * s0];
+  // base twiddles kept in registers: float64 w^1 and w^4, float32 w^1..w^3, w^4, w^8, w^12
+  constexpr bool kTwoBases = sizeof(T) == 8;
+  T bwr[16], bwi[16];
+#pragma unroll
+  for (int q = 1; q < 16; ++q) {
+    if (kTwoBases ? (q == 1 || q == 4) : (q < 4 || (q & 3) == 0)) { const CT w = a.tw[q * s0 + c]; bwr[q] = w.x; bwi[q] = w.y; }
+  }
+  const int64_t f_step = gridDim.x >> 4;
+  int64_t f = blockIdx.x >> 4;
+  // copy side: thread tid moves natural column 256 b + tid to slot (tid & 15) + 17 (tid >> 4); read side: slot r + 17 c'
+  const uint32_t put_u32 = smem_u32(head_smem) + (uint32_t)((tid & 15) + 17 * (tid >> 4)) * 8u;
+  const float2* get = sbuf + r + 17 * cp;
+  auto prefetch = [&](int64_t seg, int buf) {
+    const float2* src = a.iq + seg * a.frame_stride + 256 * b + tid;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) cp_async_8(put_u32 + (uint32_t)((buf * 16 + j) * 272 * 8), src + j * s0);
+  };
+  if (f < a.n_frames) prefetch(f, 0);
+  cp_async_commit();
+  for (int it = 0; f < a.n_frames; f += f_step, ++it) {
+    cp_async_wait<0>();                                      // my copies of this segment have landed ...
+    __syncthreads();                                         // ... everybody's have, and the other buffer is no longer read
+    if (f + f_step < a.n_frames) prefetch(f + f_step, (it + 1) & 1);
+    cp_async_commit();
+    T re[16], im[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float2 v = get[((it & 1) * 16 + j) * 272];
+      const T wv = swin[j * 256 + tid];
+      re[j] = (T)v.x * wv;
+      im[j] = (T)v.y * wv;
+    }
+    dft16<T>(re, im);
+    T wr[16], wi[16];
+#pragma unroll
+    for (int q = 1; q < 16; ++q) {
+      if (kTwoBases ? (q == 1 || q == 4) : (q < 4 || (q & 3) == 0)) { wr[q] = bwr[q]; wi[q] = bwi[q]; }
+    }
+    if constexpr (kTwoBases) {
+      wr[2] = wr[1]; wi[2] = wi[1]; cmul<T>(wr[2], wi[2], wr[1], wi[1]);
+      wr[3] = wr[2]; wi[3] = wi[2]; cmul<T>(wr[3], wi[3], wr[1], wi[1]);
+      wr[8] = wr[4]; wi[8] = wi[4]; cmul<T>(wr[8], wi[8], wr[4], wi[4]);
+      wr[12] = wr[8]; wi[12] = wi[8]; cmul<T>(wr[12], wi[12], wr[4], wi[4]);
+    }
+    CT* dst = a.y + ((f * 16) * 16 + b) * 256 + tid;
+    dst[0] = mk<T>(re[0], im[0]);
+#pragma unroll
+    for (int q = 1; q < 16; ++q) {
+      T xr = wr[q & 3], xi = wi[q & 3];
+      if ((q & 3) == 0) { xr = wr[q]; xi = wi[q]; }
+      else if (q >= 4) cmul<T>(xr, xi, wr[q & ~3], wi[q & ~3]);
+      cmul<T>(re[q], im[q], xr, xi);
+      dst[(int64_t)q * 4096] = mk<T>(re[q], im[q]);
+    }
+  }
+}
+
 }  // namespace tdsa

@@ -13,6 +13,21 @@ cudaError_t launch_welch_cluster_f64(const WelchClusterArgs<double>& a, int clus
 #include "tdsa_big.cuh"
 namespace tdsa {
 cudaError_t launch_big_head_f64(const BigArgs<double>& a, int sm, cudaStream_t s, int passes) {
+  if (passes == 0) {                                        // head for fft_wl_kernel tails (N = 65536)
+    static int occ_of[kMaxDevices] = {};
+    const int dev = current_device();
+    if (occ_of[dev] == 0) {
+      cudaError_t ea = cudaFuncSetAttribute(big_head_wl_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, head_wl_smem<double>());
+      if (ea != cudaSuccess) return ea;
+      int o = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, big_head_wl_kernel<double>, 256, head_wl_smem<double>()) != cudaSuccess) o = 2;
+      occ_of[dev] = std::max(o, 1);
+    }
+    const int grid = 16 * (int)std::max<int64_t>(1, std::min<int64_t>(a.n_frames, (int64_t)sm * occ_of[dev] / 16));
+    big_head_wl_kernel<double><<<grid, 256, head_wl_smem<double>(), s>>>(a);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+  }
   if (passes == 1) {
     const int64_t work = a.n_frames * (((int64_t)1 << a.log2n) >> 4);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)sm * 8));

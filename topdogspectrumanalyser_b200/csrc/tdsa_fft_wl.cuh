@@ -40,7 +40,12 @@
 
 namespace tdsa {
 
-enum : int { kAccSum = 1, kAccMax = 2, kAccMin = 4, kAccGroup = 8, kAccRows = 16 };
+enum : int { kAccSum = 1, kAccMax = 2, kAccMin = 4, kAccGroup = 8, kAccRows = 16, kAccSub = 32 };
+// kAccSub (tail of the 65536-point Welch path, tdsa_big.cuh): the "frames" are the sixteen 4096-point sub-transforms
+// of each segment, already windowed, in complex T and in thread order ([frame][j][tid], written by big_head_wl_kernel).
+// No window, no TMA staging: every thread loads its sixteen values with coalesced 16-byte (float64) loads.  CTA b only
+// takes sub-transforms of class b % 16 (sub-transform s holds the bins k = s mod 16), so that its TMEM accumulators
+// see one set of bins for the whole launch; each class has its own claim counter (sched.next[2 + s]).
 constexpr int kMaxPeers = 8;
 
 // arguments of the accumulating epilogue
@@ -123,9 +128,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 struct WlSched {
-  int* next;       // next unclaimed unit (frame, or group of frames)
+  int* next;       // next unclaimed unit (frame, or group of frames); kAccSub: next[2 + s] = next segment of class s
   int* done;       // CTAs that have left the frame loop
 };
+constexpr int kWlSchedWords = 2 + 16;
 
 // W32^j = exp(-2 pi i j / 32), j = 0..15 (pass-A pre-twiddles of the half-bin engine); j is a compile-time constant
 // at every use (unrolled loops), so these fold to immediates
@@ -219,9 +225,11 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
   CT* reg = ex + r * REGION;
   const CT* twe = a.tw + e * kWlTwPerEngine;                // this engine's tables
 
+  constexpr bool SUB = (ACC & kAccSub) != 0;
+  static_assert(!SUB || (NB == 1 && !HAS_DC && (ACC & (kAccGroup | kAccRows)) == 0), "sub-transform tail: one engine, accumulate only");
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) {
+    for (int s = 0; s < (SUB ? 0 : NSTAGE); ++s) {
       mbar_init(ctrl_u32 + 8 * s, 1);
       if constexpr (NB > 1 || TDSA_WL_EARLY) mbar_init(ctrl_u32 + 32 + 8 * s, 8 * NB);     // one arrival per warp
     }
@@ -242,8 +250,10 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
   T win[NWIN];
   T twlr[16], twli[16];
   if constexpr (TWMODE == 1) {
+    if constexpr (!SUB) {
 #pragma unroll
-    for (int j = 0; j < NWIN; ++j) win[j] = wperm[j * TH + tid];
+      for (int j = 0; j < NWIN; ++j) win[j] = wperm[j * TH + tid];
+    }
 #pragma unroll
     for (int j = 1; j < 16; ++j) { const CT x = tw_last[j * 256 + te]; twlr[j] = x.x; twli[j] = x.y; }
   } else {
@@ -266,6 +276,11 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
   const int group = (ACC & kAccGroup) ? acc.group : 1;
   int unit_base = 0, unit_pos = 0;                          // thread 0: the unit being handed out, frames already taken from it
   auto next_frame = [&]() -> int {                          // thread 0 only
+    if constexpr (SUB) {
+      const int cls = (int)(blockIdx.x & 15);
+      const int u = atomicAdd(sched.next + 2 + cls, 1);
+      return ((int64_t)u * 16 >= a.n_frames) ? 0x7fffffff : u * 16 + cls;
+    }
     if (unit_pos == 0 || unit_pos == group) {
       const int u = atomicAdd(sched.next, 1);
       if ((int64_t)u * group >= a.n_frames) { unit_pos = group; return 0x7fffffff; }
@@ -287,8 +302,12 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     }
   };
   if (tid == 0) {
+    if constexpr (SUB) {
+      slot[0] = next_frame();
+    } else {
 #pragma unroll
-    for (int s = 0; s < NSTAGE; ++s) issue_stage(s, next_frame());
+      for (int s = 0; s < NSTAGE; ++s) issue_stage(s, next_frame());
+    }
   }
   __syncthreads();
   if constexpr (kUseTmem) {
@@ -340,7 +359,7 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       uint32_t (&hi16)[16] = *reinterpret_cast<uint32_t (*)[16]>(&wraw[16]);
       tmem_ld16_nowait(twin, lo16);
       tmem_ld16_nowait(twin + 16, hi16);
-    } else if constexpr (TWMODE != 1) {                      // window values for pass A, re-read every frame (register budget)
+    } else if constexpr (TWMODE != 1 && !SUB) {              // window values for pass A, re-read every frame (register budget)
 #pragma unroll
       for (int j = 0; j < NWIN; ++j) win[j] = wperm[j * TH + tid];
     }
@@ -356,8 +375,9 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     };
     if constexpr (TDSA_WL_EARLY && NB == 1) { if (tid == 0) fnext = next_frame(); }
     TDSA_STAMP(0);
-    mbar_wait(ctrl_u32 + 8 * stg, (uint32_t)((it / NSTAGE) & 1));
-    const int f = slot[stg];                                 // written by thread 0 before it armed / completed the barrier
+    if constexpr (!SUB) mbar_wait(ctrl_u32 + 8 * stg, (uint32_t)((it / NSTAGE) & 1));
+    // written by thread 0 before it armed / completed the barrier (SUB: before the previous frame's Y barrier)
+    const int f = SUB ? slot[it & 1] : slot[stg];
     if (f >= a.n_frames) break;
 #ifdef TDSA_DEBUG_TIMING
     if (it == 0 && tid == 0 && a.dbg != nullptr) {
@@ -377,15 +397,23 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       if constexpr (HAS_DC) { const double2 d = a.dc[f]; dcr = (T)d.x; dci = (T)d.y; }
       TDSA_STAMP(1);
       const unsigned char* src = stage_ptr + (size_t)stg * W::STAGE_BYTES + stage_off;
-      float2 v[16];
+      float2 v[SUB ? 1 : 16];
+      if constexpr (SUB) {
+        const CT* y = a.in_ct + (int64_t)f * 4096 + tid;     // [frame][j][tid]: 256 consecutive values per j
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(src + j * 2048);
+        for (int j = 0; j < 16; ++j) { const CT x = __ldcg(y + j * 256); re[j] = x.x; im[j] = x.y; }
+      } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if constexpr (HAS_DC) { re[j] = (T)v[j].x - dcr; im[j] = (T)v[j].y - dci; }
-        else { re[j] = (T)v[j].x; im[j] = (T)v[j].y; }
+        for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(src + j * 2048);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if constexpr (HAS_DC) { re[j] = (T)v[j].x - dcr; im[j] = (T)v[j].y - dci; }
+          else { re[j] = (T)v[j].x; im[j] = (T)v[j].y; }
+        }
       }
-      if constexpr (NB == 1) {
+      if constexpr (SUB) {
+        dft16<T>(re, im);
+      } else if constexpr (NB == 1) {
         dft16_win<T>(re, im, win);
       } else {
         // radix-2 DIF step on the staged read: s[n] = x[n] w[n] +- x[n + 4096] w[n + 4096] (the sign lives in the table)
@@ -420,6 +448,7 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       if (l == 0) mbar_arrive(ctrl_u32 + 32 + 8 * stg);
     }
     if constexpr (TDSA_WL_EARLY && NB == 1) { if (tid == 0) try_refill(false); }
+    else if constexpr (SUB) { if (tid == 0) slot[(it + 1) & 1] = next_frame(); }   // read by everyone after the Y barrier
     else { if (tid == 0) fnext = next_frame(); }             // consumed after the barrier below
     TDSA_STAMP(3);
     // ---- pass B: thread ka = c reads A_j[ka] (j = 0..15), pre-twiddle [j][ka], radix 16 over j --------------
@@ -471,7 +500,7 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     // Measured (round 2): letting the LAST warp to finish its staged reads refill the stage (shared-memory counter, frame
     // claimed at the top of the iteration) instead of thread 0 after this barrier was slower: 78.0 -> 83.9 us (f32),
     // 135.2 -> 139.4 us (f64) at N = 4096, 206.8 -> 219.1 us (f64) at N = 8192.
-    if (tid == 0) {
+    if (tid == 0 && !SUB) {
       if constexpr (TDSA_WL_EARLY && NB == 1) {
         try_refill(true);
       } else {
@@ -650,6 +679,10 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     __threadfence();
     if (atomicAdd(sched.done, 1) == (int)gridDim.x - 1) {
       *sched.next = 0;
+      if constexpr (SUB) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sched.next[2 + i] = 0;
+      }
       *sched.done = 0;
       __threadfence();
     }

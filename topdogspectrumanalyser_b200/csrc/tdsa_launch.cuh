@@ -265,7 +265,8 @@ cudaError_t launch_wl_final(const FftArgs<T>& a, const CUtensorMap& tmap, const 
   constexpr int kThreads = 256 * NB;
   constexpr int kMinCtas = NB == 1 ? 2 : 1;
   static const size_t kExtraSmem = [] { const char* e = getenv("TDSA_DEBUG_EXTRA_SMEM"); return e ? (size_t)atol(e) : (size_t)0; }();
-  const size_t kSmem = std::min<size_t>(WlPlan<T, NB>::smem_bytes(kStages) + kExtraSmem, 227 * 1024);
+  constexpr bool kSub = (ACC & kAccSub) != 0;                  // direct loads: no staging buffers
+  const size_t kSmem = std::min<size_t>(WlPlan<T, NB>::smem_bytes(kSub ? 0 : kStages) + kExtraSmem, 227 * 1024);
   auto kern = fft_wl_kernel<T, Epi, kTwMode, kStages, HAS_DC, kMinCtas, (sizeof(T) == 4 ? TDSA_WL_TWB_BASE_F32 : 0) != 0, NB, ACC>;
   static int occ_of[kMaxDevices] = {};          // 0 = not queried on that device yet
   if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
@@ -285,7 +286,9 @@ cudaError_t launch_wl_final(const FftArgs<T>& a, const CUtensorMap& tmap, const 
   const int occ = occ_of[device];
   const int group = (ACC & kAccGroup) ? std::max(acc.group, 1) : 1;
   const int64_t n_units = a.n_frames / group;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_units, (int64_t)sm_count * occ));
+  int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_units, (int64_t)sm_count * occ));
+  if constexpr (kSub)                                          // CTA b serves class b % 16: whole sets of sixteen classes
+    grid = 16 * (int)std::max<int64_t>(1, std::min<int64_t>(a.n_frames / 16, (int64_t)sm_count * occ / 16));
   if (info) {
     info->threads = kThreads; info->smem = (int)kSmem; info->ctas_per_sm = occ; info->grid = grid;
     info->stages = kStages; info->logr = 4;
@@ -331,6 +334,7 @@ constexpr int kAccAvg = kAccSum;                               // running averag
 constexpr int kAccHold = kAccMax | kAccMin | kAccRows;         // dB rows + max/min hold on un-averaged frames
 constexpr int kAccWelch = kAccSum | kAccMax;                   // Welch mean + peak
 constexpr int kAccGroupMean = kAccSum | kAccGroup;             // one dB row per group of frames
+constexpr int kAccWelchSub = kAccSum | kAccMax | kAccSub;      // Welch mean + peak over the sub-transforms of 65536-point segments
 
 template <typename T>
 cudaError_t launch_wl_impl(int epi, const FftArgs<T>& a, const WlLaunch& L, cudaStream_t s, LaunchInfo* info, bool dry) {
@@ -348,6 +352,7 @@ cudaError_t launch_wl_impl(int epi, const FftArgs<T>& a, const WlLaunch& L, cuda
       case kAccHold: if (!dc) TDSA_WL_GO(EpiDb, false, 1, kAccHold); break;
       case kAccWelch: if (!dc) TDSA_WL_GO(EpiDb, false, 1, kAccWelch); break;
       case kAccGroupMean: if (!dc) TDSA_WL_GO(EpiDb, false, 1, kAccGroupMean); break;
+      case kAccWelchSub: if (!dc) TDSA_WL_GO(EpiDb, false, 1, kAccWelchSub); break;
       default: break;
     }
   } else if (L.nb == 2 && !dc) {
@@ -363,7 +368,8 @@ cudaError_t launch_wl_impl(int epi, const FftArgs<T>& a, const WlLaunch& L, cuda
 inline bool wl_supported(int nb, int epi, int acc_flags, bool dc) {
   if (nb == 1) {
     if (acc_flags == 0) return epi == kEpiDb || epi == kEpiLinear;
-    return !dc && (acc_flags == kAccAvg || acc_flags == kAccHold || acc_flags == kAccWelch || acc_flags == kAccGroupMean);
+    return !dc && (acc_flags == kAccAvg || acc_flags == kAccHold || acc_flags == kAccWelch || acc_flags == kAccGroupMean ||
+                   acc_flags == kAccWelchSub);
   }
   if (nb == 2 && !dc) return acc_flags == kAccGroupMean;
   return false;
@@ -419,5 +425,6 @@ template <typename T> struct BigArgs;
 // passes = 2: big_head_kernel (N = 256*M); passes = 1: big_head1_kernel (N = 16*M)
 cudaError_t launch_big_head_f32(const BigArgs<float>& a, int sm, cudaStream_t s, int passes);
 cudaError_t launch_big_head_f64(const BigArgs<double>& a, int sm, cudaStream_t s, int passes);
+// passes = 0: big_head_wl_kernel (N = 65536, output in the thread order of fft_wl_kernel's kAccSub mode)
 
 }  // namespace tdsa

@@ -164,6 +164,33 @@ __global__ void __launch_bounds__(256) welch_acc_finish_kernel(const double* __r
   peak_db[k] = to_db<float>(m, ep);
 }
 
+__global__ void __launch_bounds__(256) welch_sub_clear_kernel(double* __restrict__ part_sum, float* __restrict__ part_max, int64_t count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) { part_sum[i] = 0.0; part_max[i] = -INFINITY; }
+}
+
+// Welch over 65536-point segments whose 4096-point tails accumulated per class (fft_wl_kernel, kAccSub): partial row b
+// holds sub-transform s = b % 16, whose local bin kl is bin s + 16 kl of the segment spectrum
+__global__ void __launch_bounds__(256) welch_sub_finish_kernel(const double* __restrict__ part_sum, const float* __restrict__ part_max,
+                                                              int n_parts, int64_t n_seg, double scale, double floor, int mode,
+                                                              float* __restrict__ avg_db, float* __restrict__ peak_db) {
+  const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (t >= 65536) return;
+  const int kl = t & 4095, s = t >> 12;
+  double sum = 0.0;
+  float m = -INFINITY;
+  for (int b = s; b < n_parts; b += 16) {
+    sum += part_sum[(int64_t)b * 4096 + kl];
+    m = fmaxf(m, part_max[(int64_t)b * 4096 + kl]);
+  }
+  EpiParams ep;
+  ep.db_out = nullptr; ep.lin_out = nullptr; ep.scale = 1.0; ep.floor = floor; ep.mode = mode;
+  const int k = s + 16 * kl;
+  avg_db[k] = to_db<double>(sum * scale / (double)n_seg, ep);
+  ep.scale = scale;
+  peak_db[k] = to_db<float>(m, ep);
+}
+
 // Config-4 rows from split groups: each group's `split` unit sums are added, divided by the frames of the group and
 // converted to one dB row, stored locally (group_db) or straight into every rank's row table (peers, NVLink stores).
 struct GroupFinishArgs {

@@ -39,16 +39,18 @@ def _welch_oracle(stream, n, hop, block=64):
 
 
 CFG3_PATHS = {   # name -> environment switches of tdsa_welch (read at every call)
-    "head_wl_tail": {"TDSA_WELCH_SUB": "1"},                              # default: radix-16 head + warp-local tails, state in TMEM
+    "head_wl_tail": {},                                                   # default: radix-16 head kernel + warp-local tail kernel
+    "fused": {"TDSA_WELCH_FUSED": "1"},                                   # both in ONE kernel, intermediate in an L2-resident ring
     "cluster": {"TDSA_WELCH_SUB": "0", "TDSA_WELCH_CLUSTER": "1"},        # round-1 16-CTA cluster kernel
     "two_kernel": {"TDSA_WELCH_SUB": "0", "TDSA_WELCH_CLUSTER": "0"},     # round-1 head + classic tail + linear rows
 }
+CFG3_KEYS = ("TDSA_WELCH_FUSED", "TDSA_WELCH_SUB", "TDSA_WELCH_CLUSTER")
 
 
 def test_cfg3_full_size_welch_all_paths(dev, parity_log):
-    """2^26 samples, N = 65536, hop 32768 -> 2047 segments: the default path (one radix-16 head pass, 4096-point tails in
-    fft_wl_kernel with the Welch state in tensor memory), the 16-CTA cluster kernel and the two-kernel path against the
-    oracle: the float64 plan at north_star's 1e-4 dB, the float32 plan at 1e-3 dB."""
+    """2^26 samples, N = 65536, hop 32768 -> 2047 segments: the default path (radix-16 head kernel, then 4096-point tails
+    in fft_wl_kernel with the Welch state in tensor memory), the same in one fused launch, the 16-CTA cluster kernel and
+    the round-1 two-kernel path against the oracle: the float64 plan at north_star's 1e-4 dB, the float32 plan at 1e-3 dB."""
     import torch
     from topdogspectrumanalyser_b200.engine import SpectrumPlan
     n, hop, total = 65536, 32768, 1 << 26
@@ -56,7 +58,7 @@ def test_cfg3_full_size_welch_all_paths(dev, parity_log):
     want_avg, want_peak, nseg = _welch_oracle(stream, n, hop)
     assert nseg == 2047
     x = torch.from_numpy(stream).to(dev)
-    keys = ("TDSA_WELCH_SUB", "TDSA_WELCH_CLUSTER")
+    keys = CFG3_KEYS
     old = {k: os.environ.get(k) for k in keys}
     try:
         for name, env in CFG3_PATHS.items():
@@ -82,19 +84,23 @@ def test_cfg3_full_size_welch_all_paths(dev, parity_log):
                 os.environ[k] = old[k]
 
 
+@pytest.mark.parametrize("fused", ["1", "0"])
 @pytest.mark.parametrize("nseg", [1, 3, 17, 40])
-def test_welch_65536_few_segments(dev, nseg):
-    """Fewer segments than CTAs / classes with no work / odd counts: the head + warp-local-tail path at 1e-4 dB."""
+def test_welch_65536_few_segments(dev, nseg, fused, monkeypatch):
+    """Fewer segments than groups / CTAs with no work / odd counts: the fused and the two-launch path at 1e-4 dB."""
     import torch
     from topdogspectrumanalyser_b200.engine import SpectrumPlan
+    monkeypatch.setenv("TDSA_WELCH_FUSED", fused)
     n, hop = 65536, 16384
     stream = synth.cfg3_stream(n_samples=n + hop * (nseg - 1) + 5, seed=11 + nseg)
     want_avg, want_peak, got_nseg = _welch_oracle(stream, n, hop)
     assert got_nseg == nseg
     plan = SpectrumPlan(n, device=dev)
-    avg, peak = plan.welch(torch.from_numpy(stream).to(dev), hop)
-    assert np.abs(avg.cpu().numpy() - want_avg).max() <= TOL_DB
-    assert np.abs(peak.cpu().numpy() - want_peak).max() <= TOL_DB
+    x = torch.from_numpy(stream).to(dev)
+    for _ in range(2):                                    # the second call runs on re-armed counters
+        avg, peak = plan.welch(x, hop)
+        assert np.abs(avg.cpu().numpy() - want_avg).max() <= TOL_DB
+        assert np.abs(peak.cpu().numpy() - want_peak).max() <= TOL_DB
     plan.close()
 
 

@@ -20,7 +20,8 @@ def ev_time(fn, reps):
 # config 3: 2^26 samples, N = 65536, hop 32768 -> 2047 segments, avg + peak rows
 stream = torch.from_numpy(synth.cfg3_stream(1 << 26, seed=2)).to(dev)
 import os
-for path, env in (("head + warp-local tails (default)", {"TDSA_WELCH_SUB": "1"}),
+for path, env in (("head kernel + warp-local tail kernel (default)", {"TDSA_WELCH_SUB": "1", "TDSA_WELCH_FUSED": "0"}),
+                  ("head + warp-local tails in one kernel, L2 ring (opt-in)", {"TDSA_WELCH_SUB": "1", "TDSA_WELCH_FUSED": "1"}),
                   ("cluster kernel (round 1)", {"TDSA_WELCH_SUB": "0", "TDSA_WELCH_CLUSTER": "1"}),
                   ("two kernels + linear rows (round 1)", {"TDSA_WELCH_SUB": "0", "TDSA_WELCH_CLUSTER": "0"})):
     os.environ.update(env)
@@ -31,7 +32,7 @@ for path, env in (("head + warp-local tails (default)", {"TDSA_WELCH_SUB": "1"})
                           "ms": t * 1e3, "input_samples_per_s": (1 << 26) / t, "segment_samples_per_s": 2047 * 65536 / t,
                           "hbm_frac_8B_per_input_sample": 8 * (1 << 26) / t / 6534.1e9}), flush=True)
         plan.close()
-os.environ.pop("TDSA_WELCH_SUB", None); os.environ.pop("TDSA_WELCH_CLUSTER", None)
+for k in ("TDSA_WELCH_SUB", "TDSA_WELCH_CLUSTER", "TDSA_WELCH_FUSED"): os.environ.pop(k, None)
 del stream
 # config 4 on one GPU: 300 sub-bands x 16 frames x 8192
 iq = torch.from_numpy(synth.cfg4_subbands(300, 16, 8192, seed=3)).to(dev)

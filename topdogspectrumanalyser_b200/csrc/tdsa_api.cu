@@ -221,6 +221,15 @@ static bool welch_sub_enabled() {       // TDSA_WELCH_SUB=0: the older cluster /
   return !(e && e[0] == '0');
 }
 
+// TDSA_WELCH_FUSED=1: head pass and tails in ONE kernel, intermediate in an L2-resident ring (0.6 GB of DRAM traffic
+// instead of 4.9 GB).  Measured slower than the two launches (round 2, 2047 segments: 1.25 vs 1.09 ms in float64, 0.70 vs
+// 0.61 ms in float32: every iteration of a CTA becomes a chain of latency-bound phases -- 64 KB of ring stores, then 64 KB
+// of ring loads queued behind them -- with only two CTAs per SM to overlap; profiles/r02_experiments.md), so it is opt-in.
+static bool welch_fused_enabled() {
+  const char* e = getenv("TDSA_WELCH_FUSED");
+  return e && e[0] == '1';
+}
+
 static bool wl_enabled() {
   static const bool on = [] { const char* e = getenv("TDSA_WL"); return !(e && e[0] == '0'); }();
   return on;
@@ -959,7 +968,55 @@ int tdsa_welch(tdsa_handle_t p, const void* iq_stream, int64_t n_samples, int64_
       return TDSA_OK;
     }
   }
-  // 65536-point segments, default: one radix-16 head pass over every segment (big_head_wl_kernel: windowed samples ->
+  // 65536-point segments, opt-in (TDSA_WELCH_FUSED=1): ONE kernel (fft_wl_kernel, kAccFused).  Groups of sixteen CTAs own whole segments: each
+  // CTA runs one column block of the radix-16 head pass into the group's ring of kFusedRing segments (complex T, stays in L2), then
+  // the 4096-point sub-transform of its class with the Welch sum and peak in tensor memory; one finish kernel.
+  if (p->log2n == 16 && welch_sub_enabled() && welch_fused_enabled() && nseg < (1 << 26)) {
+    if (p->win_dirty) { int rcw = upload_window(p); if (rcw) return rcw; }
+    const bool f32 = p->precision == TDSA_PREC_F32;
+    const size_t csz = f32 ? sizeof(float2) : sizeof(double2);
+    WlLaunch L;
+    L.tmap = &p->tmap; L.sched = WlSched{p->d_sched, p->d_sched + 1}; L.nb = 1; L.acc_flags = kAccWelchFused;
+    L.device = p->device; L.sm_count = p->sm_count; L.wperm = nullptr;
+    LaunchInfo info;
+    cudaError_t e;
+    if (f32) { FftArgs<float> t{}; t.n_frames = nseg * 16; e = launch_wl_f32(kEpiDb, t, L, p->stream, &info, true); }
+    else { FftArgs<double> t{}; t.n_frames = nseg * 16; e = launch_wl_f64(kEpiDb, t, L, p->stream, &info, true); }
+    if (e != cudaSuccess) return fail(TDSA_ERR_CUDA, "welch fused query failed: %s", cudaGetErrorString(e));
+    const int grid = info.grid, groups = grid / 16;
+    if (info.ctas_per_sm * p->sm_count >= grid) {               // every CTA resident at once, or the groups could wait forever
+      int rcs = ensure_scratch(&p->scratch2, &p->scratch2_bytes, (size_t)groups * kFusedRing * n * csz);
+      if (rcs) return rcs;
+      const size_t per = (size_t)4096 * (sizeof(double) + sizeof(float));
+      rcs = ensure_scratch(&p->acc_parts, &p->acc_parts_bytes, per * (size_t)grid);
+      if (rcs) return rcs;
+      double* ps = (double*)p->acc_parts;
+      float* pmx = (float*)(ps + (size_t)grid * 4096);
+      WlAcc acc;
+      acc.part_sum = ps; acc.part_max = pmx;
+      acc.fused_iq = (const float2*)iq_stream; acc.fused_hop = hop; acc.fused_nseg = nseg;
+      acc.fused_tw = f32 ? (const void*)p->d_twh32 : (const void*)p->d_twh64;
+      acc.fused_y = p->scratch2; acc.fused_cnt = p->d_sched + 18;
+      L.acc = acc;
+      if (f32) {
+        FftArgs<float> t{};
+        t.n_frames = nseg * 16; t.window = p->d_win32; t.tw = p->d_twin32; t.ep = make_epi(p, nullptr, nullptr);
+        e = launch_wl_f32(kEpiDb, t, L, p->stream, nullptr, false);
+      } else {
+        FftArgs<double> t{};
+        t.n_frames = nseg * 16; t.window = p->d_win64; t.tw = p->d_twin64; t.ep = make_epi(p, nullptr, nullptr);
+        e = launch_wl_f64(kEpiDb, t, L, p->stream, nullptr, false);
+      }
+      if (e != cudaSuccess) return fail(TDSA_ERR_CUDA, "welch fused launch failed: %s", cudaGetErrorString(e));
+      const double scale = (p->mode == TDSA_MODE_PSD) ? 1.0 / (p->fs * (double)n) : 1.0;
+      welch_sub_finish_kernel<<<65536 / 256, 256, 0, p->stream>>>(ps, pmx, grid, nseg, scale, p->floor, p->mode, avg_db, peak_db,
+                                                                  p->d_sched + 18 + 2 * groups);
+      count_launch();
+      CK(cudaGetLastError());
+      return TDSA_OK;
+    }
+  }
+  // 65536-point segments, default: two launches: one radix-16 head pass over every segment (big_head_wl_kernel: windowed samples ->
   // sixteen 4096-point sub-transform inputs per segment, complex T, in the tail's thread order), then ONE launch of the
   // warp-local kernel over all 16 * nseg sub-transforms with the Welch sum and peak in tensor memory (kAccSub).  The
   // intermediate goes through HBM once each way (16 B/point in float64) under the tail's arithmetic; no linear rows.
@@ -1025,7 +1082,7 @@ int tdsa_welch(tdsa_handle_t p, const void* iq_stream, int64_t n_samples, int64_
     }
     const double scale = (p->mode == TDSA_MODE_PSD) ? 1.0 / (p->fs * (double)n) : 1.0;
     welch_sub_finish_kernel<<<65536 / 256, 256, 0, p->stream>>>(ps, pmx, grid * (int)n_chunks, nseg, scale, p->floor, p->mode,
-                                                                avg_db, peak_db);
+                                                                avg_db, peak_db, nullptr);
     count_launch();
     CK(cudaGetLastError());
     return TDSA_OK;

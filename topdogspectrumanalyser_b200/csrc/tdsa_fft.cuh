@@ -531,16 +531,18 @@ template <typename T> struct FftArgs {
 // Phase time stamps of the first 32 frames of every warp: dbg[((block*8 + warp)*32 + it)*16 + i] = clock64,
 // and the SM id of each block behind them (tools/phase_timing.py reads the dump).
 #ifdef TDSA_DEBUG_TIMING
-#define TDSA_STAMP(i)                                                                                         \
+#define TDSA_STAMP_AT(i, it_)                                                                                  \
   do {                                                                                                        \
-    if ((threadIdx.x & 31) == 0 && a.dbg != nullptr && it < 32 && blockDim.x == 256) {                        \
+    if ((threadIdx.x & 31) == 0 && a.dbg != nullptr && (it_) < 32 && blockDim.x == 256) {                     \
       long long c_;                                                                                           \
       asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_)::"memory");                                            \
-      a.dbg[(((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32 + it) * 16 + (i)] = c_;                      \
+      a.dbg[(((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32 + (it_)) * 16 + (i)] = c_;                   \
     }                                                                                                         \
   } while (0)
+#define TDSA_STAMP(i) TDSA_STAMP_AT(i, it)
 #else
 #define TDSA_STAMP(i) do {} while (0)
+#define TDSA_STAMP_AT(i, it_) do {} while (0)
 #endif
 
 // ---- named barriers (ids 1..4; id 0 is __syncthreads) ---------------------------------------

@@ -40,12 +40,22 @@
 
 namespace tdsa {
 
-enum : int { kAccSum = 1, kAccMax = 2, kAccMin = 4, kAccGroup = 8, kAccRows = 16, kAccSub = 32 };
+enum : int { kAccSum = 1, kAccMax = 2, kAccMin = 4, kAccGroup = 8, kAccRows = 16, kAccSub = 32, kAccFused = 64 };
 // kAccSub (tail of the 65536-point Welch path, tdsa_big.cuh): the "frames" are the sixteen 4096-point sub-transforms
 // of each segment, already windowed, in complex T and in thread order ([frame][j][tid], written by big_head_wl_kernel).
 // No window, no TMA staging: every thread loads its sixteen values with coalesced 16-byte (float64) loads.  CTA b only
 // takes sub-transforms of class b % 16 (sub-transform s holds the bins k = s mod 16), so that its TMEM accumulators
 // see one set of bins for the whole launch; each class has its own claim counter (sched.next[2 + s]).
+//
+// kAccFused (with kAccSub): the head pass runs inside the same kernel, so that the intermediate never leaves the L2.
+// The grid is cut into groups of sixteen CTAs (group g = blockIdx / 16, class s = blockIdx % 16); group g owns the
+// segments g, g + G, g + 2G, ... completely: for a segment, CTA (g, s) first computes column block s of the head pass
+// (samples 256 s + t + 4096 j: window, radix 16, twiddle W_65536^(c q)) and writes its 256 values of each of the sixteen
+// sub-transforms into the group's ring of kFusedRing segments; once all sixteen CTAs of the group have done so it transforms
+// sub-transform s.  The head of segment i + 1 is issued BEFORE the tail of segment i, so the group's two counters
+// (heads done, tails done; release / acquire through global memory) are normally already satisfied when they are
+// looked at.  All CTAs must be co-resident (two per SM); a spin that does not end sets an error word instead of hanging.
+// Measured slower than head and tails as two launches (see welch_fused_enabled in tdsa_api.cu): opt-in.
 constexpr int kMaxPeers = 8;
 
 // arguments of the accumulating epilogue
@@ -63,6 +73,13 @@ struct WlAcc {
   float* peer_rows[kMaxPeers] = {};
   int n_peers = 0;
   int64_t peer_row0 = 0;
+  // kAccFused: the head pass' inputs and the groups' rings / counters
+  const float2* fused_iq = nullptr; // sample stream
+  int64_t fused_hop = 0;            // samples between segment starts
+  int64_t fused_nseg = 0;
+  const void* fused_tw = nullptr;   // complex T [16][4096]: W_65536^(c q)
+  void* fused_y = nullptr;          // complex T [groups][kFusedRing][16 q][16 j][256]
+  int* fused_cnt = nullptr;         // [groups][2] {heads done, tails done}, then one error word at [2 * groups]
   int group = 1;                    // frames per claimed unit (kAccGroup: frames per group)
   int64_t only_row = -1;            // kAccRows: >= 0 stores the dB row of this frame only (at row 0), -1 stores every row
 };
@@ -131,7 +148,12 @@ struct WlSched {
   int* next;       // next unclaimed unit (frame, or group of frames); kAccSub: next[2 + s] = next segment of class s
   int* done;       // CTAs that have left the frame loop
 };
-constexpr int kWlSchedWords = 2 + 16;
+#ifndef TDSA_FUSED_RING
+#define TDSA_FUSED_RING 3
+#endif
+constexpr int kFusedRing = TDSA_FUSED_RING;   // segments per group ring: the head runs one segment ahead, the ring gives the slack
+constexpr int kFusedMaxGroups = 32;     // fused mode: group counters live in the scheduler block
+constexpr int kWlSchedWords = 128;      // {next, done}, 16 class counters, fused mode: [18, 18 + 2 * groups] group counters + error word
 
 // W32^j = exp(-2 pi i j / 32), j = 0..15 (pass-A pre-twiddles of the half-bin engine); j is a compile-time constant
 // at every use (unrolled loops), so these fold to immediates
@@ -200,7 +222,8 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
   // tensor memory per warp (one lane per thread): 64 accumulator columns (ACC) and / or 32 window columns (WIN_TMEM);
   // 2 * NB warps share a lane quarter, each with its own column range
   constexpr bool kWinTmem = TDSA_WL_WIN_TMEM && sizeof(T) == 8 && NB == 1 && TWMODE != 1;
-  constexpr int kTmemPerWarp = (ACC != 0 ? 64 : 0) + (kWinTmem ? 32 : 0);
+  constexpr int kFusedWinCols = (ACC & kAccFused) ? 16 * (int)sizeof(T) / 4 : 0;     // fused head: its window values
+  constexpr int kTmemPerWarp = (ACC != 0 ? 64 : 0) + (kWinTmem ? 32 : 0) + kFusedWinCols;
   constexpr int kTmemNeed = kTmemPerWarp * 2 * NB;
   constexpr int kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
   constexpr bool kUseTmem = kTmemPerWarp != 0;
@@ -226,7 +249,9 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
   const CT* twe = a.tw + e * kWlTwPerEngine;                // this engine's tables
 
   constexpr bool SUB = (ACC & kAccSub) != 0;
+  constexpr bool FUSED = (ACC & kAccFused) != 0;
   static_assert(!SUB || (NB == 1 && !HAS_DC && (ACC & (kAccGroup | kAccRows)) == 0), "sub-transform tail: one engine, accumulate only");
+  static_assert(!FUSED || (SUB && TDSA_WL_SPLIT_B2), "the fused head needs the sub-transform tail and its split barrier");
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < (SUB ? 0 : NSTAGE); ++s) {
@@ -302,7 +327,8 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     }
   };
   if (tid == 0) {
-    if constexpr (SUB) {
+    if constexpr (FUSED) {
+    } else if constexpr (SUB) {
       slot[0] = next_frame();
     } else {
 #pragma unroll
@@ -342,6 +368,129 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     tmem_st16(tacc + 48, z);
     tmem_wait_st();
   }
+  // ---- fused head pass (kAccFused) -------------------------------------------------------------------------------
+  const int f_cls = (int)(blockIdx.x & 15), f_grp = (int)(blockIdx.x >> 4), f_ngrp = (int)(gridDim.x >> 4);
+  int f_nit = 0;                                            // segments this CTA's group owns
+  CT* f_ring = nullptr;
+  int *f_hcnt = nullptr, *f_tcnt = nullptr, *f_err = nullptr;
+  volatile int* f_dead = reinterpret_cast<volatile int*>(smem_raw + W::EX_BYTES + 100);
+  const int f_col = 256 * f_cls + r + 16 * c;               // this thread's column of the segment (tail thread order)
+  // staging of the head's samples [16 j][272 float2] behind the tail's shared memory: natural column t at
+  // (t & 15) + 17 (t >> 4), filled by cp.async one segment ahead
+  float2* f_stage = reinterpret_cast<float2*>(smem_raw + W::smem_bytes(0));
+  const uint32_t f_put = base_u32 + (uint32_t)W::smem_bytes(0) + (uint32_t)((tid & 15) + 17 * (tid >> 4)) * 8u;
+  auto f_fetch = [&](int64_t seg) {                          // samples 256 f_cls + tid + 4096 j of segment seg, coalesced
+    const float2* src = acc.fused_iq + seg * acc.fused_hop + 256 * f_cls + tid;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(f_put + (uint32_t)(j * 272 * 8)), "l"(src + 4096 * j) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if constexpr (FUSED) {
+    f_nit = f_grp < acc.fused_nseg ? (int)((acc.fused_nseg - f_grp + f_ngrp - 1) / f_ngrp) : 0;
+    if (f_nit > 0) f_fetch(f_grp);
+    // the window values of this thread's column live in tensor memory (behind the accumulators): no registers, no
+    // shared memory, and no sector-inefficient permuted global reads per segment
+    const uint32_t twn = tacc + 64;
+#pragma unroll
+    for (int part = 0; part < kFusedWinCols / 16; ++part) {
+      uint32_t u[16];
+      if constexpr (sizeof(T) == 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const double wv = (double)a.window[f_col + 4096 * (8 * part + i)];
+          u[2 * i] = (uint32_t)__double2loint(wv); u[2 * i + 1] = (uint32_t)__double2hiint(wv);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) u[i] = __float_as_uint((float)a.window[f_col + 4096 * i]);
+      }
+      tmem_st16(twn + 16 * part, u);
+    }
+    tmem_wait_st();
+    f_ring = reinterpret_cast<CT*>(acc.fused_y) + (int64_t)f_grp * kFusedRing * 65536;
+    f_hcnt = acc.fused_cnt + 2 * f_grp; f_tcnt = f_hcnt + 1; f_err = acc.fused_cnt + 2 * f_ngrp;
+    if (tid == 0) *f_dead = 0;
+    __syncthreads();
+  }
+  // thread 0 polls the group counter (acquire); an endless wait (CTAs not co-resident) ends in the error word
+  auto f_wait = [&](const int* cnt, int target) {
+    if (tid == 0 && *f_dead == 0) {
+      long long polls = 0;
+      for (;;) {
+        int v, e;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+        if (v >= target) break;
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(e) : "l"(f_err) : "memory");
+        if (e != 0 || ++polls > (1ll << 24)) { *f_err = 1; *f_dead = 1; break; }
+      }
+    }
+    __syncthreads();
+  };
+  // head pass of the staged segment for column block f_cls into slot `buf` of the group's ring, then the fetch of
+  // segment `seg_after` (< 0: none).  The stores are NOT fenced here: the count that publishes them is added at the Y
+  // barrier of the following tail, when they have long been performed (a fence right here waited ~1 us for them).
+  int f_it = 0;                                              // iteration the head pass is charged to (time stamps)
+  auto f_head = [&](int buf, int64_t seg_after) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                         // everybody's copies of this segment have landed
+    TDSA_STAMP_AT(11, f_it);
+    T hr[16], hi[16];
+    {
+      T wv[16];
+      const uint32_t twn = tacc + 64;
+#pragma unroll
+      for (int part = 0; part < kFusedWinCols / 16; ++part) {
+        uint32_t u[16];
+        tmem_ld16(twn + 16 * part, u);
+        if constexpr (sizeof(T) == 8) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) wv[8 * part + i] = (T)__hiloint2double((int)u[2 * i + 1], (int)u[2 * i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) wv[i] = (T)__uint_as_float(u[i]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float2 v = f_stage[j * 272 + r + 17 * c];
+        hr[j] = (T)v.x * wv[j]; hi[j] = (T)v.y * wv[j];
+      }
+    }
+    __syncthreads();                                         // the staging area is free again
+    TDSA_STAMP_AT(12, f_it);
+    if (seg_after >= 0) f_fetch(seg_after);
+    dft16<T>(hr, hi);
+    const CT* htw = reinterpret_cast<const CT*>(acc.fused_tw) + f_col;
+    T wr[16], wi[16];
+    { const CT x = htw[1 * 4096]; wr[1] = x.x; wi[1] = x.y; }
+    { const CT x = htw[4 * 4096]; wr[4] = x.x; wi[4] = x.y; }
+    wr[2] = wr[1]; wi[2] = wi[1]; cmul<T>(wr[2], wi[2], wr[1], wi[1]);
+    wr[3] = wr[2]; wi[3] = wi[2]; cmul<T>(wr[3], wi[3], wr[1], wi[1]);
+    wr[8] = wr[4]; wi[8] = wi[4]; cmul<T>(wr[8], wi[8], wr[4], wi[4]);
+    wr[12] = wr[8]; wi[12] = wi[8]; cmul<T>(wr[12], wi[12], wr[4], wi[4]);
+    CT* dst = f_ring + ((int64_t)(buf * 16) * 16 + f_cls) * 256 + tid;   // [buf][q][j = f_cls][tid]
+    TDSA_STAMP_AT(13, f_it);
+    dst[0] = mk<T>(hr[0], hi[0]);
+#pragma unroll
+    for (int q = 1; q < 16; ++q) {
+      T xr = wr[q & 3], xi = wi[q & 3];
+      if ((q & 3) == 0) { xr = wr[q]; xi = wi[q]; }
+      else if (q >= 4) cmul<T>(xr, xi, wr[q & ~3], wi[q & ~3]);
+      cmul<T>(hr[q], hi[q], xr, xi);
+      dst[(int64_t)q * 4096] = mk<T>(hr[q], hi[q]);
+    }
+    TDSA_STAMP_AT(14, f_it);
+  };
+  bool f_head_pending = false;                               // a head pass whose count has not been added yet
+  if constexpr (FUSED) {
+    if (f_nit > 0) {
+      f_head(0, f_nit > 1 ? (int64_t)f_grp + f_ngrp : (int64_t)-1);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicAdd(f_hcnt, 1);
+    }
+  }
   const bool mag20 = a.ep.mode == kModeMag20;
   // swizzled offset of (row m = c + 16 j, column r) inside a staged 4096-sample block: 128-byte rows, 16-byte chunk
   // index XOR (row & 7); r >> 1 == w, r & 1 == h, (c + 16 j) & 7 == c & 7
@@ -375,10 +524,23 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     };
     if constexpr (TDSA_WL_EARLY && NB == 1) { if (tid == 0) fnext = next_frame(); }
     TDSA_STAMP(0);
+    if constexpr (FUSED) {
+      if (it >= f_nit) break;
+      f_it = it;
+      TDSA_STAMP(10);
+      if (it + 1 < f_nit) {
+        // head of the next segment first; its ring slot was last read by the tails of segment it + 1 - kFusedRing
+        if (it + 2 > kFusedRing) f_wait(f_tcnt, 16 * (it + 2 - kFusedRing));
+        f_head((it + 1) % kFusedRing, it + 2 < f_nit ? (int64_t)f_grp + (int64_t)(it + 2) * f_ngrp : (int64_t)-1);
+        f_head_pending = true;
+      }
+      TDSA_STAMP(15);
+      f_wait(f_hcnt, 16 * (it + 1));                         // all sixteen column blocks of this segment are in the ring
+    }
     if constexpr (!SUB) mbar_wait(ctrl_u32 + 8 * stg, (uint32_t)((it / NSTAGE) & 1));
     // written by thread 0 before it armed / completed the barrier (SUB: before the previous frame's Y barrier)
-    const int f = SUB ? slot[it & 1] : slot[stg];
-    if (f >= a.n_frames) break;
+    const int f = FUSED ? 0 : (SUB ? slot[it & 1] : slot[stg]);
+    if (!FUSED && f >= a.n_frames) break;
 #ifdef TDSA_DEBUG_TIMING
     if (it == 0 && tid == 0 && a.dbg != nullptr) {
       unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -399,7 +561,8 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       const unsigned char* src = stage_ptr + (size_t)stg * W::STAGE_BYTES + stage_off;
       float2 v[SUB ? 1 : 16];
       if constexpr (SUB) {
-        const CT* y = a.in_ct + (int64_t)f * 4096 + tid;     // [frame][j][tid]: 256 consecutive values per j
+        const CT* y = FUSED ? f_ring + (int64_t)((it % kFusedRing) * 16 + f_cls) * 4096 + tid
+                            : a.in_ct + (int64_t)f * 4096 + tid;     // [frame][j][tid]: 256 consecutive values per j
 #pragma unroll
         for (int j = 0; j < 16; ++j) { const CT x = __ldcg(y + j * 256); re[j] = x.x; im[j] = x.y; }
       } else {
@@ -448,6 +611,7 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       if (l == 0) mbar_arrive(ctrl_u32 + 32 + 8 * stg);
     }
     if constexpr (TDSA_WL_EARLY && NB == 1) { if (tid == 0) try_refill(false); }
+    else if constexpr (FUSED) { }
     else if constexpr (SUB) { if (tid == 0) slot[(it + 1) & 1] = next_frame(); }   // read by everyone after the Y barrier
     else { if (tid == 0) fnext = next_frame(); }             // consumed after the barrier below
     TDSA_STAMP(3);
@@ -495,11 +659,16 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
 #pragma unroll
     for (int q = 0; q < 16; ++q) reg[c + 17 * q] = mk<T>(re[q], im[q]);
     TDSA_STAMP(5);
+    if constexpr (FUSED) { if (f_head_pending) __threadfence(); }   // release the head pass' ring stores (performed by now)
     engine_sync();                                           // all sixteen Y_r complete; every warp has left this stage
     TDSA_STAMP(6);
     // Measured (round 2): letting the LAST warp to finish its staged reads refill the stage (shared-memory counter, frame
     // claimed at the top of the iteration) instead of thread 0 after this barrier was slower: 78.0 -> 83.9 us (f32),
     // 135.2 -> 139.4 us (f64) at N = 4096, 206.8 -> 219.1 us (f64) at N = 8192.
+    if constexpr (FUSED) {                                    // every thread's ring loads were consumed before the barrier
+      if (tid == 0) { if (f_head_pending) atomicAdd(f_hcnt, 1); atomicAdd(f_tcnt, 1); }
+      f_head_pending = false;
+    }
     if (tid == 0 && !SUB) {
       if constexpr (TDSA_WL_EARLY && NB == 1) {
         try_refill(true);
@@ -682,6 +851,9 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       if constexpr (SUB) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) sched.next[2 + i] = 0;
+      }
+      if constexpr (FUSED) {                                 // the error word stays
+        for (int i = 0; i < 2 * (int)(gridDim.x >> 4); ++i) acc.fused_cnt[i] = 0;
       }
       *sched.done = 0;
       __threadfence();

@@ -266,7 +266,9 @@ cudaError_t launch_wl_final(const FftArgs<T>& a, const CUtensorMap& tmap, const 
   constexpr int kMinCtas = NB == 1 ? 2 : 1;
   static const size_t kExtraSmem = [] { const char* e = getenv("TDSA_DEBUG_EXTRA_SMEM"); return e ? (size_t)atol(e) : (size_t)0; }();
   constexpr bool kSub = (ACC & kAccSub) != 0;                  // direct loads: no staging buffers
-  const size_t kSmem = std::min<size_t>(WlPlan<T, NB>::smem_bytes(kSub ? 0 : kStages) + kExtraSmem, 227 * 1024);
+  constexpr bool kFused = (ACC & kAccFused) != 0;              // + the head pass' sample staging [16][272] float2
+  const size_t kSmem = std::min<size_t>(WlPlan<T, NB>::smem_bytes(kSub ? 0 : kStages) + (kFused ? 16 * 272 * 8 : 0) + kExtraSmem,
+                                        227 * 1024);
   auto kern = fft_wl_kernel<T, Epi, kTwMode, kStages, HAS_DC, kMinCtas, (sizeof(T) == 4 ? TDSA_WL_TWB_BASE_F32 : 0) != 0, NB, ACC>;
   static int occ_of[kMaxDevices] = {};          // 0 = not queried on that device yet
   if (device < 0 || device >= kMaxDevices) return cudaErrorInvalidDevice;
@@ -288,7 +290,8 @@ cudaError_t launch_wl_final(const FftArgs<T>& a, const CUtensorMap& tmap, const 
   const int64_t n_units = a.n_frames / group;
   int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_units, (int64_t)sm_count * occ));
   if constexpr (kSub)                                          // CTA b serves class b % 16: whole sets of sixteen classes
-    grid = 16 * (int)std::max<int64_t>(1, std::min<int64_t>(a.n_frames / 16, (int64_t)sm_count * occ / 16));
+    grid = 16 * (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(a.n_frames / 16, (int64_t)sm_count * occ / 16),
+                                                            kFused ? kFusedMaxGroups : (1 << 20)));
   if (info) {
     info->threads = kThreads; info->smem = (int)kSmem; info->ctas_per_sm = occ; info->grid = grid;
     info->stages = kStages; info->logr = 4;
@@ -335,6 +338,7 @@ constexpr int kAccHold = kAccMax | kAccMin | kAccRows;         // dB rows + max/
 constexpr int kAccWelch = kAccSum | kAccMax;                   // Welch mean + peak
 constexpr int kAccGroupMean = kAccSum | kAccGroup;             // one dB row per group of frames
 constexpr int kAccWelchSub = kAccSum | kAccMax | kAccSub;      // Welch mean + peak over the sub-transforms of 65536-point segments
+constexpr int kAccWelchFused = kAccWelchSub | kAccFused;       // ... with the head pass in the same kernel (intermediate stays in L2)
 
 template <typename T>
 cudaError_t launch_wl_impl(int epi, const FftArgs<T>& a, const WlLaunch& L, cudaStream_t s, LaunchInfo* info, bool dry) {
@@ -353,6 +357,7 @@ cudaError_t launch_wl_impl(int epi, const FftArgs<T>& a, const WlLaunch& L, cuda
       case kAccWelch: if (!dc) TDSA_WL_GO(EpiDb, false, 1, kAccWelch); break;
       case kAccGroupMean: if (!dc) TDSA_WL_GO(EpiDb, false, 1, kAccGroupMean); break;
       case kAccWelchSub: if (!dc) TDSA_WL_GO(EpiDb, false, 1, kAccWelchSub); break;
+      case kAccWelchFused: if (!dc) TDSA_WL_GO(EpiDb, false, 1, kAccWelchFused); break;
       default: break;
     }
   } else if (L.nb == 2 && !dc) {
@@ -369,7 +374,7 @@ inline bool wl_supported(int nb, int epi, int acc_flags, bool dc) {
   if (nb == 1) {
     if (acc_flags == 0) return epi == kEpiDb || epi == kEpiLinear;
     return !dc && (acc_flags == kAccAvg || acc_flags == kAccHold || acc_flags == kAccWelch || acc_flags == kAccGroupMean ||
-                   acc_flags == kAccWelchSub);
+                   acc_flags == kAccWelchSub || acc_flags == kAccWelchFused);
   }
   if (nb == 2 && !dc) return acc_flags == kAccGroupMean;
   return false;

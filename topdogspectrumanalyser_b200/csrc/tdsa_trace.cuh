@@ -173,9 +173,14 @@ __global__ void __launch_bounds__(256) welch_sub_clear_kernel(double* __restrict
 // holds sub-transform s = b % 16, whose local bin kl is bin s + 16 kl of the segment spectrum
 __global__ void __launch_bounds__(256) welch_sub_finish_kernel(const double* __restrict__ part_sum, const float* __restrict__ part_max,
                                                               int n_parts, int64_t n_seg, double scale, double floor, int mode,
-                                                              float* __restrict__ avg_db, float* __restrict__ peak_db) {
+                                                              float* __restrict__ avg_db, float* __restrict__ peak_db,
+                                                              const int* __restrict__ err) {
   const int t = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (t >= 65536) return;
+  if (err != nullptr && *err != 0) {   // the fused kernel gave up waiting for its group (CTAs not co-resident): no result
+    avg_db[t] = __int_as_float(0x7fc00000); peak_db[t] = __int_as_float(0x7fc00000);
+    return;
+  }
   const int kl = t & 4095, s = t >> 12;
   double sum = 0.0;
   float m = -INFINITY;

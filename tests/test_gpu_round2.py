@@ -136,10 +136,20 @@ def test_two_engine_8192_kernel(dev, parity_log, prec, tol):
         classic = plan.psd_db(x).cpu().numpy().astype(np.float64)
         assert np.abs(classic - want).max() <= tol
         assert np.abs(classic - got).max() <= (2e-5 if prec == "f64" else tol)
+        lin = plan.power_linear(x[:40]).cpu().numpy()            # float64 linear rows (the general trace path's input)
+        assert np.abs(10 * np.log10(lin + O.POWER_LOG_FLOOR) - want[:40]).max() <= tol
         plan.close()
     plan = SpectrumPlan(n, "hanning", mode="psd", fs=20e6, precision=prec, device=dev)
     want = O.power_db_batch(iq[:64], O.make_window("hanning", n), O.MODE_PSD, fs=20e6)
     got = plan.group_avg_db(x[:64].view(64, 1, n)).cpu().numpy()
+    assert np.abs(got - want).max() <= tol
+    plan.close()
+    # overlapping frames of a flat stream (stride 1000 samples) in mag20 mode
+    stream = synth.cfg3_stream(n_samples=8192 + 1000 * 36, seed=507)
+    frames = np.lib.stride_tricks.as_strided(stream, shape=(37, n), strides=(1000 * stream.itemsize, stream.itemsize))
+    want = O.power_db_batch(np.ascontiguousarray(frames), O.make_window("hanning", n), O.MODE_MAG20)
+    plan = SpectrumPlan(n, "hanning", mode="mag20", precision=prec, device=dev)
+    got = plan.psd_db(torch.from_numpy(stream).to(dev), n_frames=37, frame_stride=1000).cpu().numpy()
     assert np.abs(got - want).max() <= tol
     plan.close()
 

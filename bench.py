@@ -253,6 +253,39 @@ CFG4 = {"bands": 300, "frames": 16, "n_fft": 8192, "band_hz": 20e6}
 _CFG4_KEEP = {}
 
 
+def measure_cfg3(dev, reps=5):
+    """Config 3 at full size on this rank's GPU: 2^26 samples, 65536-point Welch, hop 32768 (2047 segments) -> mean and
+    peak rows.  Input made on the device (noise + two tones); parity of this path at this size is a -m gpu test."""
+    import torch
+    from topdogspectrumanalyser_b200.engine import SpectrumPlan
+    n, hop, total = 65536, 32768, 1 << 26
+    g = torch.Generator(device=dev); g.manual_seed(3)
+    x = torch.randn(total, 2, generator=g, device=dev, dtype=torch.float32).mul_(0.05)
+    t = torch.arange(total, device=dev, dtype=torch.float64)
+    for k, a in ((0.1234, 0.5), (-0.3101, 0.05)):
+        ph = (2 * np.pi * k) * t
+        x[:, 0] += (a * torch.cos(ph)).float(); x[:, 1] += (a * torch.sin(ph)).float()
+    del t
+    stream = torch.view_as_complex(x)
+    nseg = (total - n) // hop + 1
+    out = {"workload": f"cfg3: {total} samples, {n}-point segments, hop {hop}: {nseg} segments -> avg + peak rows", "segments": nseg}
+    for prec in ("f64", "f32"):
+        plan = SpectrumPlan(n, precision=prec, device=dev)
+        for _ in range(2):
+            avg, peak = plan.welch(stream, hop)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            avg, peak = plan.welch(stream, hop)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[prec] = {"ms": ms, "input_samples_per_s": total / (ms * 1e-3), "segment_samples_per_s": nseg * n / (ms * 1e-3),
+                     "finite": bool(torch.isfinite(avg).all() and torch.isfinite(peak).all()),
+                     "peak_bin": int(torch.argmax(avg))}
+        plan.close()
+    return out
+
+
 def measure_cfg4(dev, world, rank, precision, reps=20):
     import torch
     import torch.distributed as dist
@@ -389,6 +422,7 @@ def main():
     ap.add_argument("--min-seconds", type=float, default=0.25,
                     help="also run the headline launch back to back for at least this long (sustained clocks); 0 = skip")
     ap.add_argument("--no-cfg4", action="store_true", help="skip the config-4 (wideband stitch) object")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the config-3 (65536-point Welch) object")
     ap.add_argument("--no-other-sizes", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -592,6 +626,12 @@ def main():
             cfg4 = measure_cfg4(dev, world, rank, args.precision)
         except Exception as e:                              # noqa: BLE001 - the headline line must still be printed
             cfg4 = {"error": repr(e)[:300]}
+    cfg3 = None
+    if not args.no_cfg3 and rank == 0:
+        try:
+            cfg3 = measure_cfg3(dev)
+        except Exception as e:                              # noqa: BLE001
+            cfg3 = {"error": repr(e)[:300]}
     peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     traffic = None
     try:
@@ -651,6 +691,7 @@ def main():
                     "host_placement": placement, "host_link_ceiling": host_link},
             "sustained": sustained,
             "other_sizes": other_sizes,
+            "cfg3": cfg3,
             "cfg4": cfg4,
             "gpu_launches": main_run["launches"],
             "clocks": main_run["clocks"],

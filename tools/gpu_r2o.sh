@@ -13,4 +13,4 @@ PY
 timeout 600 python bench.py --impl reference --steps 5 --warmup 2 2>&1 | tail -1 | cut -c 1-300
 timeout 900 python tools/configs_bench.py > gpurun_out/configs_o.jsonl 2> gpurun_out/configs_o.err; echo "configs rc=$?"; cut -c 1-260 gpurun_out/configs_o.jsonl
 timeout 600 python tools/acc_bench.py 2>&1 | tee gpurun_out/acc_bench_o.jsonl | cut -c 1-200
-timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:fft_wl -s 3 -c 1 -f -o gpurun_out/r02_wl_f64_final python bench.py --precision f64 --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --min-seconds 0 --no-cfg4 --no-other-sizes > gpurun_out/ncu_wl_f64_final.log 2>&1; echo "ncu rc=$?"
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:fft_wl -s 3 -c 1 -f -o gpurun_out/r02_wl_f64_final python bench.py --precision f64 --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --min-seconds 0 --no-cfg4 --no-cfg3 --no-other-sizes > gpurun_out/ncu_wl_f64_final.log 2>&1; echo "ncu rc=$?"

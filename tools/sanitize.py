@@ -38,8 +38,20 @@ for prec in ("f64", "f32"):
     plan8.group_avg_db(g[:, :1].contiguous())
     torch.cuda.synchronize(); plan8.close()
     print("ok round-2 kernels", prec)
-plan = SpectrumPlan(65536, device=dev)
-plan.welch(torch.from_numpy(synth.cfg3_stream(1 << 18)).to(dev), 32768)
+# config 3: head kernel (cp.async staging) + warp-local tails (direct loads, per-class claims); the fused one-kernel variant
+# (group counters in global memory, L2 ring); the round-1 cluster kernel and two-kernel path
+s3 = torch.from_numpy(synth.cfg3_stream(65536 + 32768 * 20)).to(dev)
+for env in ({}, {"TDSA_WELCH_FUSED": "1"}, {"TDSA_WELCH_SUB": "0"}, {"TDSA_WELCH_SUB": "0", "TDSA_WELCH_CLUSTER": "0"}):
+    for k in ("TDSA_WELCH_FUSED", "TDSA_WELCH_SUB", "TDSA_WELCH_CLUSTER"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
+    for prec in ("f64", "f32"):
+        plan = SpectrumPlan(65536, precision=prec, device=dev)
+        a, pk = plan.welch(s3, 32768)
+        torch.cuda.synchronize(); plan.close()
+        print("ok cfg3", env, prec, float(a[0]), bool(torch.isfinite(a).all()))
+for k in ("TDSA_WELCH_FUSED", "TDSA_WELCH_SUB", "TDSA_WELCH_CLUSTER"):
+    os.environ.pop(k, None)
 rows = torch.randn(6, 4096, device=dev)
 st = TraceState(4096, dev); st.start_tare(); st.max_hold_enabled = True
 trace_update(rows, st, -1.0)

@@ -181,6 +181,24 @@ template <typename T> __device__ __forceinline__ T w32_msin(int j) {   // imagin
 #ifndef TDSA_WL_EPI_F32SQ
 #define TDSA_WL_EPI_F32SQ 0
 #endif
+// TDSA_WL_WIDEN_INT = 1 (float64): the staged float32 samples are widened to float64 with integer instructions (exponent
+// re-bias + mantissa shift; zero / denormal -> signed zero, inf / nan -> exponent all ones) instead of 32 F2F.F64.F32 per
+// thread and frame, which cost ~4 cycles each on the FP64 pipe (8 % of the pipe's time per frame).
+#ifndef TDSA_WL_WIDEN_INT
+#define TDSA_WL_WIDEN_INT 0
+#endif
+template <typename T> __device__ __forceinline__ T widen_sample(float x) { return (T)x; }
+#if TDSA_WL_WIDEN_INT
+template <> __device__ __forceinline__ double widen_sample<double>(float x) {
+  const uint32_t b = __float_as_uint(x);
+  const uint32_t ex = b & 0x7f800000u;
+  uint32_t hi = (b & 0x80000000u) | (((b & 0x7fffffffu) >> 3) + 0x38000000u);
+  uint32_t lo = b << 29;
+  if (ex == 0u) { hi = b & 0x80000000u; lo = 0u; }
+  if (ex == 0x7f800000u) hi |= 0x7ff00000u;
+  return __hiloint2double((int)hi, (int)lo);
+}
+#endif
 // last-pass base twiddles held in registers: 6 (w^1..w^3, w^4, w^8, w^12; 24 registers in float64) or 2 (w^1, w^4; the
 // other four bases by multiplication every frame: 16 registers fewer, 16 DFMA more)
 #ifndef TDSA_WL_TWL_BASE2
@@ -571,7 +589,7 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if constexpr (HAS_DC) { re[j] = (T)v[j].x - dcr; im[j] = (T)v[j].y - dci; }
-          else { re[j] = (T)v[j].x; im[j] = (T)v[j].y; }
+          else { re[j] = widen_sample<T>(v[j].x); im[j] = widen_sample<T>(v[j].y); }
         }
       }
       if constexpr (SUB) {

@@ -229,6 +229,13 @@ template <> __device__ __forceinline__ double widen_sample<double>(float x) {
 #ifndef TDSA_WL_SPLIT_B2
 #define TDSA_WL_SPLIT_B2 1
 #endif
+// TDSA_WL_SPLIT_ALL = 1: every thread arrives on the regions-free barrier; 0: lane 0 of each warp after a __syncwarp.  Same
+// speed (round 2: 128.9 / 77.8 us against 129.0 / 78.4 us), but compute-sanitizer's racecheck credits an mbarrier arrival to
+// the arriving thread only and reported the other lanes' last-pass reads against the next frame's team stores as WAR hazards
+// with the per-warp arrival (2.7 million reports on the config-3 workload, none with one arrival per thread); on.
+#ifndef TDSA_WL_SPLIT_ALL
+#define TDSA_WL_SPLIT_ALL 1
+#endif
 
 template <typename T, typename Epi, int TWMODE, int NSTAGE, bool HAS_DC, int MIN_CTAS, bool TWB_BASE, int NB, int ACC>
 __global__ void __launch_bounds__(256 * NB, MIN_CTAS)
@@ -276,7 +283,7 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       mbar_init(ctrl_u32 + 8 * s, 1);
       if constexpr (NB > 1 || TDSA_WL_EARLY) mbar_init(ctrl_u32 + 32 + 8 * s, 8 * NB);     // one arrival per warp
     }
-    if constexpr (TDSA_WL_SPLIT_B2 && NB == 1) mbar_init(ctrl_u32 + 24, 8);     // "regions free": one arrival per warp
+    if constexpr (TDSA_WL_SPLIT_B2 && NB == 1) mbar_init(ctrl_u32 + 24, TDSA_WL_SPLIT_ALL ? 256 : 8);     // "regions free": one arrival per warp
     fence_mbar_init();
   }
   for (int i = te; i < W::TW_SMEM; i += 256) tws[i] = twe[i];
@@ -703,8 +710,12 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       for (int j = 0; j < 16; ++j) { const CT x = col[j * REGION]; re[j] = x.x; im[j] = x.y; }
     }
     if constexpr (TDSA_WL_SPLIT_B2 && NB == 1) {
+#if TDSA_WL_SPLIT_ALL
+      mbar_arrive(ctrl_u32 + 24);
+#else
       __syncwarp();                                          // the warp's loads are ordered before its one arrival
       if (l == 0) mbar_arrive(ctrl_u32 + 24);
+#endif
     } else {
       engine_sync();                                         // regions may be overwritten by the next frame's pass A
     }

@@ -179,7 +179,14 @@ int tdsa_group_avg_db_peers(tdsa_handle_t h, const void* iq, int64_t n_groups, i
  * segments s = 0 .. floor((n_samples - n_fft)/hop), each transformed as kernel 1;
  * avg_db = 10*log10(mean_s |X_s|^2 + floor) (TraceAverager 'lin' with n >= nseg,
  * signal_processing.py:56-59), peak_db = fmax_s dB_s (display_data_processor.py:382).
- * Outputs are float32 [n_fft]. Uses plan-owned scratch; synchronous only w.r.t. the stream. */
+ * Outputs are float32 [n_fft]. Uses plan-owned scratch; synchronous only w.r.t. the stream.
+ * n_fft <= 4096: one launch of the warp-local kernel, sum and maximum of |X|^2 per bin in tensor memory.
+ * n_fft = 65536: a radix-16 head kernel writes the sixteen 4096-point sub-transform inputs of every segment (complex T,
+ * 16 B per point in float64: plan scratch of n_segments * 2^20 bytes, at most 2048 segments per pass), one launch of the
+ * warp-local kernel transforms them with the same tensor-memory state, a finish kernel un-permutes and takes the dB.
+ * Environment switches, read at every call, select the measured alternatives: TDSA_WELCH_FUSED=1 (head and tails in one
+ * kernel, intermediate in an L2-resident ring; NaN rows if its CTAs cannot all be resident), TDSA_WELCH_SUB=0 (round-1
+ * paths: the 16-CTA cluster kernel, or with TDSA_WELCH_CLUSTER=0 the two-kernel path through float64 linear rows). */
 int tdsa_welch(tdsa_handle_t h, const void* iq_stream, int64_t n_samples, int64_t hop, float* avg_db,
                float* peak_db);
 

@@ -104,6 +104,30 @@ def test_welch_65536_few_segments(dev, nseg, fused, monkeypatch):
     plan.close()
 
 
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_welch_65536_psd_blackman(dev, fused, monkeypatch, parity_log):
+    """PSD scaling (1 / (fs N)) and a different window through the config-3 path; second plan in float32 at 1e-3 dB."""
+    import torch
+    from topdogspectrumanalyser_b200.engine import SpectrumPlan
+    monkeypatch.setenv("TDSA_WELCH_FUSED", fused)
+    n, hop, fs = 65536, 20000, 20e6
+    stream = synth.cfg3_stream(n_samples=n + hop * 24 + 17, seed=77)
+    w = O.make_window("blackman", n)
+    nseg = (stream.shape[0] - n) // hop + 1
+    seg = np.lib.stride_tricks.as_strided(stream, shape=(nseg, n), strides=(hop * stream.itemsize, stream.itemsize))
+    p = O.linear_power_batch(np.ascontiguousarray(seg), w, workers=-1) / (fs * n)
+    want_avg = 10 * np.log10(p.mean(axis=0) + O.LOG_FLOOR)        # PSD mode: floor 1e-12 (rtl_samples.py:175-179)
+    want_peak = 10 * np.log10(p.max(axis=0) + O.LOG_FLOOR)
+    x = torch.from_numpy(stream).to(dev)
+    for prec, tol in (("f64", TOL_DB), ("f32", 1e-3)):
+        plan = SpectrumPlan(n, "blackman", mode="psd", fs=fs, precision=prec, device=dev)
+        avg, peak = plan.welch(x, hop)
+        ea = float(np.abs(avg.cpu().numpy() - want_avg).max()); ep = float(np.abs(peak.cpu().numpy() - want_peak).max())
+        parity_log(f"welch65536_psd_blackman_fused{fused}_{prec}", max(ea, ep), tol=tol, segments=nseg)
+        assert ea <= tol and ep <= tol, (prec, ea, ep)
+        plan.close()
+
+
 def test_cfg4_full_size_rows_and_grid(dev, parity_log):
     """300 sub-bands x 16 frames x 8192 points on one GPU: every dB row within 1e-4 dB, the 2 457 600-bin stitched grid
     bit-equal to the reference's argsort + np.interp (hackrf_sweep.py:150-166)."""

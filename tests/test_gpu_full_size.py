@@ -85,13 +85,15 @@ def test_cfg3_full_size_welch_all_paths(dev, parity_log):
 
 
 @pytest.mark.parametrize("fused", ["1", "0"])
-@pytest.mark.parametrize("nseg", [1, 3, 17, 40])
-def test_welch_65536_few_segments(dev, nseg, fused, monkeypatch):
-    """Fewer segments than groups / CTAs with no work / odd counts: the fused and the two-launch path at 1e-4 dB."""
+@pytest.mark.parametrize("nseg,hop", [(1, 16384), (3, 16384), (17, 16384), (40, 16384), (9, 12345)])
+def test_welch_65536_few_segments(dev, nseg, hop, fused, monkeypatch):
+    """Fewer segments than groups / CTAs with no work / odd counts: the fused and the two-launch path at 1e-4 dB.
+    The odd hop puts segment starts on 8-byte boundaries only (the head kernel's 8-byte cp.async staging instead of its
+    128-byte bulk copies)."""
     import torch
     from topdogspectrumanalyser_b200.engine import SpectrumPlan
     monkeypatch.setenv("TDSA_WELCH_FUSED", fused)
-    n, hop = 65536, 16384
+    n = 65536
     stream = synth.cfg3_stream(n_samples=n + hop * (nseg - 1) + 5, seed=11 + nseg)
     want_avg, want_peak, got_nseg = _welch_oracle(stream, n, hop)
     assert got_nseg == nseg

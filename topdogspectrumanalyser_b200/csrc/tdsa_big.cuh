@@ -114,9 +114,10 @@ __device__ __forceinline__ void cp_async_8(uint32_t dst_smem, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// shared memory of big_head_wl_kernel: two sample buffers [16 j][272 float2] (256 columns at pitch 17 per 16) and the
-// CTA's window slice [16 j][256] in T
-template <typename T> constexpr int head_wl_smem() { return 2 * 16 * 272 * 8 + 16 * 256 * (int)sizeof(T); }
+// shared memory of big_head_wl_kernel: two sample buffers [16 j][16 groups][18 float2] (sixteen columns per group, pitch 18:
+// 144-byte groups keep bulk-copy destinations 16-byte aligned), the CTA's window slice [16 j][256] in T, two mbarriers
+constexpr int kHeadPitch = 18, kHeadRow = 16 * kHeadPitch, kHeadBuf = 16 * kHeadRow * 8;
+template <typename T> constexpr int head_wl_smem() { return 2 * kHeadBuf + 16 * 256 * (int)sizeof(T) + 16; }
 
 // Head of the 65536-point Welch path whose tails run through fft_wl_kernel (kAccSub): like big_head1_kernel, one radix-16
 // over the samples c + 4096 j of a windowed segment and the post-twiddle W_N^(c q), but
@@ -127,13 +128,14 @@ template <typename T> constexpr int head_wl_smem() { return 2 * 16 * 272 * 8 + 1
 //     + tid] is sample n0 = r + 16 c' + 256 j of the 4096-point input, (r, c') = wl_thread_identity(tid).  The 256
 //     values of one (q, j) are exactly one CTA's columns (j = b), so head thread tid computes the column the tail's
 //     thread tid will want and stores are fully coalesced (dst[tid]);
-//   * the samples of the NEXT segment travel global -> shared by cp.async in natural column order (coalesced, no
-//     registers) while this segment is transformed; the permutation to the tail's order happens on the shared-memory
-//     read (pitch 17: at most two wavefronts per 8-byte warp read).
+//   * the samples of the NEXT segment travel global -> shared in natural column order while this segment is
+//     transformed; the permutation to the tail's order happens on the shared-memory read (groups of sixteen columns at
+//     pitch 18).  BULK: one 128-byte cp.async.bulk per thread and segment (sixteen columns of one row j), completion on an
+//     mbarrier (needs 16-byte aligned segment starts: even hop); otherwise sixteen 8-byte cp.async per thread.
 // Measured (round 2, 2047 segments): storing in permuted order cost 1.07 GB of DRAM fill reads in float32 (half
 // sectors); permuted global loads of samples and window doubled the L2 read traffic (7.4 GB, the L2 limit) at 704 us
 // (float64); see profiles/r02_experiments.md.
-template <typename T>
+template <typename T, bool BULK>
 __global__ void __launch_bounds__(256, 2) big_head_wl_kernel(const BigArgs<T> a) {
   using CT = typename CplxOf<T>::type;
   constexpr int64_t s0 = 4096;                              // columns per segment
@@ -144,10 +146,15 @@ __global__ void __launch_bounds__(256, 2) big_head_wl_kernel(const BigArgs<T> a)
   const int r = 2 * wl_w + ((wl_l >> 3) & 1), cp = (wl_l & 7) + 8 * (wl_l >> 4);
   const int c = 256 * b + r + 16 * cp;                      // this thread's column of the segment
   extern __shared__ __align__(16) unsigned char head_smem[];
-  float2* sbuf = reinterpret_cast<float2*>(head_smem);       // [2][16][272]
-  T* swin = reinterpret_cast<T*>(head_smem + 2 * 16 * 272 * 8);   // [16][256], thread order
+  float2* sbuf = reinterpret_cast<float2*>(head_smem);       // [2][16][16][18]
+  T* swin = reinterpret_cast<T*>(head_smem + 2 * kHeadBuf);   // [16][256], thread order
+  const uint32_t bar_u32 = smem_u32(head_smem) + (uint32_t)(2 * kHeadBuf + 16 * 256 * (int)sizeof(T));   // full[2]
+  if constexpr (BULK) {
+    if (tid == 0) { mbar_init(bar_u32, 1); mbar_init(bar_u32 + 8, 1); fence_mbar_init(); }
+  }
 #pragma unroll
   for (int j = 0; j < 16; ++j) swin[j * 256 + tid] = a.window[c + j * s0];
+  __syncthreads();
   // base twiddles kept in registers: float64 w^1 and w^4, float32 w^1..w^3, w^4, w^8, w^12
   constexpr bool kTwoBases = sizeof(T) == 8;
   T bwr[16], bwi[16];
@@ -157,25 +164,34 @@ __global__ void __launch_bounds__(256, 2) big_head_wl_kernel(const BigArgs<T> a)
   }
   const int64_t f_step = gridDim.x >> 4;
   int64_t f = blockIdx.x >> 4;
-  // copy side: thread tid moves natural column 256 b + tid to slot (tid & 15) + 17 (tid >> 4); read side: slot r + 17 c'
-  const uint32_t put_u32 = smem_u32(head_smem) + (uint32_t)((tid & 15) + 17 * (tid >> 4)) * 8u;
-  const float2* get = sbuf + r + 17 * cp;
+  // copy side: natural column t of row j goes to slot (t & 15) + 18 (t >> 4) of row j; read side: slot r + 18 c'
+  const float2* get = sbuf + r + kHeadPitch * cp;
   auto prefetch = [&](int64_t seg, int buf) {
-    const float2* src = a.iq + seg * a.frame_stride + 256 * b + tid;
+    if constexpr (BULK) {                                    // thread (j = tid >> 4, g = tid & 15): columns 16 g .. 16 g + 15 of row j
+      const uint32_t bar = bar_u32 + 8 * buf;
+      if (tid == 0) mbar_arrive_expect_tx(bar, 16 * 256 * 8);
+      const float2* src = a.iq + seg * a.frame_stride + s0 * (tid >> 4) + 256 * b + 16 * (tid & 15);
+      bulk_g2s(smem_u32(head_smem) + (uint32_t)(buf * kHeadBuf + (tid >> 4) * kHeadRow * 8 + (tid & 15) * kHeadPitch * 8), src, 128, bar);
+    } else {
+      const uint32_t put = smem_u32(head_smem) + (uint32_t)(buf * kHeadBuf + ((tid & 15) + kHeadPitch * (tid >> 4)) * 8);
+      const float2* src = a.iq + seg * a.frame_stride + 256 * b + tid;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) cp_async_8(put_u32 + (uint32_t)((buf * 16 + j) * 272 * 8), src + j * s0);
+      for (int j = 0; j < 16; ++j) cp_async_8(put + (uint32_t)(j * kHeadRow * 8), src + j * s0);
+    }
   };
   if (f < a.n_frames) prefetch(f, 0);
-  cp_async_commit();
+  if constexpr (!BULK) cp_async_commit();
   for (int it = 0; f < a.n_frames; f += f_step, ++it) {
-    cp_async_wait<0>();                                      // my copies of this segment have landed ...
+    if constexpr (BULK) mbar_wait(bar_u32 + 8 * (it & 1), (uint32_t)((it >> 1) & 1));   // this segment's samples have landed
+    else cp_async_wait<0>();                                 // my copies of this segment have landed ...
     __syncthreads();                                         // ... everybody's have, and the other buffer is no longer read
+    if constexpr (BULK) fence_proxy_async();                 // generic-proxy reads of that buffer before the async-proxy writes
     if (f + f_step < a.n_frames) prefetch(f + f_step, (it + 1) & 1);
-    cp_async_commit();
+    if constexpr (!BULK) cp_async_commit();
     T re[16], im[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float2 v = get[((it & 1) * 16 + j) * 272];
+      const float2 v = get[((it & 1) * 16 + j) * kHeadRow];
       const T wv = swin[j * 256 + tid];
       re[j] = (T)v.x * wv;
       im[j] = (T)v.y * wv;

@@ -14,17 +14,24 @@ cudaError_t launch_welch_cluster_f64(const WelchClusterArgs<double>& a, int clus
 namespace tdsa {
 cudaError_t launch_big_head_f64(const BigArgs<double>& a, int sm, cudaStream_t s, int passes) {
   if (passes == 0) {                                        // head for fft_wl_kernel tails (N = 65536)
-    static int occ_of[kMaxDevices] = {};
+    // staging by 128-byte bulk copies (needs 16-byte aligned segment starts) or by 8-byte cp.async.  Measured (round 2, head
+    // kernel alone, 2047 segments): float64 433 us against 575 us, float32 324 us against 290 us: bulk copies in float64 only;
+    // TDSA_HEAD_BULK=0 / 1 forces one variant
+    static const int bulk_env = [] { const char* e = getenv("TDSA_HEAD_BULK"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+    const bool bulk_ok = bulk_env < 0 ? sizeof(double) == 8 : bulk_env == 1;
+    const bool bulk = bulk_ok && ((uintptr_t)a.iq & 15) == 0 && (a.frame_stride & 1) == 0;
+    auto kern = bulk ? big_head_wl_kernel<double, true> : big_head_wl_kernel<double, false>;
+    static int occ_of[kMaxDevices][2] = {};
     const int dev = current_device();
-    if (occ_of[dev] == 0) {
-      cudaError_t ea = cudaFuncSetAttribute(big_head_wl_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, head_wl_smem<double>());
+    if (occ_of[dev][bulk] == 0) {
+      cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, head_wl_smem<double>());
       if (ea != cudaSuccess) return ea;
       int o = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, big_head_wl_kernel<double>, 256, head_wl_smem<double>()) != cudaSuccess) o = 2;
-      occ_of[dev] = std::max(o, 1);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, 256, head_wl_smem<double>()) != cudaSuccess) o = 2;
+      occ_of[dev][bulk] = std::max(o, 1);
     }
-    const int grid = 16 * (int)std::max<int64_t>(1, std::min<int64_t>(a.n_frames, (int64_t)sm * occ_of[dev] / 16));
-    big_head_wl_kernel<double><<<grid, 256, head_wl_smem<double>(), s>>>(a);
+    const int grid = 16 * (int)std::max<int64_t>(1, std::min<int64_t>(a.n_frames, (int64_t)sm * occ_of[dev][bulk] / 16));
+    kern<<<grid, 256, head_wl_smem<double>(), s>>>(a);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
   }

@@ -22,8 +22,8 @@ template <typename T> struct BigArgs {
 template <typename T>
 __global__ void __launch_bounds__(256, 2) big_head_kernel(const BigArgs<T> a) {
   using CT = typename CplxOf<T>::type;
-  extern __shared__ __align__(16) unsigned char smem_raw[];   // 4096 complex T
-  CT* ex = reinterpret_cast<CT*>(smem_raw);
+  extern __shared__ __align__(16) unsigned char big_smem[];   // 4096 complex T
+  CT* ex = reinterpret_cast<CT*>(big_smem);
   const int t = threadIdx.x;
   const int cl = t & 15, hi = t >> 4;
   const int64_t n = (int64_t)1 << a.log2n;

@@ -107,9 +107,8 @@ __global__ void __launch_bounds__(1024) find_peaks_snap_kernel(const float* __re
   int32_t* ord = val + 8192;                                  // rank in position order -> candidate slot (for neighbours)
   unsigned char* keep = reinterpret_cast<unsigned char*>(ord + 8192);
   __shared__ int s_n, s_best, s_kept;
-  __shared__ float s_bestv;
   const int t = threadIdx.x, nt = blockDim.x;
-  if (t == 0) { s_n = 0; s_best = -1; s_kept = 0; s_bestv = -INFINITY; }
+  if (t == 0) { s_n = 0; s_best = -1; s_kept = 0; }
   for (int i = t; i < 8192; i += nt) { key[i] = -INFINITY; val[i] = 0x7fffffff; }
   __syncthreads();
   // 1 + 2: local maxima (plateau midpoints) that reach the height

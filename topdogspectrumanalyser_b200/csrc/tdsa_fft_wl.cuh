@@ -723,7 +723,6 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     {
       T wr[16], wi[16];
       wr[0] = T(1); wi[0] = T(0);
-#pragma unroll
       if constexpr (TWMODE != 1 && TDSA_WL_TWL_BASE2 && sizeof(T) == 8) {
         wr[1] = twlr[1]; wi[1] = twli[1]; wr[4] = twlr[4]; wi[4] = twli[4];
         wr[2] = wr[1]; wi[2] = wi[1]; cmul<T>(wr[2], wi[2], wr[1], wi[1]);

@@ -1,0 +1,29 @@
+#!/bin/bash
+# two-engine N = 8192 group-mean kernel with the window in tensor memory: parity + timing
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_round2.py tests/test_gpu_state.py tests/test_gpu_full_size.py -q -x -k "8192 or group or cfg4 or wideband or two_engine" 2>&1 | tail -3
+cat > /tmp/tg.py <<'PY'
+import os, sys, torch
+sys.path.insert(0, os.getcwd())
+from topdogspectrumanalyser_b200 import synth
+from topdogspectrumanalyser_b200.engine import SpectrumPlan
+from topdogspectrumanalyser_b200.sweep import WidebandSweep
+dev = torch.device("cuda:0")
+def ev_time(fn, reps=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+g = torch.from_numpy(synth.cfg4_subbands(300, 16, 8192, seed=3)).to(dev)
+for prec in ("f64", "f32"):
+    plan = SpectrumPlan(8192, precision=prec, device=dev)
+    print(prec, "group mean 300x16x8192: %.1f us" % ev_time(lambda: plan.group_avg_db(g)), flush=True)
+    print(prec, "group mean 38x16x8192 (one of 8 ranks): %.1f us" % ev_time(lambda: plan.group_avg_db(g[:38])), flush=True)
+    plan.close()
+    sw = WidebandSweep(300, 20e6, 8192, 0.0, precision=prec, device=dev)
+    print(prec, "cfg4 sweep: %.1f us" % ev_time(lambda: sw.run(g)), flush=True)
+PY
+timeout 300 python /tmp/tg.py

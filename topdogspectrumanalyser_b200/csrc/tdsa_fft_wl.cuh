@@ -207,6 +207,9 @@ template <> __device__ __forceinline__ double widen_sample<double>(float x) {
 #ifndef TDSA_WL_WIN_TMEM
 #define TDSA_WL_WIN_TMEM 0
 #endif
+#ifndef TDSA_WL_WIN2_TMEM
+#define TDSA_WL_WIN2_TMEM 1
+#endif
 // TDSA_WL_TWB_SMEM_BASE (float64): pass-B twiddles W256^(j c) from a few base values of the shared table plus complex
 // multiplies instead of fifteen LDS.128 per thread and frame.  Measured (8192 frames, on top of the split barrier):
 // 0: 132.1 us; 1 (six bases, nine multiplies): 129.0 us; 2 (w^1 and w^4 only, thirteen multiplies): 128.0 us.  The same
@@ -248,7 +251,12 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
   // 2 * NB warps share a lane quarter, each with its own column range
   constexpr bool kWinTmem = TDSA_WL_WIN_TMEM && sizeof(T) == 8 && NB == 1 && TWMODE != 1;
   constexpr int kFusedWinCols = (ACC & kAccFused) ? 16 * (int)sizeof(T) / 4 : 0;     // fused head: its window values
-  constexpr int kTmemPerWarp = (ACC != 0 ? 64 : 0) + (kWinTmem ? 32 : 0) + kFusedWinCols;
+  // two engines, float64: the thread's 32 window values (both halves of the frame) live in tensor memory.  The permuted
+  // table is 128 KB for the CTA and does not stay in what is left of the L1 next to 212 KB of shared memory, so the
+  // per-frame re-read went to L2: `long_scoreboard` was the top stall of the config-4 kernel (2.25 cycles per issued
+  // instruction, r02_group8192_f64_before_tmem_window_ncu_full.txt; 266 -> 233 us for config 4's 300 x 16 frames).  64 columns per thread: with the accumulators all 512 columns of the SM.
+  constexpr bool kWin2Tmem = TDSA_WL_WIN2_TMEM && sizeof(T) == 8 && NB == 2 && TWMODE != 1 && ACC != 0;
+  constexpr int kTmemPerWarp = (ACC != 0 ? 64 : 0) + (kWinTmem ? 32 : 0) + kFusedWinCols + (kWin2Tmem ? 64 : 0);
   constexpr int kTmemNeed = kTmemPerWarp * 2 * NB;
   constexpr int kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
   constexpr bool kUseTmem = kTmemPerWarp != 0;
@@ -365,6 +373,20 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     tacc = *tmem_slot + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)((tid >> 7) * kTmemPerWarp);
     twin = tacc + (ACC != 0 ? 64 : 0);
+  }
+  if constexpr (kWin2Tmem) {                                 // columns [64, 128): win[0..31] as float64 pairs
+    const uint32_t tw2 = tacc + 64;
+#pragma unroll
+    for (int part = 0; part < 4; ++part) {
+      uint32_t u[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const double wv = (double)wperm[(8 * part + i) * TH + tid];
+        u[2 * i] = (uint32_t)__double2loint(wv); u[2 * i + 1] = (uint32_t)__double2hiint(wv);
+      }
+      tmem_st16(tw2 + 16 * part, u);
+    }
+    tmem_wait_st();
   }
   if constexpr (kWinTmem) {                                  // park the window values of pass A in tensor memory
     uint32_t u[16];
@@ -533,7 +555,7 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       uint32_t (&hi16)[16] = *reinterpret_cast<uint32_t (*)[16]>(&wraw[16]);
       tmem_ld16_nowait(twin, lo16);
       tmem_ld16_nowait(twin + 16, hi16);
-    } else if constexpr (TWMODE != 1 && !SUB) {              // window values for pass A, re-read every frame (register budget)
+    } else if constexpr (TWMODE != 1 && !SUB && !kWin2Tmem) {   // window values for pass A, re-read every frame (register budget)
 #pragma unroll
       for (int j = 0; j < NWIN; ++j) win[j] = wperm[j * TH + tid];
     }
@@ -607,12 +629,31 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
         // radix-2 DIF step on the staged read: s[n] = x[n] w[n] +- x[n + 4096] w[n + 4096] (the sign lives in the table)
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = *reinterpret_cast<const float2*>(src + 32768 + j * 2048);
+        if constexpr (kWin2Tmem) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          T hr = (T)v[j].x, hi = (T)v[j].y;
-          if constexpr (HAS_DC) { hr -= dcr; hi -= dci; }
-          re[j] = fm<T>(hr, win[16 + j], re[j] * win[j]);
-          im[j] = fm<T>(hi, win[16 + j], im[j] * win[j]);
+          for (int half = 0; half < 2; ++half) {               // eight samples of each frame half per step
+            uint32_t ulo[16], uhi[16];
+            tmem_ld16_nowait(tacc + 64 + 16 * half, ulo);
+            tmem_ld16_nowait(tacc + 64 + 32 + 16 * half, uhi);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = 8 * half + i;
+              const T wl = (T)__hiloint2double((int)ulo[2 * i + 1], (int)ulo[2 * i]);
+              const T wh = (T)__hiloint2double((int)uhi[2 * i + 1], (int)uhi[2 * i]);
+              const T hr = (T)v[j].x, hi = (T)v[j].y;
+              re[j] = fm<T>(hr, wh, re[j] * wl);
+              im[j] = fm<T>(hi, wh, im[j] * wl);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            T hr = (T)v[j].x, hi = (T)v[j].y;
+            if constexpr (HAS_DC) { hr -= dcr; hi -= dci; }
+            re[j] = fm<T>(hr, win[16 + j], re[j] * win[j]);
+            im[j] = fm<T>(hi, win[16 + j], im[j] * win[j]);
+          }
         }
         if (e == 0) {
           dft16<T>(re, im);

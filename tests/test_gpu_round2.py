@@ -132,7 +132,7 @@ def test_two_engine_8192_kernel(dev, parity_log, prec, tol):
         err = np.abs(got - want)
         parity_log(f"wl8192_{prec}_{window}", err.max(), tol=tol, over_1e4=int((err > 1e-4).sum()), bins=int(err.size))
         assert err.max() <= tol
-        # and the four-pass classic kernel that serves plain dB rows at this size agrees with it
+        # plain dB rows (float64: the same two-engine kernel with a row epilogue; float32: the four-pass classic kernel)
         classic = plan.psd_db(x).cpu().numpy().astype(np.float64)
         assert np.abs(classic - want).max() <= tol
         assert np.abs(classic - got).max() <= (2e-5 if prec == "f64" else tol)
@@ -150,6 +150,11 @@ def test_two_engine_8192_kernel(dev, parity_log, prec, tol):
     want = O.power_db_batch(np.ascontiguousarray(frames), O.make_window("hanning", n), O.MODE_MAG20)
     plan = SpectrumPlan(n, "hanning", mode="mag20", precision=prec, device=dev)
     got = plan.psd_db(torch.from_numpy(stream).to(dev), n_frames=37, frame_stride=1000).cpu().numpy()
+    assert np.abs(got - want).max() <= tol
+    # an odd stride cannot be described by the tensor map: the four-pass classic kernel serves these rows
+    frames = np.lib.stride_tricks.as_strided(stream, shape=(36, n), strides=(1001 * stream.itemsize, stream.itemsize))
+    want = O.power_db_batch(np.ascontiguousarray(frames), O.make_window("hanning", n), O.MODE_MAG20)
+    got = plan.psd_db(torch.from_numpy(stream).to(dev), n_frames=36, frame_stride=1001).cpu().numpy()
     assert np.abs(got - want).max() <= tol
     plan.close()
 

@@ -238,7 +238,7 @@ static bool wl_enabled() {
 // true when this batch can take a warp-local kernel (epilogue / accumulator combination instantiated, frames
 // describable by a tensor map); fills p->tmap: [frame][256 * nb rows][32 floats], 128-byte swizzle, box = 256 rows
 static bool wl_prepare(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t stride, int epi, int acc_flags, bool dc) {
-  if (!wl_enabled() || p->wl_nb == 0 || !p->d_wperm64 || !wl_supported(p->wl_nb, epi, acc_flags, dc)) return false;
+  if (!wl_enabled() || p->wl_nb == 0 || !p->d_wperm64 || !wl_supported(p->wl_nb, epi, acc_flags, dc, p->precision == TDSA_PREC_F64)) return false;
   if (((uintptr_t)iq & 15) != 0 || (stride & 1) != 0 || stride <= 0 || n_frames <= 0 || n_frames >= (1 << 30)) return false;
   if (p->tmap_ptr == iq && p->tmap_frames == n_frames && p->tmap_stride == stride) return true;
   EncodeTiledFn enc = encode_tiled_fn();
@@ -415,7 +415,7 @@ static int run_fused(tdsa_plan* p, const void* iq, int64_t n_frames, int64_t str
   if (p->win_dirty && !dry) { int rc = upload_window(p); if (rc) return rc; }
   if (is_big(p)) return run_big(p, iq, n_frames, stride, dc, epi, db, lin, info, dry);
   // dry runs (launch geometry queries) describe the warp-local kernel whenever the size has one
-  const bool wl = dry ? (wl_enabled() && p->wl_nb != 0 && p->d_wperm64 && wl_supported(p->wl_nb, epi, 0, dc != nullptr) && encode_tiled_fn())
+  const bool wl = dry ? (wl_enabled() && p->wl_nb != 0 && p->d_wperm64 && wl_supported(p->wl_nb, epi, 0, dc != nullptr, p->precision == TDSA_PREC_F64) && encode_tiled_fn())
                       : wl_prepare(p, iq, n_frames, stride, epi, 0, dc != nullptr);
   if (wl) return run_wl(p, iq, n_frames, stride, dc, epi, db, lin, 0, WlAcc(), info, dry);
   cudaError_t e;

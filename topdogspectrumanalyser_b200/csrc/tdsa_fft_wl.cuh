@@ -255,7 +255,8 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
   // table is 128 KB for the CTA and does not stay in what is left of the L1 next to 212 KB of shared memory, so the
   // per-frame re-read went to L2: `long_scoreboard` was the top stall of the config-4 kernel (2.25 cycles per issued
   // instruction, r02_group8192_f64_before_tmem_window_ncu_full.txt; 266 -> 233 us for config 4's 300 x 16 frames).  64 columns per thread: with the accumulators all 512 columns of the SM.
-  constexpr bool kWin2Tmem = TDSA_WL_WIN2_TMEM && sizeof(T) == 8 && NB == 2 && TWMODE != 1 && ACC != 0;
+  constexpr bool kWin2Tmem = TDSA_WL_WIN2_TMEM && sizeof(T) == 8 && NB == 2 && TWMODE != 1;
+  constexpr int kWin2Col = ACC != 0 ? 64 : 0;                 // behind the accumulators when there are any
   constexpr int kTmemPerWarp = (ACC != 0 ? 64 : 0) + (kWinTmem ? 32 : 0) + kFusedWinCols + (kWin2Tmem ? 64 : 0);
   constexpr int kTmemNeed = kTmemPerWarp * 2 * NB;
   constexpr int kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
@@ -375,7 +376,7 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     twin = tacc + (ACC != 0 ? 64 : 0);
   }
   if constexpr (kWin2Tmem) {                                 // columns [64, 128): win[0..31] as float64 pairs
-    const uint32_t tw2 = tacc + 64;
+    const uint32_t tw2 = tacc + kWin2Col;
 #pragma unroll
     for (int part = 0; part < 4; ++part) {
       uint32_t u[16];
@@ -633,8 +634,8 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
 #pragma unroll
           for (int half = 0; half < 2; ++half) {               // eight samples of each frame half per step
             uint32_t ulo[16], uhi[16];
-            tmem_ld16_nowait(tacc + 64 + 16 * half, ulo);
-            tmem_ld16_nowait(tacc + 64 + 32 + 16 * half, uhi);
+            tmem_ld16_nowait(tacc + kWin2Col + 16 * half, ulo);
+            tmem_ld16_nowait(tacc + kWin2Col + 32 + 16 * half, uhi);
             tmem_wait_ld();
 #pragma unroll
             for (int i = 0; i < 8; ++i) {

@@ -361,22 +361,26 @@ cudaError_t launch_wl_impl(int epi, const FftArgs<T>& a, const WlLaunch& L, cuda
       default: break;
     }
   } else if (L.nb == 2 && !dc) {
-    // Two engines (N = 8192): only the group-mean epilogue.  For plain dB rows the two-engine kernel measured no better
-    // than the four-pass classic kernel (f32 0.55 vs 0.58, f64 0.30 vs 0.31 of HBM: the engines share one stage and
-    // run in lock step), so those stay on fft_fused_kernel; frames_per_group = 1 gives its dB rows when wanted.
+    // Two engines (N = 8192): the group-mean epilogue in both precisions, and plain dB rows in float64.  Plain rows,
+    // round 2: at first no better than the four-pass classic kernel (f64 207 vs 199 us, f32 115 vs 105 us: the engines
+    // share one stage and run in lock step); with the float64 window values in tensor memory 188 us through the
+    // group epilogue with one frame per group, so float64 rows take this kernel and float32 rows stay on the classic one.
     if (L.acc_flags == kAccGroupMean) TDSA_WL_GO(EpiDb, false, 2, kAccGroupMean);
+    if constexpr (sizeof(T) == 8) {
+      if (L.acc_flags == 0 && epi == kEpiDb) TDSA_WL_GO(EpiDb, false, 2, 0);
+    }
   }
 #undef TDSA_WL_GO
   return cudaErrorInvalidValue;
 }
 // true when launch_wl_impl has an instantiation for this combination
-inline bool wl_supported(int nb, int epi, int acc_flags, bool dc) {
+inline bool wl_supported(int nb, int epi, int acc_flags, bool dc, bool f64 = false) {
   if (nb == 1) {
     if (acc_flags == 0) return epi == kEpiDb || epi == kEpiLinear;
     return !dc && (acc_flags == kAccAvg || acc_flags == kAccHold || acc_flags == kAccWelch || acc_flags == kAccGroupMean ||
                    acc_flags == kAccWelchSub || acc_flags == kAccWelchFused);
   }
-  if (nb == 2 && !dc) return acc_flags == kAccGroupMean;
+  if (nb == 2 && !dc) return acc_flags == kAccGroupMean || (f64 && acc_flags == 0 && epi == kEpiDb);
   return false;
 }
 cudaError_t launch_wl_f32(int epi, const FftArgs<float>& a, const WlLaunch& L, cudaStream_t s, LaunchInfo* info, bool dry);

@@ -998,6 +998,7 @@ int tdsa_welch(tdsa_handle_t p, const void* iq_stream, int64_t n_samples, int64_
       acc.fused_tw = f32 ? (const void*)p->d_twh32 : (const void*)p->d_twh64;
       acc.fused_y = p->scratch2; acc.fused_cnt = p->d_sched + 18;
       L.acc = acc;
+      CK(cudaMemsetAsync(p->d_sched + 18 + 2 * groups, 0, sizeof(int), p->stream));   // the error word of an earlier call
       if (f32) {
         FftArgs<float> t{};
         t.n_frames = nseg * 16; t.window = p->d_win32; t.tw = p->d_twin32; t.ep = make_epi(p, nullptr, nullptr);

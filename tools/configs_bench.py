@@ -48,6 +48,12 @@ for prec in ("f64", "f32"):
     st = WaterfallStreamer(4096, 65536, 1024, "exp", 8, precision=prec, device=dev)
     st.run(lambda c: chunks[c % 64], 64)
     stats = st.run(lambda c: chunks[c % 64], 3052)
+    # the same 10 s of signal with the producer writing into the pinned slot in place (acquire / commit: what a device
+    # reader thread does), i.e. without the 512 KB host copy of push_chunk
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for c in range(3052):
+        st.acquire(); st.commit()
+    torch.cuda.synchronize(); inplace_s = time.perf_counter() - t0
     # per-chunk latency: push one chunk and wait until its rows are visible in the ring
     torch.cuda.synchronize(); lat = []
     for c in range(50):
@@ -73,5 +79,6 @@ for prec in ("f64", "f32"):
     print(json.dumps({"config": "cfg5 streaming waterfall 20 Msps x 10 s, 65536-sample pinned chunks", "precision": prec,
                       "seconds_for_10s_of_signal": stats["seconds"], "real_time_factor": stats["real_time_factor"],
                       "samples_per_s": stats["samples_per_s"], "chunk_latency_ms_median": float(np.median(lat)) * 1e3,
+                      "in_place_producer": {"seconds_for_10s_of_signal": inplace_s, "real_time_factor": 3052 * 65536 / inplace_s / 20e6},
                       "graphs": st.use_graphs, "h2d_under_previous_compute_frac": ov / h2d if h2d else None,
                       "timeline_first_chunks": tl[:4]}))

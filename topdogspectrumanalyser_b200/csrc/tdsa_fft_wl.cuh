@@ -207,6 +207,12 @@ template <> __device__ __forceinline__ double widen_sample<double>(float x) {
 #ifndef TDSA_WL_WIN_TMEM
 #define TDSA_WL_WIN_TMEM 0
 #endif
+// TDSA_WL_WIN_RELOAD = 1 (float64, one engine): force the per-frame re-read of the sixteen window values.  The source asks
+// for it, but ptxas hoists the loop-invariant loads and keeps the values in 32 registers (ncu: 54 k global load requests
+// per launch instead of one million).  Measured: 127.9 -> 135.2 us with the forced re-read, so the hoisted form stays.
+#ifndef TDSA_WL_WIN_RELOAD
+#define TDSA_WL_WIN_RELOAD 0
+#endif
 #ifndef TDSA_WL_WIN2_TMEM
 #define TDSA_WL_WIN2_TMEM 1
 #endif
@@ -558,7 +564,16 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       tmem_ld16_nowait(twin + 16, hi16);
     } else if constexpr (TWMODE != 1 && !SUB && !kWin2Tmem) {   // window values for pass A, re-read every frame (register budget)
 #pragma unroll
-      for (int j = 0; j < NWIN; ++j) win[j] = wperm[j * TH + tid];
+      for (int j = 0; j < NWIN; ++j) {
+#if TDSA_WL_WIN_RELOAD
+        if constexpr (sizeof(T) == 8 && NB == 1) {           // volatile: really re-read per frame (ptxas otherwise hoists 32 registers)
+          double wv;
+          asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(wv) : "l"(wperm + j * TH + tid));
+          win[j] = (T)wv;
+        } else
+#endif
+        win[j] = wperm[j * TH + tid];
+      }
     }
     int fnext = 0;
     bool refilled = false;

@@ -87,7 +87,7 @@ def test_fused_holds_without_averaging(dev, parity_log, last_only):
 @pytest.mark.parametrize("mode,navg", [("exp", 16), ("lin", 700), ("lin", 5000)])
 def test_general_scan_in_l2_sized_chunks(dev, parity_log, mode, navg):
     """Averaging AND holds AND every row out: the frame-ordered scan (parallel over 32-frame blocks through the affine
-    form of the recurrence), run over more frames than one 32 MB chunk of float64 rows holds (1024 frames at N = 4096),
+    form of the recurrence), run over more frames than one 64 MB chunk of float64 rows holds (2048 frames at N = 4096),
     so the state is carried across block and chunk boundaries; 'lin' capped inside the run and never capped."""
     import torch
     from topdogspectrumanalyser_b200.engine import SpectrumPlan, TraceState

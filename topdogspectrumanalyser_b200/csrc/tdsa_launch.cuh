@@ -63,9 +63,17 @@ constexpr int kMinLog2R8 = 9, kMaxLog2R8 = 13;
 #define TDSA_DEFAULT_LOGR_F64 4
 #endif
 
+#ifndef TDSA_SMALL_CTAS_F64
+#define TDSA_SMALL_CTAS_F64 6
+#endif
 template <typename T, int LOG2N, int LOGR> constexpr int target_ctas() {
   constexpr int th = Plan<T, LOG2N, LOGR>::THREADS;
   if (LOGR == 3) return th >= 1024 ? 1 : (1024 / th > 8 ? 8 : 1024 / th);      // 64 registers per thread
+  // float64, N <= 2048 (CTAs of 32 .. 128 threads): ask for 12 warps per SM.  With the old bound of two CTAs the kernel took
+  // 170 registers and ran 4 CTAs of 64 threads per SM at N = 1024; 6 CTAs (156 registers, one staging buffer) measured
+  // 127.2 -> 115.3 us at N = 1024, 123.9 -> 115.8 us at N = 512, 133.9 -> 123.7 us at N = 2048 (round 2); 5 or 7 per SM are
+  // both slower (130 us: 7 needs 128 registers and spills).
+  if (sizeof(T) == 8 && th <= 128 && th >= 32) return TDSA_SMALL_CTAS_F64 * 64 / th;
   return (th >= 512) ? 1 : ((sizeof(T) == 4 && th == 256) ? TDSA_F32_CTAS : 2);
 }
 

@@ -252,6 +252,9 @@ template <typename T> int effective_logr(int log2n) {
 #ifndef TDSA_WL_TWB_BASE_F32    // float32: pass-B twiddles from six base values in registers instead of 15 LDS.64 per frame
 #define TDSA_WL_TWB_BASE_F32 1   // measured: 80.7 -> 78.8 us
 #endif
+#ifndef TDSA_WL_CTAS_F32          // CTAs per SM the float32 one-engine kernel (plain rows) is built for
+#define TDSA_WL_CTAS_F32 2
+#endif
 #ifndef TDSA_WL_STAGES_F64
 #define TDSA_WL_STAGES_F64 1
 #endif
@@ -271,7 +274,7 @@ cudaError_t launch_wl_final(const FftArgs<T>& a, const CUtensorMap& tmap, const 
   constexpr int kStages = (NB == 2 && sizeof(T) == 8) ? 1 : (sizeof(T) == 4 ? TDSA_WL_STAGES_F32 : TDSA_WL_STAGES_F64);
   constexpr int kTwMode = sizeof(T) == 4 ? TDSA_F32_TWMODE : TDSA_F64_TWMODE;
   constexpr int kThreads = 256 * NB;
-  constexpr int kMinCtas = NB == 1 ? 2 : 1;
+  constexpr int kMinCtas = NB == 1 ? ((sizeof(T) == 4 && ACC == 0) ? TDSA_WL_CTAS_F32 : 2) : 1;
   static const size_t kExtraSmem = [] { const char* e = getenv("TDSA_DEBUG_EXTRA_SMEM"); return e ? (size_t)atol(e) : (size_t)0; }();
   constexpr bool kSub = (ACC & kAccSub) != 0;                  // direct loads: no staging buffers
   constexpr bool kFused = (ACC & kAccFused) != 0;              // + the head pass' sample staging [16][272] float2

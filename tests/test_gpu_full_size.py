@@ -106,6 +106,34 @@ def test_welch_65536_few_segments(dev, nseg, hop, fused, monkeypatch):
     plan.close()
 
 
+def test_welch_65536_more_segments_than_one_pass(dev, parity_log):
+    """2053 heavily overlapping segments (hop 1024): the head + tail pair runs twice (2048 segments per pass of the
+    intermediate buffer), the second pass with five segments on a smaller grid whose unused partial rows must read as
+    empty; the fused variant takes all of them in one launch."""
+    import torch
+    from topdogspectrumanalyser_b200.engine import SpectrumPlan
+    n, hop, nseg = 65536, 1024, 2053
+    stream = synth.cfg3_stream(n_samples=n + hop * (nseg - 1), seed=91)
+    want_avg, want_peak, got = _welch_oracle(stream, n, hop)
+    assert got == nseg
+    x = torch.from_numpy(stream).to(dev)
+    old = os.environ.get("TDSA_WELCH_FUSED")
+    try:
+        for fused in ("0", "1"):
+            os.environ["TDSA_WELCH_FUSED"] = fused
+            plan = SpectrumPlan(n, device=dev)
+            avg, peak = plan.welch(x, hop)
+            ea = float(np.abs(avg.cpu().numpy() - want_avg).max()); ep = float(np.abs(peak.cpu().numpy() - want_peak).max())
+            parity_log(f"welch65536_2053_segments_fused{fused}", max(ea, ep), tol=TOL_DB)
+            assert ea <= TOL_DB and ep <= TOL_DB, (fused, ea, ep)
+            plan.close()
+    finally:
+        if old is None:
+            os.environ.pop("TDSA_WELCH_FUSED", None)
+        else:
+            os.environ["TDSA_WELCH_FUSED"] = old
+
+
 @pytest.mark.parametrize("fused", ["0", "1"])
 def test_welch_65536_psd_blackman(dev, fused, monkeypatch, parity_log):
     """PSD scaling (1 / (fs N)) and a different window through the config-3 path; second plan in float32 at 1e-3 dB."""

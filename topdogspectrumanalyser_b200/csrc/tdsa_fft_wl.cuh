@@ -238,6 +238,11 @@ template <> __device__ __forceinline__ double widen_sample<double>(float x) {
 #ifndef TDSA_WL_SPLIT_B2
 #define TDSA_WL_SPLIT_B2 1
 #endif
+// The same split barrier per engine of the two-engine kernel: measured slower in float64 (group mean 236 -> 273 us, rows
+// 182 -> 234 us; float32 160 -> 154 us), so off: with one CTA per SM the rendezvous keeps the two engines' phases apart.
+#ifndef TDSA_WL_SPLIT_B2_NB2
+#define TDSA_WL_SPLIT_B2_NB2 0
+#endif
 // TDSA_WL_SPLIT_ALL = 1: every thread arrives on the regions-free barrier; 0: lane 0 of each warp after a __syncwarp.  Same
 // speed (round 2: 128.9 / 77.8 us against 129.0 / 78.4 us), but compute-sanitizer's racecheck credits an mbarrier arrival to
 // the arriving thread only and reported the other lanes' last-pass reads against the next frame's team stores as WAR hazards
@@ -288,6 +293,7 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
   CT* reg = ex + r * REGION;
   const CT* twe = a.tw + e * kWlTwPerEngine;                // this engine's tables
 
+  constexpr bool kSplitB2 = TDSA_WL_SPLIT_B2 && NSTAGE <= 2 && (NB == 1 || TDSA_WL_SPLIT_B2_NB2);
   constexpr bool SUB = (ACC & kAccSub) != 0;
   constexpr bool FUSED = (ACC & kAccFused) != 0;
   static_assert(!SUB || (NB == 1 && !HAS_DC && (ACC & (kAccGroup | kAccRows)) == 0), "sub-transform tail: one engine, accumulate only");
@@ -298,7 +304,10 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
       mbar_init(ctrl_u32 + 8 * s, 1);
       if constexpr (NB > 1 || TDSA_WL_EARLY) mbar_init(ctrl_u32 + 32 + 8 * s, 8 * NB);     // one arrival per warp
     }
-    if constexpr (TDSA_WL_SPLIT_B2 && NB == 1) mbar_init(ctrl_u32 + 24, TDSA_WL_SPLIT_ALL ? 256 : 8);     // "regions free": one arrival per warp
+    if constexpr (kSplitB2) {                                 // "regions free", one per engine (the slots of stages 2 and 3)
+#pragma unroll
+      for (int en = 0; en < NB; ++en) mbar_init(ctrl_u32 + 16 + 8 * en, TDSA_WL_SPLIT_ALL ? 256 : 8);
+    }
     fence_mbar_init();
   }
   for (int i = te; i < W::TW_SMEM; i += 256) tws[i] = twe[i];
@@ -692,8 +701,8 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
     }
     TDSA_STAMP(2);
     // ---- team-local 16x16 transpose: A_c[ka] at position c + 16 ka, row pitch 17 ---------------------------
-    if constexpr (TDSA_WL_SPLIT_B2 && NB == 1) {
-      if (it > 0) mbar_wait(ctrl_u32 + 24, (uint32_t)((it - 1) & 1));        // every warp has read the previous frame's Y
+    if constexpr (kSplitB2) {
+      if (it > 0) mbar_wait(ctrl_u32 + 16 + 8 * e, (uint32_t)((it - 1) & 1));   // every warp of the engine has read the previous frame's Y
     }
 #pragma unroll
     for (int q = 0; q < 16; ++q) reg[c + 17 * q] = mk<T>(re[q], im[q]);
@@ -775,12 +784,12 @@ fft_wl_kernel(const FftArgs<T> a, const __grid_constant__ CUtensorMap tmap, cons
 #pragma unroll
       for (int j = 0; j < 16; ++j) { const CT x = col[j * REGION]; re[j] = x.x; im[j] = x.y; }
     }
-    if constexpr (TDSA_WL_SPLIT_B2 && NB == 1) {
+    if constexpr (kSplitB2) {
 #if TDSA_WL_SPLIT_ALL
-      mbar_arrive(ctrl_u32 + 24);
+      mbar_arrive(ctrl_u32 + 16 + 8 * e);
 #else
       __syncwarp();                                          // the warp's loads are ordered before its one arrival
-      if (l == 0) mbar_arrive(ctrl_u32 + 24);
+      if (l == 0) mbar_arrive(ctrl_u32 + 16 + 8 * e);
 #endif
     } else {
       engine_sync();                                         // regions may be overwritten by the next frame's pass A

@@ -622,7 +622,7 @@ def main():
     other_sizes = None
     if not args.no_other_sizes:
         other_sizes = {}
-        for n_fft in (1024, 8192):
+        for n_fft in (1024, 2048, 8192):
             other_sizes[str(n_fft)] = {pr: measure_size(n_fft, BATCH * N_FFT // n_fft, pr) for pr in ("f64", "f32")}
     cfg4 = None
     if not args.no_cfg4:
